@@ -1,0 +1,126 @@
+"""The reference's filter semantics (plane selection, per-plane parameters, frame props) on top
+of the per-plane CPU oracle.  Test infrastructure: mirrors what getFrame does in
+src/vapoursynth/{boxblur,bilateral,planeminmax,planeaverage}.zig so parity tests can run the
+same call against the oracle and against the CUDA product.
+
+A clip is {"format": name, "planes": [np.ndarray, ...]} (see oracle/fixtures.py).
+"""
+import numpy as np
+
+import oracle
+from oracle.fixtures import FORMATS
+
+
+def _fmt(clip):
+    return FORMATS[clip["format"]]
+
+
+def _plane_mask(clip, planes, default_all=True):
+    n = len(clip["planes"])
+    if planes is None:
+        return [True] * n if default_all else [i == 0 for i in range(n)]
+    return [i in planes for i in range(n)]
+
+
+def boxblur(clip, planes=None, hradius=1, hpasses=1, vradius=1, vpasses=1):
+    mask = _plane_mask(clip, planes)
+    out = [oracle.boxblur_plane(p, hradius, hpasses, vradius, vpasses) if m else p.copy()
+           for p, m in zip(clip["planes"], mask)]
+    return {"format": clip["format"], "planes": out}
+
+
+def _listify(v):
+    if v is None:
+        return []
+    return list(v) if isinstance(v, (list, tuple)) else [v]
+
+
+def bilateral(clip, ref=None, sigmaS=None, sigmaR=None, planes=None, algorithm=None, PBFICnum=None):
+    fam, st, bits, ssw, ssh = _fmt(clip)
+    rc, prm = oracle.bilateral_derive(fam == "YUV", st == "f", bits, ssw, ssh, len(clip["planes"]),
+                                      _listify(sigmaS), _listify(sigmaR), planes, _listify(algorithm), _listify(PBFICnum))
+    assert rc == 0, f"oracle bilateral_derive rc={rc}"
+    out = []
+    for i, p in enumerate(clip["planes"]):
+        if not prm.process[i]:
+            out.append(p.copy())
+            continue
+        assert prm.algorithm[i] == 2, "oracle restates algorithm 2 only"
+        r = None if ref is None else ref["planes"][i]
+        out.append(oracle.bilateral_plane(p, prm.sigmaS[i], prm.sigmaR[i], prm.radius[i], prm.step[i], prm.hist_len, r))
+    return {"format": clip["format"], "planes": out}
+
+
+def _props(values_per_plane, keys, prop):
+    """Append semantics of the reference: scalar for one processed plane, list for several."""
+    res = {}
+    for k in keys:
+        vals = [v[k] for v in values_per_plane if k in v]
+        if vals:
+            res[prop + k] = vals[0] if len(vals) == 1 else vals
+    return res
+
+
+def planeminmax(clip, minthr=0.0, maxthr=0.0, clipb=None, planes=None, prop="psm"):
+    fam, st, bits, ssw, ssh = _fmt(clip)
+    mask = _plane_mask(clip, planes, default_all=False)
+    vals = []
+    for i, (p, m) in enumerate(zip(clip["planes"], mask)):
+        if m:
+            vals.append(oracle.planeminmax_plane(p, bits, minthr, maxthr, None if clipb is None else clipb["planes"][i]))
+    return _props(vals, ("Min", "Max", "Diff"), prop)
+
+
+def planeaverage(clip, exclude, clipb=None, planes=None, prop="psm"):
+    fam, st, bits, ssw, ssh = _fmt(clip)
+    mask = _plane_mask(clip, planes, default_all=False)
+    vals = []
+    for i, (p, m) in enumerate(zip(clip["planes"], mask)):
+        if m:
+            vals.append(oracle.planeaverage_plane(p, bits, exclude, None if clipb is None else clipb["planes"][i]))
+    return _props(vals, ("Avg", "Diff"), prop)
+
+
+def golden_stats(clip):
+    """tests/golden.py:106-121 of the reference: per-plane {avg,min,max} via std.PlaneStats."""
+    fam, st, bits, ssw, ssh = _fmt(clip)
+    return {f"p{i}": oracle.plane_stats(p, bits) for i, p in enumerate(clip["planes"])}
+
+
+def parse_case_id(key: str):
+    """Inverse of the reference's Case.id (tests/golden.py:40-56): 'FMT|geometry|k=v,...[|variant]'."""
+    parts = key.split("|")
+    fmt, geometry, argstr = parts[0], parts[1], parts[2]
+    variant = parts[3] if len(parts) > 3 else ""
+    args = {}
+    if argstr != "default":
+        # split on commas that are not inside [...]
+        items, depth, cur = [], 0, ""
+        for ch in argstr:
+            if ch == "[":
+                depth += 1
+            elif ch == "]":
+                depth -= 1
+            if ch == "," and depth == 0:
+                items.append(cur)
+                cur = ""
+            else:
+                cur += ch
+        items.append(cur)
+        for it in items:
+            k, v = it.split("=", 1)
+            if v.startswith("["):
+                args[k] = [_num(x) for x in v[1:-1].split(",") if x]
+            else:
+                args[k] = _num(v)
+    return fmt, geometry, args, variant
+
+
+def _num(s):
+    try:
+        return int(s)
+    except ValueError:
+        try:
+            return float(s)
+        except ValueError:
+            return s

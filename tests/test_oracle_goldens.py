@@ -1,0 +1,94 @@
+"""Pins the CPU oracle to the reference's own golden vectors.
+
+tests/golden/*.json are verbatim copies of /root/reference/tests/goldens/*.json (values recorded
+from the real Zig plugin under VapourSynth).  Each case rebuilds the reference's fixture clip
+(oracle/fixtures.py), runs the oracle and compares with the recorded snapshot - tighter than the
+reference's own rel=1e-6 (tests/golden.py:187-191): averages to 1e-12 relative, min/max exact.
+
+Keys that need VapourSynth's std.BoxBlur (a different plugin) for their second clip, and the
+algorithm=1 (PBFIC) keys, are not reproducible here and are listed as skipped.
+"""
+import json
+from pathlib import Path
+
+import pytest
+
+import oracle_api as oa
+from oracle import fixtures as fx
+
+GOLD = Path(__file__).resolve().parent / "golden"
+
+
+def _load(name):
+    return json.loads((GOLD / f"{name}.json").read_text())
+
+
+def _close(a, e, rel):
+    return abs(a - e) <= rel * max(abs(e), 1e-300) or abs(a - e) <= 1e-15
+
+
+def _assert_stats(actual, expected, rel=1e-12):
+    assert set(actual) == set(expected)
+    for p in expected:
+        assert actual[p]["min"] == expected[p]["min"], (p, actual[p], expected[p])
+        assert actual[p]["max"] == expected[p]["max"], (p, actual[p], expected[p])
+        assert _close(actual[p]["avg"], expected[p]["avg"], rel), (p, actual[p], expected[p])
+
+
+def _assert_props(actual, expected, rel=1e-12):
+    assert set(actual) == set(expected), (actual, expected)
+    for k, e in expected.items():
+        a = actual[k]
+        if isinstance(e, list):
+            assert isinstance(a, list) and len(a) == len(e), (k, a, e)
+            for x, y in zip(a, e):
+                assert _close(x, y, rel), (k, a, e)
+        else:
+            assert _close(a, e, rel), (k, a, e)
+
+
+# --------------------------------------------------------------------------- BoxBlur
+@pytest.mark.parametrize("key", sorted(_load("boxblur")))
+def test_boxblur_golden(key):
+    fmt, geo, args, variant = oa.parse_case_id(key)
+    out = oa.boxblur(fx.make_clip(fmt, geo), **args)
+    _assert_stats(oa.golden_stats(out), _load("boxblur")[key])
+
+
+# --------------------------------------------------------------------------- Bilateral
+@pytest.mark.parametrize("key", sorted(_load("bilateral")))
+def test_bilateral_golden(key):
+    fmt, geo, args, variant = oa.parse_case_id(key)
+    if variant == "ref":
+        pytest.skip("joint clip is built with VapourSynth's std.BoxBlur (not part of vszip)")
+    if args.get("algorithm") == 1:
+        pytest.skip("algorithm 1 (PBFIC) is outside the restated hot path (SURVEY 8f rank 2)")
+    out = oa.bilateral(fx.make_clip(fmt, geo), **args)
+    _assert_stats(oa.golden_stats(out), _load("bilateral")[key])
+
+
+# --------------------------------------------------------------------------- PlaneMinMax
+@pytest.mark.parametrize("key", sorted(_load("planeminmax")))
+def test_planeminmax_golden(key):
+    fmt, geo, args, variant = oa.parse_case_id(key)
+    clip = fx.make_clip(fmt, geo)
+    use_clipb = bool(args.pop("variant_clipb", 0)) or variant == "ref"
+    if use_clipb:  # tests/test_planeminmax.py:71-72 of the reference: clipb = src.vszip.BoxBlur(1, 1)
+        args["clipb"] = oa.boxblur(clip, hradius=1, vradius=1)
+    prop = args.get("prop", "psm")
+    got = oa.planeminmax(clip, **args)
+    got = {k[len(prop):]: v for k, v in got.items()}
+    _assert_props(got, _load("planeminmax")[key])
+
+
+# --------------------------------------------------------------------------- PlaneAverage
+@pytest.mark.parametrize("key", sorted(_load("planeaverage")))
+def test_planeaverage_golden(key):
+    fmt, geo, args, variant = oa.parse_case_id(key)
+    if variant.startswith("ref"):
+        pytest.skip("clipb is built with VapourSynth's std.BoxBlur (not part of vszip)")
+    clip = fx.make_clip(fmt, geo)
+    prop = args.get("prop", "psm")
+    got = oa.planeaverage(clip, **args)
+    got = {"avg": got[prop + "Avg"]}
+    _assert_props(got, _load("planeaverage")[key])
