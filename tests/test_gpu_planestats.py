@@ -1,0 +1,165 @@
+"""PlaneMinMax / PlaneAverage parity on the GPU against the CPU oracle and the reference's goldens.
+Integer results (min, max, integer average numerators) are exact; float averages and diffs are
+f64 tree sums compared at 1e-12 relative (the reference sums sequentially in f64)."""
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import oracle_api as oa
+import vapoursynth_zip_b200 as vz
+from helpers import noise_clip, to_node
+from oracle import fixtures as fx
+
+pytestmark = pytest.mark.gpu
+GOLD_MM = json.loads((Path(__file__).resolve().parent / "golden" / "planeminmax.json").read_text())
+GOLD_AV = json.loads((Path(__file__).resolve().parent / "golden" / "planeaverage.json").read_text())
+
+
+def props_close(got, want, rel=1e-12):
+    assert set(got) == set(want), (got, want)
+    for k, w in want.items():
+        g = got[k]
+        gl, wl = (g, w) if isinstance(w, list) else ([g], [w])
+        assert len(gl) == len(wl), (k, g, w)
+        for a, b in zip(gl, wl):
+            if isinstance(b, int):
+                assert a == b, (k, g, w)
+            else:
+                assert a == pytest.approx(b, rel=rel, abs=1e-300), (k, g, w)
+
+
+def mm(clip, clipb=None, **args):
+    node = to_node(clip).vszip.PlaneMinMax(clipb=to_node(clipb) if clipb is not None else None, **args)
+    return node.get_frame(0).props
+
+
+def av(clip, clipb=None, **args):
+    node = to_node(clip).vszip.PlaneAverage(clipb=to_node(clipb) if clipb is not None else None, **args)
+    return node.get_frame(0).props
+
+
+@pytest.mark.parametrize("key", sorted(GOLD_MM))
+def test_planeminmax_golden(key):
+    fmt, geo, args, variant = oa.parse_case_id(key)
+    clip = fx.make_clip(fmt, geo)
+    clipb = None
+    if bool(args.pop("variant_clipb", 0)) or variant == "ref":
+        clipb = oa.boxblur(clip, hradius=1, vradius=1)
+    got = mm(clip, clipb, **args)
+    want = oa.planeminmax(clip, clipb=clipb, **args)
+    props_close(got, want)
+    prop = args.get("prop", "psm")
+    golden = {prop + k: v for k, v in GOLD_MM[key].items()}
+    props_close(got, golden, rel=1e-9)
+
+
+@pytest.mark.parametrize("key", sorted(k for k in GOLD_AV if "|ref" not in k))
+def test_planeaverage_golden(key):
+    fmt, geo, args, variant = oa.parse_case_id(key)
+    clip = fx.make_clip(fmt, geo)
+    got = av(clip, **args)
+    props_close(got, oa.planeaverage(clip, **args))
+    prop = args.get("prop", "psm")
+    props_close({prop + "Avg": got[prop + "Avg"]}, {prop + "Avg": GOLD_AV[key]["avg"]}, rel=1e-9)
+
+
+@pytest.mark.parametrize("fmt", ["GRAY8", "GRAY10", "GRAY16", "GRAYH", "GRAYS", "YUV420P16", "RGBS"])
+def test_noise_planeminmax(fmt):
+    base = "GRAY16" if fmt == "GRAY10" else fmt
+    clip = noise_clip(base, 517, 243, seed=9)
+    if fmt == "GRAY10":
+        clip = {"format": "GRAY10", "planes": [clip["planes"][0] >> 6]}
+    other = noise_clip(base, 517, 243, seed=10)
+    if fmt == "GRAY10":
+        other = {"format": "GRAY10", "planes": [other["planes"][0] >> 6]}
+    planes = list(range(len(clip["planes"])))
+    for thr in ((0, 0), (0.1, 0.1), (0.4, 0.0), (0.0, 0.33), (0.5, 0.5), (1.0, 1.0), (0.999, 0.001)):
+        for b in (None, other):
+            args = dict(minthr=thr[0], maxthr=thr[1], planes=planes)
+            props_close(mm(clip, b, **args), oa.planeminmax(clip, clipb=b, **args))
+
+
+@pytest.mark.parametrize("fmt", ["GRAY8", "GRAY16", "GRAYH", "GRAYS", "YUV420P8", "YUV444PS"])
+def test_noise_planeaverage(fmt):
+    clip = noise_clip(fmt, 517, 243, seed=19)
+    other = noise_clip(fmt, 517, 243, seed=20)
+    planes = list(range(len(clip["planes"])))
+    for ex in ([-1], [0], [128], [100, 150, 200], [0, 1]):
+        for b in (None, other):
+            props_close(av(clip, b, exclude=ex, planes=planes), oa.planeaverage(clip, ex, clipb=b, planes=planes))
+
+
+def test_threshold_drop_semantics():
+    """tests/test_planeminmax.py:99-110 of the reference."""
+    z = np.zeros((8, 64), np.uint8)
+    r = np.full((24, 64), 200, np.uint8)
+    src = vz.core.clip_from_frames("GRAY8", [[np.vstack([z, r])]])
+    assert src.vszip.PlaneMinMax(minthr=0.2).get_frame(0).props["psmMin"] == 0
+    assert src.vszip.PlaneMinMax(minthr=0.3).get_frame(0).props["psmMin"] == 200
+    src2 = vz.core.clip_from_frames("GRAY8", [[np.vstack([np.full((24, 64), 100, np.uint8), np.full((8, 64), 255, np.uint8)])]])
+    assert src2.vszip.PlaneMinMax(maxthr=0.2).get_frame(0).props["psmMax"] == 255
+    assert src2.vszip.PlaneMinMax(maxthr=0.3).get_frame(0).props["psmMax"] == 100
+
+
+def test_blank_clips_and_prop_rename():
+    """tests/test_planeminmax.py:147-160, :227-236 and tests/test_planeaverage.py:138-147 of the reference."""
+    src = vz.core.BlankClip("YUV420P16", 64, 32, color=[6777, 32768, 0])
+    out = src.vszip.PlaneMinMax(minthr=0.2, maxthr=0.3)
+    out = out.vszip.PlaneMinMax(minthr=0.2, maxthr=0.3, prop="mm_test")
+    p = out.get_frame(0).props
+    assert p["psmMin"] == p["mm_testMin"] == 6777 and p["psmMax"] == p["mm_testMax"] == 6777
+    h = vz.core.BlankClip("GRAYH", 64, 32, color=0.5).vszip.PlaneMinMax().get_frame(0).props
+    assert h["psmMin"] == 0.5 and h["psmMax"] == 0.5
+    g = vz.core.BlankClip("GRAY16", 64, 64, color=30000)
+    assert g.vszip.PlaneMinMax(minthr=1.0).get_frame(0).props["psmMin"] == 65535
+    assert g.vszip.PlaneMinMax(maxthr=1.0).get_frame(0).props["psmMax"] == 0
+    a = src.vszip.PlaneAverage(exclude=[300, 5000])
+    a = a.vszip.PlaneAverage(exclude=[300, 5000], prop="avg_test")
+    p = a.get_frame(0).props
+    assert p["psmAvg"] == 0.10341039139391164 and p["avg_testAvg"] == p["psmAvg"]
+    multi = src.vszip.PlaneAverage(exclude=[-1], planes=[0, 1, 2]).get_frame(0).props["psmAvg"]
+    assert multi == [6777 / 65535, 32768 / 65535, 0.0]
+
+
+def test_exclude_exact():
+    """tests/test_planeaverage.py:118-128 of the reference."""
+    two = np.vstack([np.full((32, 64), 1000, np.uint16), np.full((32, 64), 3000, np.uint16)])
+    src = vz.core.clip_from_frames("GRAY16", [[two]])
+    assert src.vszip.PlaneAverage(exclude=[1000]).get_frame(0).props["psmAvg"] == 3000 / 65535
+    assert src.vszip.PlaneAverage(exclude=[3000]).get_frame(0).props["psmAvg"] == 1000 / 65535
+    assert src.vszip.PlaneAverage(exclude=[1000, 3000]).get_frame(0).props["psmAvg"] == 0.0
+    twof = np.vstack([np.full((32, 64), 3.0, np.float32), np.full((32, 64), 1.0, np.float32)])
+    assert vz.core.clip_from_frames("GRAYS", [[twof]]).vszip.PlaneAverage(exclude=[3]).get_frame(0).props["psmAvg"] == 1.0
+
+
+@pytest.mark.parametrize("fmt", ["GRAY16", "GRAYS"])
+def test_full_size_config4(fmt):
+    """BASELINE config 4: 3840x2160 GRAY16 / GRAYS, PlaneMinMax(minthr, maxthr) + PlaneAverage(exclude)."""
+    clip = noise_clip(fmt, 3840, 2160, seed=31)
+    args = dict(minthr=0.1, maxthr=0.1)
+    props_close(mm(clip, **args), oa.planeminmax(clip, **args))
+    ex = [0, 32768] if fmt == "GRAY16" else [0, 1]
+    props_close(av(clip, exclude=ex), oa.planeaverage(clip, ex))
+    # a constant plane: every sample in one bin (the reference README's BlankClip case)
+    const = vz.core.BlankClip(fmt, 3840, 2160, color=0.25 if fmt == "GRAYS" else 12345)
+    p = const.vszip.PlaneMinMax(**args).get_frame(0).props
+    want = oa.planeminmax({"format": fmt, "planes": const.get_frame(0).planes}, **args)
+    props_close(p, want)
+
+
+def test_device_batch():
+    fmt, w, h, n = "GRAY16", 640, 360, 4
+    a, b = vz.DeviceClip(fmt, w, h, n), vz.DeviceClip(fmt, w, h, n)
+    a.fill_noise(seed=1)
+    b.fill_noise(seed=2)
+    mmf = vz.PlaneMinMaxFilter(a.info(), b.info(), minthr=0.1, maxthr=0.2)
+    avf = vz.PlaneAverageFilter(a.info(), b.info(), exclude=[7, 9])
+    got_mm = mmf.run_device(a, b)
+    got_av = avf.run_device(a, b)
+    for i in range(n):
+        ca = {"format": fmt, "planes": a.download(i)}
+        cb = {"format": fmt, "planes": b.download(i)}
+        props_close(got_mm[i], oa.planeminmax(ca, minthr=0.1, maxthr=0.2, clipb=cb))
+        props_close(got_av[i], oa.planeaverage(ca, [7, 9], clipb=cb))

@@ -1,0 +1,211 @@
+// bilateral_kernels.cu — sm_100a kernel for vszip.Bilateral, algorithm 2 ("truncated" window).
+//
+// Semantics restated from src/filters/bilateral.zig:178-304: per output pixel, a centre tap plus
+// (yy, xx) in {1, 1+step, ...} <= radius, four diagonal taps each, weights gs[yy][xx] * gr[range index],
+// f32 accumulation with separate multiply/add in the reference's association order, replicate edges.
+//
+// Design: a CTA computes a 32x8 tile.  The tile plus halo is staged once in shared memory, already
+// widened to f32 and with edge replication applied, so every tap is a conflict-free LDS.  The range
+// weight comes from one of three sources, chosen per plane at create time:
+//   W_SMEM    the reference's LUT copied to shared memory (8..12-bit clips, or small sigmaR where the LUT
+//             is short): bit-identical weights;
+//   W_COMPUTE C * 2^(c2 * idx^2) on the MUFU unit when the LUT (up to 256 KB) does not fit in shared
+//             memory: weights within ~2 ulp, integer outputs within 1 LSB;
+//   W_GLOBAL  gathers from the full LUT in HBM/L2: bit-identical, slow (validation / VSZIP_BILATERAL_EXACT=1).
+#include <cuda_fp16.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+
+#include "filter.h"
+
+namespace vsz {
+
+enum WeightMode { W_SMEM = 0, W_COMPUTE = 1, W_GLOBAL = 2 };
+
+static constexpr int TW = 32, TH = 8;
+
+struct BilateralPlaneParams {
+    const float* gs;   // (radius+1)^2, device
+    const float* gr;   // full LUT, device
+    int radius, step;
+    int lut_len;       // entries [0, lut_len) are distinct; larger indices use gr[lut_len-1]
+    int smem_lut;      // entries copied to shared memory (W_SMEM)
+    float c2, cnorm;   // W_COMPUTE: weight = cnorm * exp2(c2 * idx^2)
+};
+
+struct BilateralParams {
+    BilateralPlaneParams pl[3];  // indexed by PlaneJob::aux (the real plane number)
+    float peak;
+    int tiles_x[3];              // tiles per row, indexed like job.pl[]
+};
+
+template <typename T> __device__ __forceinline__ float widen(T v) { return (float)v; }
+template <> __device__ __forceinline__ float widen<__half>(__half v) { return __half2float(v); }
+
+template <typename T> struct BTr { static constexpr bool flt = false; };
+template <> struct BTr<__half> { static constexpr bool flt = true; };
+template <> struct BTr<float> { static constexpr bool flt = true; };
+
+// range index (src/filters/bilateral.zig:15-22) from widened samples
+template <typename T> __device__ __forceinline__ int range_index(float a, float b) {
+    if constexpr (BTr<T>::flt) {
+        float d = __fsub_rn(a, b);
+        if constexpr (sizeof(T) == 2) d = __half2float(__float2half_rn(d));  // the subtraction is rounded in f16
+        const float m = fminf(1.0f, fabsf(d));
+        return (int)__fadd_rn(__fmul_rn(m, 65535.0f), 0.5f);
+    } else {
+        return (int)fabsf(__fsub_rn(a, b));  // exact: both are integers below 2^16
+    }
+}
+
+template <int WM>
+__device__ __forceinline__ float range_weight(int idx, const BilateralPlaneParams& pp, const float* s_lut) {
+    idx = min(idx, pp.lut_len - 1);
+    if constexpr (WM == W_SMEM) return s_lut[idx];
+    else if constexpr (WM == W_GLOBAL) return __ldg(pp.gr + idx);
+    else {
+        const float f = (float)idx;
+        return pp.cnorm * exp2f(pp.c2 * f * f);
+    }
+}
+
+template <typename T, bool JOINT, int WM>
+__global__ void __launch_bounds__(TW * TH) bilateral_kernel(const BatchJob job, const BilateralParams prm) {
+    extern __shared__ float smem_f[];
+    int k = job.nplanes - 1;
+    while (k > 0 && (int)blockIdx.x < job.pl[k].cta_begin) --k;
+    const PlaneJob& pj = job.pl[k];
+    const BilateralPlaneParams& pp = prm.pl[pj.aux];
+    const int local = blockIdx.x - pj.cta_begin;
+    const int tx = local % prm.tiles_x[k], ty = local / prm.tiles_x[k];
+    const int x0 = tx * TW, y0 = ty * TH;
+    const int r = pp.radius, step = pp.step, r2 = r + 1;
+    const int tw = TW + 2 * r, th = TH + 2 * r;
+
+    float* s_src = smem_f;
+    float* s_ref = JOINT ? s_src + tw * th : s_src;
+    float* s_gs = s_ref + tw * th;
+    float* s_lut = s_gs + r2 * r2;
+
+    const char* src = job.src + (size_t)blockIdx.y * job.src_fs + pj.src_off;
+    const char* ref = JOINT ? job.ref + (size_t)blockIdx.y * job.ref_fs + pj.ref_off : nullptr;
+    const int tid = threadIdx.y * TW + threadIdx.x;
+    for (int i = tid; i < tw * th; i += TW * TH) {
+        const int lx = i % tw, ly = i / tw;
+        const int gx = min(max(x0 + lx - r, 0), pj.w - 1);
+        const int gy = min(max(y0 + ly - r, 0), pj.h - 1);
+        s_src[i] = widen<T>(reinterpret_cast<const T*>(src + (size_t)gy * pj.src_pitch)[gx]);
+        if constexpr (JOINT) s_ref[i] = widen<T>(reinterpret_cast<const T*>(ref + (size_t)gy * pj.ref_pitch)[gx]);
+    }
+    for (int i = tid; i < r2 * r2; i += TW * TH) s_gs[i] = pp.gs[i];
+    if constexpr (WM == W_SMEM)
+        for (int i = tid; i < pp.smem_lut; i += TW * TH) s_lut[i] = pp.gr[i];
+    __syncthreads();
+
+    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+    if (x >= pj.w || y >= pj.h) return;
+    const int cxy = (threadIdx.y + r) * tw + threadIdx.x + r;
+    const float cref = s_ref[cxy];
+    float wsum = __fmul_rn(s_gs[0], range_weight<WM>(0, pp, s_lut));
+    float sum = __fmul_rn(s_src[cxy], wsum);
+    for (int yy = 1; yy < r2; yy += step) {
+        const int up = cxy - yy * tw, dn = cxy + yy * tw;
+        for (int xx = 1; xx < r2; xx += step) {
+            const float sw = s_gs[yy * r2 + xx];
+            const float g1 = range_weight<WM>(range_index<T>(cref, s_ref[up + xx]), pp, s_lut);
+            const float g2 = range_weight<WM>(range_index<T>(cref, s_ref[dn + xx]), pp, s_lut);
+            const float g3 = range_weight<WM>(range_index<T>(cref, s_ref[up - xx]), pp, s_lut);
+            const float g4 = range_weight<WM>(range_index<T>(cref, s_ref[dn - xx]), pp, s_lut);
+            const float gsum = __fadd_rn(__fadd_rn(__fadd_rn(g1, g2), g3), g4);
+            wsum = __fadd_rn(wsum, __fmul_rn(sw, gsum));
+            const float p1 = __fmul_rn(s_src[up + xx], g1), p2 = __fmul_rn(s_src[dn + xx], g2);
+            const float p3 = __fmul_rn(s_src[up - xx], g3), p4 = __fmul_rn(s_src[dn - xx], g4);
+            const float psum = __fadd_rn(__fadd_rn(__fadd_rn(p1, p2), p3), p4);
+            sum = __fadd_rn(sum, __fmul_rn(sw, psum));
+        }
+    }
+    const float q = __fdiv_rn(sum, wsum);
+    T* out = reinterpret_cast<T*>(job.dst + (size_t)blockIdx.y * job.dst_fs + pj.dst_off + (size_t)y * pj.dst_pitch) + x;
+    if constexpr (std::is_same<T, float>::value) *out = q;
+    else if constexpr (std::is_same<T, __half>::value) *out = __float2half_rn(q);
+    else *out = (T)fminf(fmaxf(__fadd_rn(q, 0.5f), 0.0f), prm.peak);  // trunc(clamp(q + 0.5, 0, peak))
+}
+
+// =========================================================================== host
+static constexpr int kSmemLutMaxEntries = 12288;  // 48 KB
+
+static int weight_mode_for(int lut_len) {
+    static const bool force_exact = [] { const char* e = getenv("VSZIP_BILATERAL_EXACT"); return e && e[0] == '1'; }();
+    if (lut_len <= kSmemLutMaxEntries) return W_SMEM;
+    return force_exact ? W_GLOBAL : W_COMPUTE;
+}
+
+int bilateral_weights_exact(int lut_len) { return weight_mode_for(lut_len) != W_COMPUTE; }
+
+template <typename T, bool JOINT>
+static int launch_mode(int wm, const BatchJob& j, const BilateralParams& prm, int nf, size_t smem, cudaStream_t st) {
+    const dim3 grid(j.ctas_per_frame, nf), block(TW, TH);
+#define VSZ_BL(WMV)                                                                                       \
+    {                                                                                                     \
+        auto kern = bilateral_kernel<T, JOINT, WMV>;                                                      \
+        VSZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+        kern<<<grid, block, smem, st>>>(j, prm);                                                          \
+    }
+    if (wm == W_SMEM) VSZ_BL(W_SMEM)
+    else if (wm == W_COMPUTE) VSZ_BL(W_COMPUTE)
+    else VSZ_BL(W_GLOBAL)
+#undef VSZ_BL
+    count_launch();
+    return 0;
+}
+
+template <typename T>
+static int run_bilateral_t(const FrameLayout& l, const bool mask[3], const char* src, size_t sfs, const char* ref, size_t rfs, char* dst,
+                           size_t dfs, int count, const BilateralLaunch& bp, cudaStream_t st) {
+    // planes with different weight sources / radii need different shared-memory sizes: one launch per plane
+    for (int p = 0; p < l.nplanes; ++p) {
+        if (!mask[p]) continue;
+        bool one[3] = {false, false, false};
+        one[p] = true;
+        BilateralParams prm{};
+        prm.peak = bp.peak;
+        BilateralPlaneParams& pp = prm.pl[p];
+        pp.gs = bp.gs[p]; pp.gr = bp.gr[p];
+        pp.radius = bp.radius[p]; pp.step = bp.step[p];
+        pp.lut_len = bp.lut_len[p];
+        const int wm = weight_mode_for(pp.lut_len);
+        pp.smem_lut = wm == W_SMEM ? pp.lut_len : 0;
+        pp.c2 = bp.c2[p]; pp.cnorm = bp.cnorm[p];
+        const int r = pp.radius;
+        BatchJob j = make_batch(l, one, src, sfs, ref, rfs, dst, dfs, [](int w, int h) { return ((w + TW - 1) / TW) * ((h + TH - 1) / TH); });
+        prm.tiles_x[0] = (l.pl[p].w + TW - 1) / TW;
+        const size_t tile = (size_t)(TW + 2 * r) * (TH + 2 * r);
+        const size_t smem = (tile * (ref ? 2 : 1) + (size_t)(r + 1) * (r + 1) + (size_t)pp.smem_lut) * sizeof(float);
+        if (smem > 227 * 1024) { set_error("Bilateral: spatial radius %d does not fit the shared-memory tile", r); return -2; }
+        for (int f0 = 0; f0 < count; f0 += 65535) {
+            const int nf = std::min(65535, count - f0);
+            BatchJob jj = j;
+            jj.src += (size_t)f0 * sfs; jj.dst += (size_t)f0 * dfs;
+            if (ref) jj.ref += (size_t)f0 * rfs;
+            const int rc = ref ? launch_mode<T, true>(wm, jj, prm, nf, smem, st) : launch_mode<T, false>(wm, jj, prm, nf, smem, st);
+            if (rc) return rc;
+        }
+    }
+    VSZ_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int run_bilateral(const FrameLayout& l, const bool mask[3], const char* src, size_t src_fs, const char* ref, size_t ref_fs, char* dst,
+                  size_t dst_fs, int count, const BilateralLaunch& bp, cudaStream_t st) {
+    switch (l.kind) {
+        case K_U8: return run_bilateral_t<uint8_t>(l, mask, src, src_fs, ref, ref_fs, dst, dst_fs, count, bp, st);
+        case K_U16: return run_bilateral_t<uint16_t>(l, mask, src, src_fs, ref, ref_fs, dst, dst_fs, count, bp, st);
+        case K_F16: return run_bilateral_t<__half>(l, mask, src, src_fs, ref, ref_fs, dst, dst_fs, count, bp, st);
+        case K_F32: return run_bilateral_t<float>(l, mask, src, src_fs, ref, ref_fs, dst, dst_fs, count, bp, st);
+    }
+    return -1;
+}
+
+}  // namespace vsz

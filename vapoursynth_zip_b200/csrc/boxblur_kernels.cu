@@ -1,0 +1,590 @@
+// boxblur_kernels.cu — sm_100a kernels for vszip.BoxBlur.
+//
+// Semantics restated from the reference (see DESIGN.md §BoxBlur for the derivation):
+//   runtime path  (src/filters/boxblur_runtime.zig:10-119): per line and pass a running box sum with
+//       SYM (edge-repeating) mirroring; integer S += inv2*(a-b), out = S>>16; float S += (a-b)*div.
+//   comptime path (src/filters/boxblur_comptime.zig:10-159): V first with exact R101q column sums and a
+//       rounded mean, then the runtime H pass; float uses direct tap-ordered sums (:161-263).
+//
+// Design: a line (row or column) is owned by exactly one thread, which streams along it once and
+// pipelines all `P` passes of that axis: at time t stage p works on position t - p*r, its "add"
+// operand is the value stage p-1 produced in the same step (a register), its "sub" operand is the
+// value stage p-1 produced 2r+1 steps ago.  Every stage keeps those last 2r+1 values in a shared-
+// memory delay ring and all stages share one slot index (t mod (2r+1)), so a stage costs one LDS, one
+// STS (the same address: an exchange) and the multiply-adds; no pass ever touches HBM for
+// intermediates.  Lines are packed 4/sizeof(T) per thread into 32-bit words so ring traffic and global
+// accesses are 32-bit per lane.  The arithmetic per line is the reference's own op sequence, hence
+// bit-exact for integer AND float formats.
+//
+//   blur_v_kernel : lines = columns, thread = 32-bit column group; global access coalesced by construction.
+//   blur_h_kernel : lines = rows; a CTA owns NT*NL rows and stages 32-position tiles through shared
+//                   memory (coalesced row segments in, transposed so each thread reads its own rows).
+//   ctf_*_kernel  : comptime float path (direct sums, R101q).
+#include <cuda_fp16.h>
+
+#include "common.h"
+
+namespace vsz {
+
+enum BlurMode { MODE_RT = 0, MODE_CTV = 1 };
+
+// --------------------------------------------------------------------------- pixel traits
+template <typename T> struct Px;
+template <> struct Px<uint8_t> { static constexpr int NL = 4; using Acc = uint32_t; static constexpr bool flt = false; };
+template <> struct Px<uint16_t> { static constexpr int NL = 2; using Acc = uint32_t; static constexpr bool flt = false; };
+template <> struct Px<__half> { static constexpr int NL = 2; using Acc = float; static constexpr bool flt = true; };
+template <> struct Px<float> { static constexpr int NL = 1; using Acc = float; static constexpr bool flt = true; };
+
+template <typename T> __device__ __forceinline__ void unpack(uint32_t w, typename Px<T>::Acc (&v)[Px<T>::NL]);
+template <> __device__ __forceinline__ void unpack<uint8_t>(uint32_t w, uint32_t (&v)[4]) {
+    v[0] = w & 0xffu; v[1] = (w >> 8) & 0xffu; v[2] = (w >> 16) & 0xffu; v[3] = w >> 24;
+}
+template <> __device__ __forceinline__ void unpack<uint16_t>(uint32_t w, uint32_t (&v)[2]) {
+    v[0] = w & 0xffffu; v[1] = w >> 16;
+}
+template <> __device__ __forceinline__ void unpack<__half>(uint32_t w, float (&v)[2]) {
+    const __half2 h = *reinterpret_cast<const __half2*>(&w);
+    const float2 f = __half22float2(h);
+    v[0] = f.x; v[1] = f.y;
+}
+template <> __device__ __forceinline__ void unpack<float>(uint32_t w, float (&v)[1]) { v[0] = __uint_as_float(w); }
+
+// Parameters of one axis, uniform over the launch.
+struct AxisParams {
+    int r;          // radius
+    int ring;       // 2r+1
+    uint32_t inv2;  // inv >> 16
+    uint32_t inv;   // floor((2^32 + r) / (2r+1))  (fits u32 for r >= 1)
+    float div;      // 1 / (2r+1) in f32
+};
+
+// --------------------------------------------------------------------------- one stage's arithmetic
+// Integer stages keep S = 16.16 fixed point in u32: the reference's u64 running sum stays below 2^32
+// (its Debug build would trap on the narrowing cast otherwise), so modular u32 arithmetic is exact.
+template <typename T, int MODE>
+struct StageOps {
+    using X = Px<T>;
+    using Acc = typename X::Acc;
+    static constexpr int NL = X::NL;
+
+    // returns the packed output word after folding (a - b) into S
+    static __device__ __forceinline__ uint32_t update(Acc (&S)[NL], uint32_t aw, uint32_t bw, const AxisParams& ap) {
+        Acc a[NL], b[NL];
+        unpack<T>(aw, a);
+        unpack<T>(bw, b);
+#pragma unroll
+        for (int l = 0; l < NL; ++l) {
+            if constexpr (X::flt) {
+                const float d = __fsub_rn(a[l], b[l]);
+                S[l] = __fadd_rn(S[l], __fmul_rn(d, ap.div));
+            } else if constexpr (MODE == MODE_CTV) {
+                S[l] = S[l] + a[l] - b[l];
+            } else {
+                S[l] = S[l] + ap.inv2 * (a[l] - b[l]);
+            }
+        }
+        return emit(S, ap);
+    }
+
+    // packed output of the current state
+    static __device__ __forceinline__ uint32_t emit(const Acc (&S)[NL], const AxisParams& ap) {
+        if constexpr (std::is_same<T, float>::value) {
+            return __float_as_uint(S[0]);
+        } else if constexpr (std::is_same<T, __half>::value) {
+            const __half2 h = __floats2half2_rn(S[0], S[1]);
+            return *reinterpret_cast<const uint32_t*>(&h);
+        } else {
+            uint32_t o[NL];
+#pragma unroll
+            for (int l = 0; l < NL; ++l) {
+                if constexpr (MODE == MODE_CTV)
+                    o[l] = (uint32_t)(((uint64_t)S[l] * ap.inv + 0x80000000ull) >> 32);  // rounded mean
+                else
+                    o[l] = S[l] >> 16;
+            }
+            if constexpr (NL == 2) return o[0] | (o[1] << 16);
+            else return o[0] | (o[1] << 8) | (o[2] << 16) | (o[3] << 24);
+        }
+    }
+
+    // start-of-line state from the first r+1 samples of the previous stage (read through `rd(pos)`)
+    template <class RD>
+    static __device__ __forceinline__ void init(Acc (&S)[NL], const AxisParams& ap, RD rd) {
+        Acc v[NL];
+        if constexpr (X::flt) {
+            // sum = in[r]; sum += in[x]*2 for x = 0..r-1 (in that order); sum *= div
+            unpack<T>(rd(ap.r), v);
+#pragma unroll
+            for (int l = 0; l < NL; ++l) S[l] = v[l];
+            for (int x = 0; x < ap.r; ++x) {
+                unpack<T>(rd(x), v);
+#pragma unroll
+                for (int l = 0; l < NL; ++l) S[l] = __fadd_rn(S[l], __fmul_rn(v[l], 2.0f));
+            }
+#pragma unroll
+            for (int l = 0; l < NL; ++l) S[l] = __fmul_rn(S[l], ap.div);
+        } else if constexpr (MODE == MODE_CTV) {
+            // reflect-101 window at row 0: in[0] + 2*sum(in[1..r])
+            unpack<T>(rd(0), v);
+#pragma unroll
+            for (int l = 0; l < NL; ++l) S[l] = v[l];
+            for (int x = 1; x <= ap.r; ++x) {
+                unpack<T>(rd(x), v);
+#pragma unroll
+                for (int l = 0; l < NL; ++l) S[l] += 2u * v[l];
+            }
+        } else {
+            // W0 = in[r] + 2*sum(in[0..r-1]);  S0 = (W0*inv + 2^31) >> 16
+            unpack<T>(rd(ap.r), v);
+            uint32_t w0[NL];
+#pragma unroll
+            for (int l = 0; l < NL; ++l) w0[l] = v[l];
+            for (int x = 0; x < ap.r; ++x) {
+                unpack<T>(rd(x), v);
+#pragma unroll
+                for (int l = 0; l < NL; ++l) w0[l] += 2u * v[l];
+            }
+#pragma unroll
+            for (int l = 0; l < NL; ++l) S[l] = (uint32_t)(((uint64_t)w0[l] * ap.inv + 0x80000000ull) >> 16);
+        }
+    }
+};
+
+// --------------------------------------------------------------------------- the per-thread pipeline
+// ring layout: word index ((slot * P + q) * NT + tid): stage offsets are compile-time immediates.
+template <typename T, int P, int MODE, int NT>
+struct LinePipe {
+    using Ops = StageOps<T, MODE>;
+    using Acc = typename Px<T>::Acc;
+    static constexpr int NL = Px<T>::NL;
+
+    Acc S[P][NL];
+    uint32_t* ring;  // &ring_base[tid]
+    int n;
+    AxisParams ap;
+
+    __device__ __forceinline__ uint32_t& cell(int slot, int q) { return ring[(slot * P + q) * NT]; }
+    __device__ __forceinline__ int slot_of(int pos, int q) const { return (pos + q * ap.r) % ap.ring; }
+
+    // all stages strictly interior: r < x_p < n - r for every p.  `slot` = t mod ring.
+    __device__ __forceinline__ uint32_t step_fast(int slot, uint32_t v) {
+        uint32_t* base = ring + slot * (P * NT);
+#pragma unroll
+        for (int q = 0; q < P; ++q) {
+            const uint32_t old = base[q * NT];
+            base[q * NT] = v;
+            v = Ops::update(S[q], v, old, ap);
+        }
+        return v;
+    }
+
+    // any t in [0, n + P*r): handles start-up, mirrored edges and drain.  Returns true when the last
+    // stage produced position t - P*r (value in `out`).
+    __device__ __forceinline__ bool step_edge(int t, int slot, uint32_t v_in, uint32_t& out) {
+        bool act_prev = t < n;  // "stage 0" = the input stream
+        uint32_t v = v_in;
+#pragma unroll
+        for (int q = 0; q < P; ++q) {
+            uint32_t old = 0;
+            if (act_prev) {  // stage q publishes its value of this step into its delay ring
+                old = cell(slot, q);
+                cell(slot, q) = v;
+            }
+            const int x = t - (q + 1) * ap.r;  // position of stage q+1
+            const bool act = (x >= 0) && (x < n);
+            if (act) {
+                if (x == 0) {
+                    Ops::init(S[q], ap, [&](int pos) { return cell(slot_of(pos, q), q); });
+                    if constexpr (MODE == MODE_CTV) {
+                        v = Ops::emit(S[q], ap);
+                    } else {
+                        const uint32_t c = cell(slot_of(ap.r, q), q);
+                        v = Ops::update(S[q], c, c, ap);  // the reference's x = 0 step adds in[r] - in[r]
+                    }
+                } else {
+                    uint32_t a, b;
+                    if constexpr (MODE == MODE_CTV) {
+                        a = (x + ap.r < n) ? v : cell(slot_of(x - 1, q), q);
+                        b = (x <= ap.r) ? cell(slot_of(ap.r - x + 1, q), q) : (act_prev ? old : cell(slot, q));
+                    } else {
+                        a = (x + ap.r < n) ? v : cell(slot_of(2 * n - ap.r - x - 1, q), q);
+                        b = (x <= ap.r) ? cell(slot_of(ap.r - x, q), q) : (act_prev ? old : cell(slot, q));
+                    }
+                    v = Ops::update(S[q], a, b, ap);
+                }
+            }
+            act_prev = act;
+        }
+        out = v;
+        return act_prev;
+    }
+};
+
+__device__ __forceinline__ const PlaneJob& find_plane(const BatchJob& b, int cta, int& local) {
+    int k = b.nplanes - 1;
+    while (k > 0 && cta < b.pl[k].cta_begin) --k;
+    local = cta - b.pl[k].cta_begin;
+    return b.pl[k];
+}
+
+// --------------------------------------------------------------------------- V: lines are columns
+template <typename T, int P, int MODE, int NT>
+__global__ void __launch_bounds__(NT) blur_v_kernel(const BatchJob job, const AxisParams ap) {
+    extern __shared__ uint32_t smem[];
+    constexpr int NL = Px<T>::NL;
+    int local;
+    const PlaneJob& pj = find_plane(job, blockIdx.x, local);
+    const int g = local * NT + threadIdx.x;  // 32-bit column group
+    if (g * NL >= pj.w) return;               // no block-level sync in this kernel
+    const char* src = job.src + (size_t)blockIdx.y * job.src_fs + pj.src_off + (size_t)g * 4;
+    char* dst = job.dst + (size_t)blockIdx.y * job.dst_fs + pj.dst_off + (size_t)g * 4;
+    const int sp = pj.src_pitch, dp = pj.dst_pitch;
+
+    LinePipe<T, P, MODE, NT> pipe;
+    pipe.ring = smem + threadIdx.x;
+    pipe.n = pj.h;
+    pipe.ap = ap;
+    const int n = pj.h, lag = P * ap.r, total = n + lag;
+    int t_lo = lag + ap.r + 1, t_hi = n;
+    if (t_lo >= t_hi) { t_lo = total; t_hi = total; }
+
+    int slot = 0;
+    auto load = [&](int t) { return *reinterpret_cast<const uint32_t*>(src + (size_t)t * sp); };
+    auto store = [&](int x, uint32_t v) { *reinterpret_cast<uint32_t*>(dst + (size_t)x * dp) = v; };
+    auto bump = [&]() { slot = (slot + 1 == ap.ring) ? 0 : slot + 1; };
+
+    int t = 0;
+    for (; t < t_lo; ++t) {
+        uint32_t o;
+        const uint32_t v = (t < n) ? load(t) : 0u;
+        if (pipe.step_edge(t, slot, v, o)) store(t - lag, o);
+        bump();
+    }
+    // steady state: 4 rows per iteration, next rows' loads issued before the dependent math
+    constexpr int U = 4;
+    if (t < t_hi) {
+        uint32_t nxt[U];
+#pragma unroll
+        for (int i = 0; i < U; ++i) nxt[i] = load(min(t + i, n - 1));
+        for (; t + U <= t_hi; t += U) {
+            uint32_t cur[U];
+#pragma unroll
+            for (int i = 0; i < U; ++i) cur[i] = nxt[i];
+#pragma unroll
+            for (int i = 0; i < U; ++i) nxt[i] = load(min(t + U + i, n - 1));
+#pragma unroll
+            for (int i = 0; i < U; ++i) {
+                const uint32_t o = pipe.step_fast(slot, cur[i]);
+                store(t + i - lag, o);
+                bump();
+            }
+        }
+        for (; t < t_hi; ++t) {
+            const uint32_t o = pipe.step_fast(slot, load(t));
+            store(t - lag, o);
+            bump();
+        }
+    }
+    for (; t < total; ++t) {
+        uint32_t o;
+        const uint32_t v = (t < n) ? load(t) : 0u;
+        if (pipe.step_edge(t, slot, v, o)) store(t - lag, o);
+        bump();
+    }
+}
+
+// --------------------------------------------------------------------------- H: lines are rows
+// CTA = NT threads = NT*NL rows.  Tiles are [position][row] in T units with (NT*NL + PAD) row pitch so
+// that both the coalesced side (32 lanes = 32 positions of one row) and the line side (32 lanes = 32
+// consecutive row groups) are bank-conflict free.
+template <typename T, int NT> struct HTile {
+    static constexpr int NL = Px<T>::NL;
+    static constexpr int CH = 32;                        // positions per input tile
+    static constexpr int OUT = 64;                       // positions in the output ring (two blocks)
+    static constexpr int PITCH_W = NT + 1;               // words per position (odd)
+    static constexpr int IN_WORDS = CH * PITCH_W;
+    static constexpr int OUT_WORDS = OUT * PITCH_W;
+};
+
+template <typename T, int P, int NT>
+__global__ void __launch_bounds__(NT) blur_h_kernel(const BatchJob job, const AxisParams ap) {
+    extern __shared__ uint32_t smem[];
+    using TL = HTile<T, NT>;
+    constexpr int NL = Px<T>::NL;
+    constexpr int ROWS = NT * NL;
+    constexpr int NWARP = NT / 32;
+    int local;
+    const PlaneJob& pj = find_plane(job, blockIdx.x, local);
+    const int row0 = local * ROWS;
+    const int nrows = min(ROWS, pj.h - row0);
+    const char* src = job.src + (size_t)blockIdx.y * job.src_fs + pj.src_off + (size_t)row0 * pj.src_pitch;
+    char* dst = job.dst + (size_t)blockIdx.y * job.dst_fs + pj.dst_off + (size_t)row0 * pj.dst_pitch;
+    const int sp = pj.src_pitch, dp = pj.dst_pitch;
+
+    uint32_t* ring = smem;
+    uint32_t* in_tile = ring + ap.ring * P * NT;
+    uint32_t* out_tile = in_tile + TL::IN_WORDS;
+    T* in_t = reinterpret_cast<T*>(in_tile);
+    T* out_t = reinterpret_cast<T*>(out_tile);
+
+    LinePipe<T, P, MODE_RT, NT> pipe;
+    pipe.ring = ring + threadIdx.x;
+    pipe.n = pj.w;
+    pipe.ap = ap;
+    const int n = pj.w, lag = P * ap.r, total = n + lag;
+    int t_lo = lag + ap.r + 1, t_hi = n;
+    if (t_lo >= t_hi) { t_lo = total; t_hi = total; }
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int slot = 0;
+    int flushed = 0;  // output positions [0, flushed) are already in global memory
+    const int nchunks = (total + TL::CH - 1) / TL::CH;
+
+    for (int c = 0; c < nchunks; ++c) {
+        const int t0 = c * TL::CH;
+        // ---- cooperative, coalesced load of positions [t0, t0+32) of every row of this CTA
+        {
+            const int x = t0 + lane;
+            if (x < n) {
+                for (int rr = warp; rr < nrows; rr += NWARP)
+                    in_t[(lane * TL::PITCH_W) * NL + rr] = *reinterpret_cast<const T*>(src + (size_t)rr * sp + (size_t)x * sizeof(T));
+            }
+        }
+        __syncthreads();
+        // ---- every thread advances its own rows by up to 32 steps
+        const int t1 = min(t0 + TL::CH, total);
+        for (int t = t0; t < t1; ++t) {
+            const uint32_t v = in_tile[(t - t0) * TL::PITCH_W + threadIdx.x];
+            uint32_t o;
+            bool have;
+            if (t >= t_lo && t < t_hi) { o = pipe.step_fast(slot, v); have = true; }
+            else have = pipe.step_edge(t, slot, v, o);
+            if (have) out_tile[((t - lag) & (TL::OUT - 1)) * TL::PITCH_W + threadIdx.x] = o;
+            slot = (slot + 1 == ap.ring) ? 0 : slot + 1;
+        }
+        __syncthreads();
+        // ---- flush every complete 32-position output block (and the tail at the very end)
+        const int produced = min(max(t1 - lag, 0), n);
+        const int upto = (t1 == total) ? n : (produced / 32) * 32;
+        for (int xb = flushed; xb < upto; xb += 32) {
+            const int x = xb + lane;
+            if (x < upto) {
+                for (int rr = warp; rr < nrows; rr += NWARP)
+                    *reinterpret_cast<T*>(dst + (size_t)rr * dp + (size_t)x * sizeof(T)) =
+                        out_t[((x & (TL::OUT - 1)) * TL::PITCH_W) * NL + rr];
+            }
+        }
+        flushed = max(flushed, upto);
+        // the next iteration's __syncthreads (after its load) orders these reads before new out_tile writes
+    }
+}
+
+// --------------------------------------------------------------------------- comptime float path
+// Direct tap-ordered sums with R101q indexing (src/filters/boxblur_comptime.zig:161-263):
+// acc = 0; for k in 0..2r: acc = acc + div * v_k; narrowed to T.  One thread per output sample.
+__device__ __forceinline__ int r101q(int i, int k, int r, int n) {
+    if (k < r) {
+        const int need = r - k;
+        return (i < need) ? min(need - i, n - 1) : i - need;
+    }
+    const int over = k - r, room = n - 1 - i;
+    return (room < over) ? i - min(over - room, i) : i + over;
+}
+
+template <typename T> __device__ __forceinline__ float ld_f(const T* p) { return (float)*p; }
+template <> __device__ __forceinline__ float ld_f<__half>(const __half* p) { return __half2float(*p); }
+template <typename T> __device__ __forceinline__ T st_f(float v);
+template <> __device__ __forceinline__ float st_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ __half st_f<__half>(float v) { return __float2half_rn(v); }
+
+template <typename T, bool VERTICAL>
+__global__ void __launch_bounds__(256) ctf_kernel(const BatchJob job, int r, float div) {
+    int local;
+    const PlaneJob& pj = find_plane(job, blockIdx.x, local);
+    // each CTA covers 256 consecutive samples of one row
+    const int ctas_per_row = (pj.w + 255) / 256;
+    const int y = local / ctas_per_row;
+    const int x = (local % ctas_per_row) * 256 + threadIdx.x;
+    if (x >= pj.w) return;
+    const char* src = job.src + (size_t)blockIdx.y * job.src_fs + pj.src_off;
+    char* dst = job.dst + (size_t)blockIdx.y * job.dst_fs + pj.dst_off;
+    float acc = 0.0f;
+    const int i = VERTICAL ? y : x, n = VERTICAL ? pj.h : pj.w;
+    const bool interior = (i >= r) && (i + r < n);
+    for (int k = 0; k <= 2 * r; ++k) {
+        const int idx = interior ? (i - r + k) : r101q(i, k, r, n);
+        const T* p = VERTICAL ? reinterpret_cast<const T*>(src + (size_t)idx * pj.src_pitch) + x
+                              : reinterpret_cast<const T*>(src + (size_t)y * pj.src_pitch) + idx;
+        acc = __fadd_rn(acc, __fmul_rn(div, ld_f<T>(p)));
+    }
+    reinterpret_cast<T*>(dst + (size_t)y * pj.dst_pitch)[x] = st_f<T>(acc);
+}
+
+// =========================================================================== host-side launchers
+static AxisParams axis_params(int r) {
+    AxisParams a{};
+    a.r = r;
+    a.ring = 2 * r + 1;
+    const uint64_t inv = ((1ull << 32) + (uint64_t)r) / (uint64_t)(2 * r + 1);
+    a.inv = (uint32_t)inv;
+    a.inv2 = (uint32_t)(inv >> 16);
+    a.div = 1.0f / (float)(2 * r + 1);
+    return a;
+}
+
+static constexpr int kMaxSmem = 227 * 1024;
+static constexpr int NT_V = 64;
+static constexpr int NT_H = 32;
+
+template <typename T, int P, int MODE>
+static int launch_v(const FrameLayout& l, const bool mask[3], const char* src, size_t src_fs, char* dst, size_t dst_fs,
+                    int count, int r, cudaStream_t st) {
+    constexpr int NL = Px<T>::NL;
+    const AxisParams ap = axis_params(r);
+    const size_t smem = (size_t)ap.ring * P * NT_V * 4;
+    if (smem > (size_t)kMaxSmem) { set_error("BoxBlur: vradius %d with %d fused passes exceeds the shared-memory delay ring", r, P); return -2; }
+    auto kern = blur_v_kernel<T, P, MODE, NT_V>;
+    VSZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    BatchJob job = make_batch(l, mask, src, src_fs, nullptr, 0, dst, dst_fs,
+                              [](int w, int) { return ((w + NL - 1) / NL + NT_V - 1) / NT_V; });
+    if (job.ctas_per_frame == 0) return 0;
+    for (int f0 = 0; f0 < count; f0 += 65535) {
+        const int nf = std::min(65535, count - f0);
+        BatchJob j = job;
+        j.src += (size_t)f0 * src_fs; j.dst += (size_t)f0 * dst_fs;
+        kern<<<dim3(job.ctas_per_frame, nf), NT_V, smem, st>>>(j, ap);
+        count_launch();
+    }
+    VSZ_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <typename T, int P>
+static int launch_h(const FrameLayout& l, const bool mask[3], const char* src, size_t src_fs, char* dst, size_t dst_fs,
+                    int count, int r, cudaStream_t st) {
+    constexpr int NL = Px<T>::NL;
+    using TL = HTile<T, NT_H>;
+    const AxisParams ap = axis_params(r);
+    const size_t smem = ((size_t)ap.ring * P * NT_H + TL::IN_WORDS + TL::OUT_WORDS) * 4;
+    if (smem > (size_t)kMaxSmem) { set_error("BoxBlur: hradius %d with %d fused passes exceeds the shared-memory delay ring", r, P); return -2; }
+    auto kern = blur_h_kernel<T, P, NT_H>;
+    VSZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    BatchJob job = make_batch(l, mask, src, src_fs, nullptr, 0, dst, dst_fs,
+                              [](int, int h) { return (h + NT_H * NL - 1) / (NT_H * NL); });
+    if (job.ctas_per_frame == 0) return 0;
+    for (int f0 = 0; f0 < count; f0 += 65535) {
+        const int nf = std::min(65535, count - f0);
+        BatchJob j = job;
+        j.src += (size_t)f0 * src_fs; j.dst += (size_t)f0 * dst_fs;
+        kern<<<dim3(job.ctas_per_frame, nf), NT_H, smem, st>>>(j, ap);
+        count_launch();
+    }
+    VSZ_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// largest number of passes one launch can fuse for this radius (shared-memory bound), at most 5
+static int max_fused(int r, bool horizontal) {
+    const size_t per_pass = (size_t)(2 * r + 1) * (horizontal ? NT_H : NT_V) * 4;
+    const size_t fixed = horizontal ? (size_t)(HTile<uint16_t, NT_H>::IN_WORDS + HTile<uint16_t, NT_H>::OUT_WORDS) * 4 : 0;
+    int p = (int)((kMaxSmem - fixed) / per_pass);
+    return p > 5 ? 5 : p;
+}
+
+template <typename T, bool H>
+static int launch_axis_p(int P, const FrameLayout& l, const bool mask[3], const char* src, size_t sfs, char* dst, size_t dfs,
+                         int count, int r, cudaStream_t st) {
+    switch (P) {
+        case 1: return H ? launch_h<T, 1>(l, mask, src, sfs, dst, dfs, count, r, st) : launch_v<T, 1, MODE_RT>(l, mask, src, sfs, dst, dfs, count, r, st);
+        case 2: return H ? launch_h<T, 2>(l, mask, src, sfs, dst, dfs, count, r, st) : launch_v<T, 2, MODE_RT>(l, mask, src, sfs, dst, dfs, count, r, st);
+        case 3: return H ? launch_h<T, 3>(l, mask, src, sfs, dst, dfs, count, r, st) : launch_v<T, 3, MODE_RT>(l, mask, src, sfs, dst, dfs, count, r, st);
+        case 4: return H ? launch_h<T, 4>(l, mask, src, sfs, dst, dfs, count, r, st) : launch_v<T, 4, MODE_RT>(l, mask, src, sfs, dst, dfs, count, r, st);
+        case 5: return H ? launch_h<T, 5>(l, mask, src, sfs, dst, dfs, count, r, st) : launch_v<T, 5, MODE_RT>(l, mask, src, sfs, dst, dfs, count, r, st);
+    }
+    set_error("BoxBlur: internal error, bad fused pass count %d", P);
+    return -3;
+}
+
+// `passes` runtime-path passes along one axis.  The first launch reads src, later ones run in place on
+// dst (a line is owned by one thread and outputs trail inputs, so in-place is race-free).
+template <typename T, bool H>
+static int run_axis(const FrameLayout& l, const bool mask[3], const char* src, size_t sfs, char* dst, size_t dfs, int count,
+                    int r, int passes, cudaStream_t st) {
+    const int cap = max_fused(r, H);
+    if (cap < 1) {
+        set_error("BoxBlur: %s %d is too large for the shared-memory delay ring (limit %d)", H ? "hradius" : "vradius", r,
+                  (int)((kMaxSmem / ((H ? NT_H : NT_V) * 4) - 1) / 2) - (H ? 100 : 0));
+        return -2;
+    }
+    const char* cur = src;
+    size_t cur_fs = sfs;
+    while (passes > 0) {
+        const int p = passes < cap ? passes : cap;
+        const int rc = launch_axis_p<T, H>(p, l, mask, cur, cur_fs, dst, dfs, count, r, st);
+        if (rc) return rc;
+        cur = dst; cur_fs = dfs;
+        passes -= p;
+    }
+    return 0;
+}
+
+template <typename T>
+static int run_ct_float(const FrameLayout& l, const bool mask[3], const char* src, size_t sfs, char* tmp, size_t tfs, char* dst,
+                        size_t dfs, int count, int r, cudaStream_t st) {
+    const float div = 1.0f / (float)(2 * r + 1);
+    auto ctas = [](int w, int h) { return ((w + 255) / 256) * h; };
+    BatchJob jv = make_batch(l, mask, src, sfs, nullptr, 0, tmp, tfs, ctas);
+    BatchJob jh = make_batch(l, mask, tmp, tfs, nullptr, 0, dst, dfs, ctas);
+    if (jv.ctas_per_frame == 0) return 0;
+    for (int f0 = 0; f0 < count; f0 += 65535) {
+        const int nf = std::min(65535, count - f0);
+        BatchJob a = jv, b = jh;
+        a.src += (size_t)f0 * sfs; a.dst += (size_t)f0 * tfs;
+        b.src += (size_t)f0 * tfs; b.dst += (size_t)f0 * dfs;
+        ctf_kernel<T, true><<<dim3(jv.ctas_per_frame, nf), 256, 0, st>>>(a, r, div);
+        ctf_kernel<T, false><<<dim3(jh.ctas_per_frame, nf), 256, 0, st>>>(b, r, div);
+        count_launch(2);
+    }
+    VSZ_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <typename T>
+static int run_boxblur_t(const FrameLayout& l, const bool mask[3], const char* src, size_t sfs, char* dst, size_t dfs, int count,
+                         int hr, int hp, int vr, int vp, cudaStream_t st) {
+    // dispatch rule of src/vapoursynth/boxblur.zig:188
+    const bool use_rt = (hr != vr) || (hr > 22) || (hp > 1) || (vp > 1);
+    if (use_rt) {
+        const bool hb = hr > 0 && hp > 0, vb = vr > 0 && vp > 0;
+        // "all H passes, then all V passes" (boxblur.zig:93-112), V in place on dst
+        if (hb) { const int rc = run_axis<T, true>(l, mask, src, sfs, dst, dfs, count, hr, hp, st); if (rc) return rc; }
+        if (vb) return run_axis<T, false>(l, mask, hb ? dst : src, hb ? dfs : sfs, dst, dfs, count, vr, vp, st);
+        return 0;
+    }
+    if constexpr (Px<T>::flt) {
+        char* tmp = nullptr;
+        const size_t bytes = l.frame_stride * (size_t)count;
+        VSZ_CUDA(cudaMallocAsync((void**)&tmp, bytes, st));
+        const int rc = run_ct_float<T>(l, mask, src, sfs, tmp, l.frame_stride, dst, dfs, count, hr, st);
+        VSZ_CUDA(cudaFreeAsync(tmp, st));
+        return rc;
+    } else {
+        // comptime integer path: exact R101q column sums + rounded mean, then the SYM H pass in place
+        int rc = launch_v<T, 1, MODE_CTV>(l, mask, src, sfs, dst, dfs, count, hr, st);
+        if (rc) return rc;
+        return launch_h<T, 1>(l, mask, dst, dfs, dst, dfs, count, hr, st);
+    }
+}
+
+int run_boxblur(const FrameLayout& l, const bool mask[3], const char* src, size_t sfs, char* dst, size_t dfs, int count, int hr,
+                int hp, int vr, int vp, cudaStream_t st) {
+    switch (l.kind) {
+        case K_U8: return run_boxblur_t<uint8_t>(l, mask, src, sfs, dst, dfs, count, hr, hp, vr, vp, st);
+        case K_U16: return run_boxblur_t<uint16_t>(l, mask, src, sfs, dst, dfs, count, hr, hp, vr, vp, st);
+        case K_F16: return run_boxblur_t<__half>(l, mask, src, sfs, dst, dfs, count, hr, hp, vr, vp, st);
+        case K_F32: return run_boxblur_t<float>(l, mask, src, sfs, dst, dfs, count, hr, hp, vr, vp, st);
+    }
+    return -1;
+}
+
+}  // namespace vsz

@@ -1,0 +1,621 @@
+// filters.cu — host side of the four filters: argument parsing/validation with the reference's
+// defaults and error strings (the twin of src/vapoursynth/{boxblur,bilateral,planeminmax,planeaverage}.zig
+// create callbacks), the synchronous getFrame-style entry points (host buffers, staged through the
+// per-request slot) and the batched device-resident entry points.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+
+#include "filter.h"
+
+using namespace vsz;
+
+namespace {
+
+// ZAPI getValue(u32/i32, ...) narrows the VapourSynth int64 with a saturating cast.
+uint32_t sat_u32(int64_t v) { return v < 0 ? 0u : (v > 0xffffffffll ? 0xffffffffu : (uint32_t)v); }
+int32_t sat_i32(int64_t v) { return v < INT32_MIN ? INT32_MIN : (v > INT32_MAX ? INT32_MAX : (int32_t)v); }
+
+// hz.mapGetPlanes (src/helper.zig:128-158): an absent key keeps the filter's default mask.
+bool parse_planes(const int64_t* planes, int n, int num_planes, const char* name, bool process[3]) {
+    if (n < 0 || planes == nullptr) return true;
+    process[0] = process[1] = process[2] = false;
+    for (int i = 0; i < n; ++i) {
+        const int64_t e = planes[i];
+        if (e < 0 || e >= num_planes) { set_error("%s: plane index out of range", name); return false; }
+        if (process[e]) { set_error("%s: plane specified twice.", name); return false; }
+        process[e] = true;
+    }
+    return true;
+}
+
+// hz.compareNodes(..., .BIGGER_THAN, ...) (src/helper.zig:166-215)
+bool compare_nodes(const vszip_video_info& a, const vszip_video_info& b, const char* name) {
+    if (a.width != b.width || a.height != b.height) { set_error("%s: all input clips must have the same width and height.", name); return false; }
+    if (a.color_family != b.color_family) { set_error("%s: all input clips must have the same color family.", name); return false; }
+    if (a.sub_sampling_w != b.sub_sampling_w || a.sub_sampling_h != b.sub_sampling_h) { set_error("%s: all input clips must have the same subsampling.", name); return false; }
+    if (a.bits_per_sample != b.bits_per_sample) { set_error("%s: all input clips must have the same bit depth.", name); return false; }
+    if (a.num_frames > b.num_frames) { set_error("%s: second clip has less frames than input clip.", name); return false; }
+    return true;
+}
+
+std::string fmt_num(double v) {  // Zig's {d}: shortest decimal that round-trips, never an exponent
+    char buf[400];
+    if (v == std::floor(v) && std::fabs(v) < 1e15) {
+        snprintf(buf, sizeof buf, "%.0f", v);
+        return buf;
+    }
+    for (int prec = 1; prec <= 17; ++prec) {
+        snprintf(buf, sizeof buf, "%.*g", prec, v);
+        if (strtod(buf, nullptr) == v) break;
+    }
+    if (strchr(buf, 'e')) snprintf(buf, sizeof buf, "%.17f", v);
+    return buf;
+}
+
+// hz.getArray (src/helper.zig:340-404)
+template <class T, class S>
+bool get_array(const S* src, int n, T def, double lo, double hi, const char* key, const char* name, T out[3], T (*conv)(S)) {
+    if (n > 3) { set_error("%s: %s has too many elements (got %d, max 3).", name, key, n); return false; }
+    for (int i = 0; i < 3; ++i) {
+        if (i < n) out[i] = conv(src[i]);
+        else if (i == 0) out[i] = def;
+        else out[i] = out[i - 1];
+        if ((double)out[i] < lo) { set_error("%s: %s value %s is below minimum %s.", name, key, fmt_num((double)out[i]).c_str(), fmt_num(lo).c_str()); return false; }
+        if ((double)out[i] > hi) { set_error("%s: %s value %s is above maximum %s.", name, key, fmt_num((double)out[i]).c_str(), fmt_num(hi).c_str()); return false; }
+    }
+    return true;
+}
+
+bool basic_vi_ok(const vszip_video_info* vi, const char* name) {
+    if (!vi || vi->width <= 0 || vi->height <= 0 || vi->num_planes < 1 || vi->num_planes > 3) {
+        set_error("%s: invalid video info", name);
+        return false;
+    }
+    return true;
+}
+
+struct SlotGuard {
+    DeviceCtx* d;
+    Slot* s;
+    explicit SlotGuard(DeviceCtx* dd) : d(dd), s(dd->acquire()) {}
+    ~SlotGuard() { d->release(s); }
+};
+
+DeviceCtx* route(int32_t n, const char* name) {
+    DeviceCtx* d = device_for_frame(n);
+    if (!d) set_error("%s: vszip_cuda_init has not been called (no GPU context; there is no CPU fallback)", name);
+    return d;
+}
+
+bool same_clip_shape(const vszip_dev_clip* a, const vszip_filter* f, const char* name) {
+    if (!a || a->vi.width != f->vi.width || a->vi.height != f->vi.height || a->layout.kind != f->sample ||
+        a->vi.num_planes != f->vi.num_planes || a->vi.sub_sampling_w != f->vi.sub_sampling_w ||
+        a->vi.sub_sampling_h != f->vi.sub_sampling_h) {
+        set_error("%s: device clip does not match the format the filter was created for", name);
+        return false;
+    }
+    return true;
+}
+
+bool range_ok(const vszip_dev_clip* c, int first, int count, const char* name) {
+    if (first < 0 || count < 0 || first + count > c->num_frames) { set_error("%s: frame range out of bounds", name); return false; }
+    return true;
+}
+
+}  // namespace
+
+extern "C" {
+
+void vszip_filter_free(vszip_filter* f) {
+    if (!f) return;
+    for (size_t d = 0; d < f->gr_dev.size(); ++d) {
+        DeviceCtx* ctx = device_ctx((int)d);
+        if (ctx) cudaSetDevice(ctx->ordinal);
+        for (float* p : f->gr_dev[d]) if (p) cudaFree(p);
+        for (float* p : f->gs_dev[d]) if (p) cudaFree(p);
+    }
+    delete f;
+}
+
+int vszip_filter_planes(const vszip_filter* f, int32_t process[3]) {
+    for (int i = 0; i < 3; ++i) process[i] = (i < f->vi.num_planes && f->process[i]) ? 1 : 0;
+    return 0;
+}
+
+// =========================================================================== BoxBlur
+vszip_filter* vszip_boxblur_create(const vszip_video_info* vi, const vszip_boxblur_args* a) {
+    static const char* name = "BoxBlur";
+    if (!basic_vi_ok(vi, name)) return nullptr;
+    SampleKind kind;
+    if (!select_kind(*vi, name, false, &kind)) return nullptr;
+    bool process[3] = {true, true, true};
+    if (!parse_planes(a->planes, a->num_planes, vi->num_planes, name, process)) return nullptr;
+    const uint32_t hr = a->has_hradius ? sat_u32(a->hradius) : 1u;
+    const uint32_t vr = a->has_vradius ? sat_u32(a->vradius) : 1u;
+    const int32_t hp = a->has_hpasses ? sat_i32(a->hpasses) : 1;
+    const int32_t vp = a->has_vpasses ? sat_i32(a->vpasses) : 1;
+    const bool vblur = vr > 0 && vp > 0, hblur = hr > 0 && hp > 0;
+    if (!vblur && !hblur) { set_error("BoxBlur: nothing to be performed"); return nullptr; }
+    // the comptime kernel blurs both axes with `hradius` whenever it is selected (boxblur.zig:188),
+    // so the size checks must hold for both axes there
+    const bool use_rt = (hr != vr) || (hr > 22) || (hp > 1) || (vp > 1);
+    for (int p = 0; p < vi->num_planes; ++p) {
+        if (!process[p]) continue;
+        const uint32_t pw = (uint32_t)vi->width >> (p ? vi->sub_sampling_w : 0);
+        const uint32_t ph = (uint32_t)vi->height >> (p ? vi->sub_sampling_h : 0);
+        if ((hblur || !use_rt) && (uint64_t)hr * 2 >= pw) { set_error("BoxBlur: hradius too large; 2*hradius must be < the (smallest processed) plane width."); return nullptr; }
+        if ((vblur || !use_rt) && (uint64_t)vr * 2 >= ph) { set_error("BoxBlur: vradius too large; 2*vradius must be < the (smallest processed) plane height."); return nullptr; }
+    }
+    vszip_filter* f = new vszip_filter();
+    f->kind = F_BOXBLUR;
+    f->vi = *vi;
+    f->sample = kind;
+    f->layout = make_layout(*vi, kind);
+    for (int i = 0; i < 3; ++i) f->process[i] = process[i] && i < vi->num_planes;
+    f->has_ref = false;
+    f->hradius = hr; f->vradius = vr; f->hpasses = hp; f->vpasses = vp;
+    return f;
+}
+
+int vszip_boxblur_get_frame(const vszip_filter* f, int32_t n, const vszip_frame* src, vszip_frame* dst) {
+    if (!f || f->kind != F_BOXBLUR) { set_error("BoxBlur: bad filter handle"); return -1; }
+    DeviceCtx* d = route(n, "BoxBlur");
+    if (!d) return -1;
+    SlotGuard g(d);
+    Slot* s = g.s;
+    VSZ_CUDA(cudaSetDevice(d->ordinal));
+    const size_t bytes = f->layout.frame_stride;
+    if (slot_reserve(d, s, 0, bytes) || slot_reserve(d, s, 2, bytes)) return -1;
+    if (stage_in(s, 0, f->layout, src, f->process)) return -1;
+    int rc = run_boxblur(f->layout, f->process, s->dev[0], 0, s->dev[2], 0, 1, (int)f->hradius, f->hpasses, (int)f->vradius, f->vpasses, s->stream);
+    if (rc) return rc;
+    if (stage_out_begin(s, f->layout, f->process)) return -1;
+    VSZ_CUDA(cudaStreamSynchronize(s->stream));
+    stage_out_finish(s, f->layout, dst, f->process);
+    return 0;
+}
+
+int vszip_boxblur_device(const vszip_filter* f, const vszip_dev_clip* src, vszip_dev_clip* dst, int32_t first, int32_t count, void* stream) {
+    static const char* name = "BoxBlur";
+    if (!f || f->kind != F_BOXBLUR) { set_error("BoxBlur: bad filter handle"); return -1; }
+    if (!same_clip_shape(src, f, name) || !same_clip_shape(dst, f, name) || !range_ok(src, first, count, name) || !range_ok(dst, first, count, name)) return -1;
+    if (src->device_index != dst->device_index) { set_error("BoxBlur: clips live on different devices"); return -1; }
+    DeviceCtx* d = device_ctx(src->device_index);
+    if (!d) { set_error("BoxBlur: library not initialised"); return -1; }
+    VSZ_CUDA(cudaSetDevice(d->ordinal));
+    cudaStream_t st = stream ? (cudaStream_t)stream : d->batch_stream;
+    const size_t fs = src->layout.frame_stride;
+    return run_boxblur(f->layout, f->process, src->base + (size_t)first * fs, fs, dst->base + (size_t)first * fs, fs, count,
+                       (int)f->hradius, f->hpasses, (int)f->vradius, f->vpasses, st);
+}
+
+// =========================================================================== Bilateral
+vszip_filter* vszip_bilateral_create(const vszip_video_info* vi, const vszip_video_info* ref_vi, const vszip_bilateral_args* a) {
+    static const char* name = "Bilateral";
+    if (!basic_vi_ok(vi, name)) return nullptr;
+    SampleKind kind;
+    if (!select_kind(*vi, name, false, &kind)) return nullptr;
+    vszip_filter* f = new vszip_filter();
+    auto fail = [&]() { vszip_filter_free(f); return (vszip_filter*)nullptr; };
+    f->kind = F_BILATERAL;
+    f->vi = *vi;
+    f->sample = kind;
+    f->layout = make_layout(*vi, kind);
+    const bool yuv = vi->color_family == VSZIP_CF_YUV;
+    f->hist_len = vi->sample_type == VSZIP_ST_INTEGER ? (1 << vi->bits_per_sample) : 65536;  // hz.getHistLen
+    f->peak = (float)(f->hist_len - 1);
+
+    double sigmaS[3], sigmaR[3];
+    int32_t algorithm[3];
+    uint32_t pbfic[3];
+    for (int i = 0; i < 3; ++i) {  // bilateral.zig:104-125
+        if (i < a->num_sigmaS) sigmaS[i] = a->sigmaS[i];
+        else if (i == 0) sigmaS[0] = 3.0;
+        else if (i == 1 && yuv && vi->sub_sampling_h != 0 && vi->sub_sampling_w != 0)
+            sigmaS[1] = sigmaS[0] / std::sqrt((double)((1u << vi->sub_sampling_h) * (1u << vi->sub_sampling_w)));
+        else sigmaS[i] = sigmaS[i - 1];
+        if (sigmaS[i] < 0) { set_error("Bilateral: Invalid \"sigmaS\" assigned, must be non-negative float number"); return fail(); }
+    }
+    if (!get_array<double, double>(a->sigmaR, a->num_sigmaR, 0.02, 0.0, std::numeric_limits<double>::max(), "sigmaR", name, sigmaR, [](double v) { return v; })) return fail();
+    if (!get_array<int32_t, int64_t>(a->algorithm, a->num_algorithm, 0, 0, 2, "algorithm", name, algorithm, [](int64_t v) { return sat_i32(v); })) return fail();
+    if (!get_array<uint32_t, int64_t>(a->PBFICnum, a->num_PBFICnum, 0u, 0, 256, "PBFICnum", name, pbfic, [](int64_t v) { return sat_u32(v); })) return fail();
+    bool process[3] = {true, true, true};
+    if (!parse_planes(a->planes, a->num_planes, vi->num_planes, name, process)) return fail();
+    for (int i = 0; i < 3; ++i)
+        if (sigmaS[i] == 0 || sigmaR[i] == 0) process[i] = false;
+    for (int i = 0; i < 3; ++i)
+        if (pbfic[i] == 1) { set_error("Bilateral: Invalid \"PBFICnum\" assigned, must be integer ranges in [0,256] except 1"); return fail(); }
+    for (int i = 0; i < 3; ++i) {  // bilateral.zig:147-162
+        if (process[i] && pbfic[i] == 0) {
+            if (sigmaR[i] >= 0.08) pbfic[i] = 4;
+            else if (sigmaR[i] >= 0.015) pbfic[i] = std::min(16u, (uint32_t)std::trunc(4 * 0.08 / sigmaR[i] + 0.5));
+            else pbfic[i] = std::min(32u, (uint32_t)std::trunc(16 * 0.015 / sigmaR[i] + 0.5));
+            if (i > 0 && yuv && (pbfic[i] % 2 == 0) && pbfic[i] < 256) pbfic[i] += 1;
+        }
+    }
+    for (int i = 0; i < 3; ++i) {  // bilateral.zig:164-199
+        BilateralPlane& b = f->bl[i];
+        b.sigmaS = sigmaS[i]; b.sigmaR = sigmaR[i]; b.algorithm = algorithm[i]; b.pbfic = pbfic[i];
+        if (!process[i]) continue;
+        const int orad = std::max((int)std::trunc(sigmaS[i] * 2 + 0.5), 1);
+        b.step = orad < 4 ? 1 : (orad < 8 ? 2 : 3);
+        b.samples = 1;
+        b.radius = 1 + (b.samples - 1) * b.step;
+        while (orad * 2 > (int)b.radius * 3) {
+            b.samples += 1;
+            b.radius = 1 + (b.samples - 1) * b.step;
+            if ((int)b.radius >= orad && b.samples > 2) {
+                b.samples -= 1;
+                b.radius = 1 + (b.samples - 1) * b.step;
+                break;
+            }
+        }
+        if (b.algorithm <= 0)
+            b.algorithm = (b.step == 1) ? 2 : ((sigmaR[i] < 0.08 && b.samples < 5) ? 2 : ((4 * b.samples * b.samples <= 15 * b.pbfic) ? 2 : 1));
+    }
+    for (int i = 0; i < vi->num_planes; ++i) {  // bilateral.zig:201-214
+        if (process[i] && f->bl[i].algorithm == 2) {
+            const uint32_t pw = (uint32_t)vi->width >> (i ? vi->sub_sampling_w : 0);
+            const uint32_t ph = (uint32_t)vi->height >> (i ? vi->sub_sampling_h : 0);
+            if (pw <= 2 * f->bl[i].radius || ph <= 2 * f->bl[i].radius) {
+                set_error("Bilateral: plane too small for the spatial radius derived from sigmaS; lower sigmaS or use a larger clip.");
+                return fail();
+            }
+        }
+    }
+    if (ref_vi && !compare_nodes(*vi, *ref_vi, name)) return fail();
+    for (int i = 0; i < 3; ++i) f->process[i] = process[i] && i < vi->num_planes;
+    f->has_ref = ref_vi != nullptr;
+    for (int i = 0; i < vi->num_planes; ++i) {
+        if (f->process[i] && f->bl[i].algorithm == 1) {
+            set_error("Bilateral: algorithm 1 (PBFIC) is selected for plane %d but only algorithm 2 has a CUDA path; "
+                      "there is no CPU fallback. Pass algorithm=2.", i);
+            return fail();
+        }
+    }
+    // LUTs (src/filters/bilateral.zig:306-334), f64 math rounded to f32, uploaded to every device
+    f->gs_host.resize(3); f->gr_host.resize(3);
+    for (int i = 0; i < vi->num_planes; ++i) {
+        if (!f->process[i]) continue;
+        BilateralPlane& b = f->bl[i];
+        const int upper = (int)b.radius + 1;
+        f->gs_host[i].resize((size_t)upper * upper);
+        for (int y = 0; y < upper; ++y)
+            for (int x = 0; x < upper; ++x)
+                f->gs_host[i][(size_t)y * upper + x] = (float)std::exp((double)(x * x + y * y) / (b.sigmaS * b.sigmaS * -2.0));
+        const double range = (double)f->peak;
+        const uint32_t top = (uint32_t)std::trunc(std::min(range, b.sigmaR * 8.0 * range + 0.5));
+        const double norm = std::sqrt(2.0 * M_PI) * b.sigmaR;
+        std::vector<float>& gr = f->gr_host[i];
+        gr.resize((size_t)f->hist_len);
+        uint32_t j = 0;
+        for (; j <= top && j < (uint32_t)f->hist_len; ++j) {
+            const double xx = ((double)j / range) / b.sigmaR;
+            gr[j] = (float)(std::exp(xx * xx / -2.0) / norm);
+        }
+        const float tail = gr[std::min<uint32_t>(top, (uint32_t)f->hist_len - 1)];
+        for (; j < (uint32_t)f->hist_len; ++j) gr[j] = tail;
+        b.lut_len = (int)std::min<uint32_t>(top + 1, (uint32_t)f->hist_len);
+        b.exact = bilateral_weights_exact(b.lut_len);
+    }
+    return f;
+}
+
+int vszip_bilateral_get_info(const vszip_filter* f, vszip_bilateral_info* o) {
+    if (!f || f->kind != F_BILATERAL) { set_error("Bilateral: bad filter handle"); return -1; }
+    for (int i = 0; i < 3; ++i) {
+        const BilateralPlane& b = f->bl[i];
+        o->sigmaS[i] = b.sigmaS; o->sigmaR[i] = b.sigmaR; o->process[i] = f->process[i]; o->algorithm[i] = b.algorithm;
+        o->PBFICnum[i] = b.pbfic; o->radius[i] = b.radius; o->samples[i] = b.samples; o->step[i] = b.step; o->exact_lut[i] = b.exact;
+    }
+    return 0;
+}
+
+// The weight tables are uploaded to a device the first time the instance runs there (create itself
+// stays GPU-free so argument validation works anywhere).
+static int bilateral_upload(const vszip_filter* cf, int dev_index) {
+    vszip_filter* f = const_cast<vszip_filter*>(cf);
+    std::lock_guard<std::mutex> lk(f->lut_mu);
+    if (f->gr_dev.size() < (size_t)num_devices()) {
+        f->gr_dev.resize(num_devices(), std::vector<float*>(3, nullptr));
+        f->gs_dev.resize(num_devices(), std::vector<float*>(3, nullptr));
+    }
+    for (int i = 0; i < f->vi.num_planes; ++i) {
+        if (!f->process[i] || f->gr_dev[dev_index][i]) continue;
+        const size_t gsb = f->gs_host[i].size() * sizeof(float), grb = f->gr_host[i].size() * sizeof(float);
+        VSZ_CUDA(cudaMalloc((void**)&f->gs_dev[dev_index][i], gsb));
+        VSZ_CUDA(cudaMalloc((void**)&f->gr_dev[dev_index][i], grb));
+        VSZ_CUDA(cudaMemcpy(f->gs_dev[dev_index][i], f->gs_host[i].data(), gsb, cudaMemcpyHostToDevice));
+        VSZ_CUDA(cudaMemcpy(f->gr_dev[dev_index][i], f->gr_host[i].data(), grb, cudaMemcpyHostToDevice));
+    }
+    return 0;
+}
+
+static BilateralLaunch bilateral_launch(const vszip_filter* f, int dev_index) {
+    BilateralLaunch bp{};
+    bp.peak = f->peak;
+    for (int i = 0; i < 3; ++i) {
+        bp.gs[i] = f->gs_dev[dev_index][i]; bp.gr[i] = f->gr_dev[dev_index][i];
+        bp.radius[i] = (int)f->bl[i].radius; bp.step[i] = (int)f->bl[i].step; bp.lut_len[i] = f->bl[i].lut_len;
+        if (f->process[i]) {
+            const double s = (double)f->peak * f->bl[i].sigmaR;
+            bp.c2[i] = (float)(-1.4426950408889634 / (2.0 * s * s));
+            bp.cnorm[i] = (float)(1.0 / (std::sqrt(2.0 * M_PI) * f->bl[i].sigmaR));
+        }
+    }
+    return bp;
+}
+
+static int device_index_of(DeviceCtx* d) {
+    for (int i = 0; i < num_devices(); ++i) if (device_ctx(i) == d) return i;
+    return 0;
+}
+
+int vszip_bilateral_get_frame(const vszip_filter* f, int32_t n, const vszip_frame* src, const vszip_frame* ref, vszip_frame* dst) {
+    if (!f || f->kind != F_BILATERAL) { set_error("Bilateral: bad filter handle"); return -1; }
+    if (f->has_ref != (ref != nullptr)) { set_error("Bilateral: ref frame presence does not match the filter instance"); return -1; }
+    DeviceCtx* d = route(n, "Bilateral");
+    if (!d) return -1;
+    SlotGuard g(d);
+    Slot* s = g.s;
+    VSZ_CUDA(cudaSetDevice(d->ordinal));
+    const size_t bytes = f->layout.frame_stride;
+    if (slot_reserve(d, s, 0, bytes) || slot_reserve(d, s, 2, bytes) || (ref && slot_reserve(d, s, 1, bytes))) return -1;
+    if (stage_in(s, 0, f->layout, src, f->process)) return -1;
+    if (ref && stage_in(s, 1, f->layout, ref, f->process)) return -1;
+    if (bilateral_upload(f, device_index_of(d))) return -1;
+    const BilateralLaunch bp = bilateral_launch(f, device_index_of(d));
+    int rc = run_bilateral(f->layout, f->process, s->dev[0], 0, ref ? s->dev[1] : nullptr, 0, s->dev[2], 0, 1, bp, s->stream);
+    if (rc) return rc;
+    if (stage_out_begin(s, f->layout, f->process)) return -1;
+    VSZ_CUDA(cudaStreamSynchronize(s->stream));
+    stage_out_finish(s, f->layout, dst, f->process);
+    return 0;
+}
+
+int vszip_bilateral_device(const vszip_filter* f, const vszip_dev_clip* src, const vszip_dev_clip* ref, vszip_dev_clip* dst,
+                           int32_t first, int32_t count, void* stream) {
+    static const char* name = "Bilateral";
+    if (!f || f->kind != F_BILATERAL) { set_error("Bilateral: bad filter handle"); return -1; }
+    if (f->has_ref != (ref != nullptr)) { set_error("Bilateral: ref clip presence does not match the filter instance"); return -1; }
+    if (!same_clip_shape(src, f, name) || !same_clip_shape(dst, f, name) || (ref && !same_clip_shape(ref, f, name))) return -1;
+    if (!range_ok(src, first, count, name) || !range_ok(dst, first, count, name) || (ref && !range_ok(ref, first, count, name))) return -1;
+    if (src->device_index != dst->device_index || (ref && ref->device_index != src->device_index)) { set_error("Bilateral: clips live on different devices"); return -1; }
+    DeviceCtx* d = device_ctx(src->device_index);
+    if (!d) { set_error("Bilateral: library not initialised"); return -1; }
+    VSZ_CUDA(cudaSetDevice(d->ordinal));
+    cudaStream_t st = stream ? (cudaStream_t)stream : d->batch_stream;
+    const size_t fs = src->layout.frame_stride;
+    if (bilateral_upload(f, src->device_index)) return -1;
+    const BilateralLaunch bp = bilateral_launch(f, src->device_index);
+    return run_bilateral(f->layout, f->process, src->base + (size_t)first * fs, fs, ref ? ref->base + (size_t)first * fs : nullptr, fs,
+                         dst->base + (size_t)first * fs, fs, count, bp, st);
+}
+
+// =========================================================================== PlaneMinMax
+vszip_filter* vszip_planeminmax_create(const vszip_video_info* vi, const vszip_video_info* clipb_vi, const vszip_planeminmax_args* a) {
+    static const char* name = "PlaneMinMax";
+    if (!basic_vi_ok(vi, name)) return nullptr;
+    SampleKind kind;
+    if (!select_kind(*vi, name, false, &kind)) return nullptr;
+    if (clipb_vi && !compare_nodes(*vi, *clipb_vi, name)) return nullptr;
+    bool process[3] = {true, false, false};
+    if (!parse_planes(a->planes, a->num_planes, vi->num_planes, name, process)) return nullptr;
+    const uint32_t hist_size = vi->sample_type == VSZIP_ST_FLOAT ? 65536u : (1u << vi->bits_per_sample);
+    // getThr (planeminmax.zig:174-192): maxthr is read first
+    const float maxthr = a->has_maxthr ? (float)a->maxthr : 0.0f;
+    if (maxthr < 0 || maxthr > 1) { set_error("PlaneMinMax: maxthr should be a float between 0.0 and 1.0"); return nullptr; }
+    const float minthr = a->has_minthr ? (float)a->minthr : 0.0f;
+    if (minthr < 0 || minthr > 1) { set_error("PlaneMinMax: minthr should be a float between 0.0 and 1.0"); return nullptr; }
+    const bool no_thr = maxthr == 0 && minthr == 0;
+    const bool do_chroma = process[1] || process[2];
+    if (do_chroma && !no_thr && vi->color_family == VSZIP_CF_YUV && vi->sample_type == VSZIP_ST_FLOAT) {
+        set_error("PlaneMinMax: you can't use maxthr/minthr with float chroma, use planes=[0] or maxthr/minthr=0");
+        return nullptr;
+    }
+    vszip_filter* f = new vszip_filter();
+    f->kind = F_PLANEMINMAX;
+    f->vi = *vi;
+    f->sample = kind;
+    f->layout = make_layout(*vi, kind);
+    for (int i = 0; i < 3; ++i) f->process[i] = process[i] && i < vi->num_planes;
+    f->has_ref = clipb_vi != nullptr;
+    f->minthr = minthr; f->maxthr = maxthr; f->hist_size = hist_size; f->no_thr = no_thr;
+    return f;
+}
+
+static void minmax_finalize(const vszip_filter* f, const StatsRaw* raw, vszip_minmax_props* out) {
+    const bool flt = f->sample == K_F16 || f->sample == K_F32;
+    memset(out, 0, sizeof *out);
+    out->is_float = flt; out->has_diff = f->has_ref;
+    const float peakf = (float)(f->hist_size - 1);  // planeminmax.zig:118-119
+    int k = 0;
+    for (int p = 0; p < f->layout.nplanes; ++p) {
+        if (!f->process[p]) continue;
+        const StatsRaw& r = raw[k];
+        out->plane[k] = p;
+        if (f->no_thr) {
+            out->imin[k] = r.bin_min; out->imax[k] = r.bin_max;
+            out->fmin[k] = (double)r.fmin; out->fmax[k] = (double)r.fmax;
+        } else {
+            out->imin[k] = r.bin_min; out->imax[k] = r.bin_max;
+            out->fmin[k] = (double)((float)r.bin_min / 65535.0f);  // src/filters/planeminmax.zig:62-63
+            out->fmax[k] = (double)((float)r.bin_max / 65535.0f);
+        }
+        if (f->has_ref) {
+            const double total = (double)((uint32_t)f->layout.pl[p].w * (uint32_t)f->layout.pl[p].h);
+            out->diff[k] = flt ? r.fdiff / total : (double)r.idiff / total / (double)peakf;
+        }
+        ++k;
+    }
+    out->count = k;
+}
+
+static int processed_planes(const vszip_filter* f) {
+    int k = 0;
+    for (int p = 0; p < f->layout.nplanes; ++p) k += f->process[p] ? 1 : 0;
+    return k;
+}
+
+int vszip_planeminmax_get_frame(const vszip_filter* f, int32_t n, const vszip_frame* a, const vszip_frame* b, vszip_minmax_props* out) {
+    if (!f || f->kind != F_PLANEMINMAX) { set_error("PlaneMinMax: bad filter handle"); return -1; }
+    if (f->has_ref != (b != nullptr)) { set_error("PlaneMinMax: clipb frame presence does not match the filter instance"); return -1; }
+    DeviceCtx* d = route(n, "PlaneMinMax");
+    if (!d) return -1;
+    SlotGuard g(d);
+    Slot* s = g.s;
+    VSZ_CUDA(cudaSetDevice(d->ordinal));
+    const size_t bytes = f->layout.frame_stride;
+    const int np = processed_planes(f);
+    const size_t scratch = stats_scratch_bytes(1, np) + 256;
+    if (slot_reserve(d, s, 0, bytes) || (b && slot_reserve(d, s, 1, bytes)) || slot_reserve(d, s, 2, scratch)) return -1;
+    if (stage_in(s, 0, f->layout, a, f->process)) return -1;
+    if (b && stage_in(s, 1, f->layout, b, f->process)) return -1;
+    StatsRaw* raw_dev = (StatsRaw*)s->dev_small;
+    int rc = run_planeminmax(f->layout, f->process, s->dev[0], 0, b ? s->dev[1] : nullptr, 0, 1, f->no_thr, f->minthr, f->maxthr,
+                             f->hist_size, s->dev[2], raw_dev, s->stream);
+    if (rc) return rc;
+    VSZ_CUDA(cudaMemcpyAsync(s->pin_small, raw_dev, sizeof(StatsRaw) * np, cudaMemcpyDeviceToHost, s->stream));
+    VSZ_CUDA(cudaStreamSynchronize(s->stream));
+    minmax_finalize(f, (const StatsRaw*)s->pin_small, out);
+    return 0;
+}
+
+int vszip_planeminmax_device(const vszip_filter* f, const vszip_dev_clip* a, const vszip_dev_clip* b, int32_t first, int32_t count,
+                             vszip_minmax_props* out, void* stream) {
+    static const char* name = "PlaneMinMax";
+    if (!f || f->kind != F_PLANEMINMAX) { set_error("PlaneMinMax: bad filter handle"); return -1; }
+    if (f->has_ref != (b != nullptr)) { set_error("PlaneMinMax: clipb presence does not match the filter instance"); return -1; }
+    if (!same_clip_shape(a, f, name) || (b && !same_clip_shape(b, f, name)) || !range_ok(a, first, count, name) || (b && !range_ok(b, first, count, name))) return -1;
+    DeviceCtx* d = device_ctx(a->device_index);
+    if (!d) { set_error("PlaneMinMax: library not initialised"); return -1; }
+    VSZ_CUDA(cudaSetDevice(d->ordinal));
+    cudaStream_t st = stream ? (cudaStream_t)stream : d->batch_stream;
+    const int np = processed_planes(f);
+    if (count == 0 || np == 0) return 0;
+    const size_t fs = a->layout.frame_stride;
+    char* scratch = nullptr;
+    const size_t sb = stats_scratch_bytes(count, np), rb = sizeof(StatsRaw) * (size_t)count * np;
+    VSZ_CUDA(cudaMallocAsync((void**)&scratch, sb + rb, st));
+    StatsRaw* raw_dev = (StatsRaw*)(scratch + sb);
+    int rc = run_planeminmax(f->layout, f->process, a->base + (size_t)first * fs, fs, b ? b->base + (size_t)first * fs : nullptr, fs, count,
+                             f->no_thr, f->minthr, f->maxthr, f->hist_size, scratch, raw_dev, st);
+    std::vector<StatsRaw> raw((size_t)count * np);
+    if (!rc && out) {
+        VSZ_CUDA(cudaMemcpyAsync(raw.data(), raw_dev, rb, cudaMemcpyDeviceToHost, st));
+        VSZ_CUDA(cudaStreamSynchronize(st));
+        for (int i = 0; i < count; ++i) minmax_finalize(f, raw.data() + (size_t)i * np, out + i);
+    }
+    VSZ_CUDA(cudaFreeAsync(scratch, st));
+    return rc;
+}
+
+// =========================================================================== PlaneAverage
+vszip_filter* vszip_planeaverage_create(const vszip_video_info* vi, const vszip_video_info* clipb_vi, const vszip_planeaverage_args* a) {
+    static const char* name = "PlaneAverage";
+    if (!basic_vi_ok(vi, name)) return nullptr;
+    if (a->num_exclude < 0 || (a->num_exclude > 0 && !a->exclude)) {  // VapourSynth rejects a missing non-opt argument itself
+        set_error("PlaneAverage: argument exclude is required");
+        return nullptr;
+    }
+    const bool u32 = vi->sample_type == VSZIP_ST_INTEGER && vi->bytes_per_sample == 4;
+    SampleKind kind = K_U16;
+    if (!u32 && !select_kind(*vi, name, true, &kind)) return nullptr;
+    if (clipb_vi && !compare_nodes(*vi, *clipb_vi, name)) return nullptr;
+    bool process[3] = {true, false, false};
+    if (!parse_planes(a->planes, a->num_planes, vi->num_planes, name, process)) return nullptr;
+    if (u32) { set_error("PlaneAverage: exclude is not supported for 32-bit integer clips."); return nullptr; }
+    vszip_filter* f = new vszip_filter();
+    f->kind = F_PLANEAVERAGE;
+    f->vi = *vi;
+    f->sample = kind;
+    f->layout = make_layout(*vi, kind);
+    for (int i = 0; i < 3; ++i) f->process[i] = process[i] && i < vi->num_planes;
+    f->has_ref = clipb_vi != nullptr;
+    f->avg_peak = (float)((1ull << vi->bits_per_sample) - 1ull);  // planeaverage.zig:112
+    for (int i = 0; i < a->num_exclude; ++i) {
+        f->exclude_f.push_back((float)a->exclude[i]);           // planeaverage.zig:122-125
+        f->exclude_i.push_back(sat_i32(a->exclude[i]));         // math.lossyCast(i32, ..)
+    }
+    if (a->num_exclude > 16) { set_error("PlaneAverage: more than 16 exclude values are not supported by the CUDA path"); delete f; return nullptr; }
+    return f;
+}
+
+static void average_finalize(const vszip_filter* f, const StatsRaw* raw, vszip_average_props* out) {
+    const bool flt = f->sample == K_F16 || f->sample == K_F32;
+    memset(out, 0, sizeof *out);
+    out->has_diff = f->has_ref;
+    int k = 0;
+    for (int p = 0; p < f->layout.nplanes; ++p) {
+        if (!f->process[p]) continue;
+        const StatsRaw& r = raw[k];
+        out->plane[k] = p;
+        const uint32_t all = (uint32_t)f->layout.pl[p].w * (uint32_t)f->layout.pl[p].h;
+        const double total = (double)(all - r.excluded);
+        // result() (src/filters/planeaverage.zig:16-24)
+        if (total == 0) out->avg[k] = 0.0;
+        else if (flt) out->avg[k] = r.fsum / total;
+        else out->avg[k] = (double)r.isum / total / (double)f->avg_peak;
+        if (f->has_ref) out->diff[k] = flt ? r.fdiff / (double)all : (double)r.idiff / (double)all / (double)f->avg_peak;
+        ++k;
+    }
+    out->count = k;
+}
+
+int vszip_planeaverage_get_frame(const vszip_filter* f, int32_t n, const vszip_frame* a, const vszip_frame* b, vszip_average_props* out) {
+    if (!f || f->kind != F_PLANEAVERAGE) { set_error("PlaneAverage: bad filter handle"); return -1; }
+    if (f->has_ref != (b != nullptr)) { set_error("PlaneAverage: clipb frame presence does not match the filter instance"); return -1; }
+    DeviceCtx* d = route(n, "PlaneAverage");
+    if (!d) return -1;
+    SlotGuard g(d);
+    Slot* s = g.s;
+    VSZ_CUDA(cudaSetDevice(d->ordinal));
+    const size_t bytes = f->layout.frame_stride;
+    const int np = processed_planes(f);
+    const size_t scratch = stats_scratch_bytes(1, np) + 256;
+    if (slot_reserve(d, s, 0, bytes) || (b && slot_reserve(d, s, 1, bytes)) || slot_reserve(d, s, 2, scratch)) return -1;
+    if (stage_in(s, 0, f->layout, a, f->process)) return -1;
+    if (b && stage_in(s, 1, f->layout, b, f->process)) return -1;
+    StatsRaw* raw_dev = (StatsRaw*)s->dev_small;
+    int rc = run_planeaverage(f->layout, f->process, s->dev[0], 0, b ? s->dev[1] : nullptr, 0, 1, f->exclude_i.data(), f->exclude_f.data(),
+                              (int)f->exclude_i.size(), s->dev[2], raw_dev, s->stream);
+    if (rc) return rc;
+    VSZ_CUDA(cudaMemcpyAsync(s->pin_small, raw_dev, sizeof(StatsRaw) * np, cudaMemcpyDeviceToHost, s->stream));
+    VSZ_CUDA(cudaStreamSynchronize(s->stream));
+    average_finalize(f, (const StatsRaw*)s->pin_small, out);
+    return 0;
+}
+
+int vszip_planeaverage_device(const vszip_filter* f, const vszip_dev_clip* a, const vszip_dev_clip* b, int32_t first, int32_t count,
+                              vszip_average_props* out, void* stream) {
+    static const char* name = "PlaneAverage";
+    if (!f || f->kind != F_PLANEAVERAGE) { set_error("PlaneAverage: bad filter handle"); return -1; }
+    if (f->has_ref != (b != nullptr)) { set_error("PlaneAverage: clipb presence does not match the filter instance"); return -1; }
+    if (!same_clip_shape(a, f, name) || (b && !same_clip_shape(b, f, name)) || !range_ok(a, first, count, name) || (b && !range_ok(b, first, count, name))) return -1;
+    DeviceCtx* d = device_ctx(a->device_index);
+    if (!d) { set_error("PlaneAverage: library not initialised"); return -1; }
+    VSZ_CUDA(cudaSetDevice(d->ordinal));
+    cudaStream_t st = stream ? (cudaStream_t)stream : d->batch_stream;
+    const int np = processed_planes(f);
+    if (count == 0 || np == 0) return 0;
+    const size_t fs = a->layout.frame_stride;
+    char* scratch = nullptr;
+    const size_t sb = stats_scratch_bytes(count, np), rb = sizeof(StatsRaw) * (size_t)count * np;
+    VSZ_CUDA(cudaMallocAsync((void**)&scratch, sb + rb, st));
+    StatsRaw* raw_dev = (StatsRaw*)(scratch + sb);
+    int rc = run_planeaverage(f->layout, f->process, a->base + (size_t)first * fs, fs, b ? b->base + (size_t)first * fs : nullptr, fs, count,
+                              f->exclude_i.data(), f->exclude_f.data(), (int)f->exclude_i.size(), scratch, raw_dev, st);
+    std::vector<StatsRaw> raw((size_t)count * np);
+    if (!rc && out) {
+        VSZ_CUDA(cudaMemcpyAsync(raw.data(), raw_dev, rb, cudaMemcpyDeviceToHost, st));
+        VSZ_CUDA(cudaStreamSynchronize(st));
+        for (int i = 0; i < count; ++i) average_finalize(f, raw.data() + (size_t)i * np, out + i);
+    }
+    VSZ_CUDA(cudaFreeAsync(scratch, st));
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,539 @@
+// planestats_kernels.cu — sm_100a reductions for vszip.PlaneAverage and vszip.PlaneMinMax.
+//
+// Semantics restated from the reference:
+//   PlaneAverage (src/filters/planeaverage.zig:26-84): acc = sum of samples not in `exclude`, count of
+//       excluded samples, optional sum |a-b| over ALL samples (float |a-b| rounded in T).
+//   PlaneMinMax  (src/filters/planeminmax.zig:11-133): raw min/max (no threshold) or a 65536-bin
+//       histogram with two cumulative scans using strict '>' against trunc(total*thr).
+//
+// Design: both are single-read streaming reductions (16-byte loads, warp-shuffle trees, one partial per
+// CTA, combined in CTA order by the last CTA to finish so float sums are run-to-run deterministic).
+// The threshold path never materialises 65536 bins: it is an exact two-level radix select.  Pass 1
+// builds the histogram of the top 8 bits of the bin index, pass 2 re-reads the plane (L2-resident for
+// planes up to ~100 MB) and histograms the remaining low bits of only the two coarse bins that contain
+// the requested ranks; the last CTA of pass 2 resolves the exact bins.  Integer counts are exact, so the
+// result is bit-identical to the reference's full histogram scan.
+#include <cuda_fp16.h>
+
+#include <algorithm>
+
+#include "filter.h"
+
+namespace vsz {
+
+static constexpr int NT = 256;
+static constexpr int MAX_CTAS_PER_PLANE = 512;
+
+struct Partial {
+    unsigned long long isum, idiff;
+    double fsum, fdiff;
+    unsigned int excluded, imin, imax;
+    float fmin, fmax;
+    unsigned int pad;
+};
+
+struct StatsPlane {
+    size_t a_off, b_off;
+    int a_pitch, b_pitch;
+    int w, h;
+    int cta_begin, nctas;
+    unsigned int tmin, tmax;  // trunc(total * thr)
+};
+
+struct StatsJob {
+    const char* a;
+    const char* b;  // nullptr when there is no clipb
+    size_t a_fs, b_fs;
+    int nplanes, ctas_per_frame;
+    StatsPlane pl[3];
+    // scratch
+    Partial* partials;        // [frame][plane][MAX_CTAS_PER_PLANE]
+    unsigned int* counters;   // [frame][plane] completed-CTA counters (two sets: pass1/avg, pass2)
+    unsigned int* coarse;     // [frame][plane][256]
+    unsigned int* fine;       // [frame][plane][2][256]
+    StatsRaw* out;            // [frame][plane]
+    // parameters
+    int nex;
+    int32_t excl_i[16];
+    float excl_f[16];
+    const int32_t* excl_i_more;  // when nex > 16 (device memory)
+    const float* excl_f_more;
+    unsigned int hist_size;
+    int shift;  // fine bits = bin & ((1<<shift)-1); coarse = bin >> shift
+};
+
+__device__ __forceinline__ const StatsPlane& find_plane(const StatsJob& j, int cta, int& k, int& local) {
+    k = j.nplanes - 1;
+    while (k > 0 && cta < j.pl[k].cta_begin) --k;
+    local = cta - j.pl[k].cta_begin;
+    return j.pl[k];
+}
+
+// --------------------------------------------------------------------------- element helpers
+template <typename T> struct El;
+template <> struct El<uint8_t> { static constexpr bool flt = false; static constexpr int PER16 = 16; };
+template <> struct El<uint16_t> { static constexpr bool flt = false; static constexpr int PER16 = 8; };
+template <> struct El<__half> { static constexpr bool flt = true; static constexpr int PER16 = 8; };
+template <> struct El<float> { static constexpr bool flt = true; static constexpr int PER16 = 4; };
+
+template <typename T> __device__ __forceinline__ float as_float(T v) { return (float)v; }
+template <> __device__ __forceinline__ float as_float<__half>(__half v) { return __half2float(v); }
+
+// |a-b| as the reference computes it: integers exactly, floats rounded in T then widened.
+template <typename T> __device__ __forceinline__ double abs_diff(T a, T b, unsigned int& idiff) {
+    if constexpr (El<T>::flt) {
+        if constexpr (sizeof(T) == 2) return (double)fabsf(__half2float(__hsub(a, b)));
+        else return (double)fabsf(__fsub_rn(a, b));
+    } else {
+        idiff += (a > b) ? (unsigned)(a - b) : (unsigned)(b - a);
+        return 0.0;
+    }
+}
+
+// histogram bin of a sample (src/filters/planeminmax.zig:26,33): ints index directly, floats use
+// sat_u16(trunc(f32(v)*65535 + 0.5)) with separate multiply and add.
+template <typename T> __device__ __forceinline__ unsigned int bin_of(T v) {
+    if constexpr (El<T>::flt) {
+        const float f = __fadd_rn(__fmul_rn(as_float<T>(v), 65535.0f), 0.5f);
+        if (!(f > 0.0f)) return 0u;  // NaN and <= 0
+        if (f >= 65535.0f) return 65535u;
+        return (unsigned int)f;
+    } else {
+        return (unsigned int)v;
+    }
+}
+
+// Visits every sample of rows [y0, y1) of a plane with 16-byte loads (+ scalar tail), calling
+// fn(a_sample, b_sample) where b_sample == a_sample if there is no second clip.
+template <typename T, bool HAS_B, class F>
+__device__ __forceinline__ void for_each_sample(const char* a, int a_pitch, const char* b, int b_pitch, int w, int y0, int y1, F fn) {
+    constexpr int V = El<T>::PER16;
+    const int nvec = w / V;
+    for (int y = y0; y < y1; ++y) {
+        const uint4* ar = reinterpret_cast<const uint4*>(a + (size_t)y * a_pitch);
+        const uint4* br = HAS_B ? reinterpret_cast<const uint4*>(b + (size_t)y * b_pitch) : nullptr;
+        for (int v = threadIdx.x; v < nvec; v += NT) {
+            const uint4 av = __ldg(ar + v);
+            uint4 bv = av;
+            if constexpr (HAS_B) bv = __ldg(br + v);
+            const T* ae = reinterpret_cast<const T*>(&av);
+            const T* be = reinterpret_cast<const T*>(&bv);
+#pragma unroll
+            for (int i = 0; i < V; ++i) fn(ae[i], be[i]);
+        }
+        const int x = nvec * V + threadIdx.x;
+        if (x < w) {
+            const T av = reinterpret_cast<const T*>(ar)[x];
+            const T bv = HAS_B ? reinterpret_cast<const T*>(br)[x] : av;
+            fn(av, bv);
+        }
+    }
+}
+
+__device__ __forceinline__ void rows_of_cta(const StatsPlane& p, int local, int& y0, int& y1) {
+    const int per = (p.h + p.nctas - 1) / p.nctas;
+    y0 = min(local * per, p.h);
+    y1 = min(y0 + per, p.h);
+}
+
+// --------------------------------------------------------------------------- block reduction + last-CTA combine
+__device__ __forceinline__ void warp_reduce(Partial& p) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        p.isum += __shfl_down_sync(0xffffffffu, p.isum, o);
+        p.idiff += __shfl_down_sync(0xffffffffu, p.idiff, o);
+        p.fsum += __shfl_down_sync(0xffffffffu, p.fsum, o);
+        p.fdiff += __shfl_down_sync(0xffffffffu, p.fdiff, o);
+        p.excluded += __shfl_down_sync(0xffffffffu, p.excluded, o);
+        p.imin = min(p.imin, __shfl_down_sync(0xffffffffu, p.imin, o));
+        p.imax = max(p.imax, __shfl_down_sync(0xffffffffu, p.imax, o));
+        p.fmin = fminf(p.fmin, __shfl_down_sync(0xffffffffu, p.fmin, o));
+        p.fmax = fmaxf(p.fmax, __shfl_down_sync(0xffffffffu, p.fmax, o));
+    }
+}
+
+__device__ __forceinline__ void combine(Partial& a, const Partial& b) {
+    a.isum += b.isum; a.idiff += b.idiff; a.fsum += b.fsum; a.fdiff += b.fdiff; a.excluded += b.excluded;
+    a.imin = min(a.imin, b.imin); a.imax = max(a.imax, b.imax);
+    a.fmin = fminf(a.fmin, b.fmin); a.fmax = fmaxf(a.fmax, b.fmax);
+}
+
+__device__ __forceinline__ Partial empty_partial() {
+    Partial p;
+    p.isum = p.idiff = 0ull; p.fsum = p.fdiff = 0.0; p.excluded = 0u;
+    p.imin = 0xffffffffu; p.imax = 0u;
+    p.fmin = __int_as_float(0x7f800000); p.fmax = __int_as_float(0xff800000);
+    p.pad = 0;
+    return p;
+}
+
+// Reduces `mine` over the CTA, stores the CTA partial and returns true in exactly one CTA per
+// (frame, plane): the last one to finish, with `total` = all partials combined in CTA order.
+__device__ bool block_finish(const StatsJob& j, int frame, int k, int local, int nctas, unsigned int* counter, Partial mine,
+                             Partial& total) {
+    __shared__ Partial s_part[NT / 32];
+    __shared__ bool s_last;
+    warp_reduce(mine);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) s_part[warp] = mine;
+    __syncthreads();
+    Partial* slots = j.partials + ((size_t)frame * j.nplanes + k) * MAX_CTAS_PER_PLANE;
+    if (threadIdx.x == 0) {
+        Partial t = s_part[0];
+        for (int i = 1; i < NT / 32; ++i) combine(t, s_part[i]);
+        slots[local] = t;
+        __threadfence();
+        const unsigned int done = atomicAdd(counter, 1u);
+        s_last = (done == (unsigned)nctas - 1u);
+    }
+    __syncthreads();
+    if (!s_last) return false;
+    __threadfence();
+    if (threadIdx.x == 0) {
+        Partial t = slots[0];
+        for (int i = 1; i < nctas; ++i) combine(t, slots[i]);
+        total = t;
+    }
+    return true;
+}
+
+// --------------------------------------------------------------------------- PlaneAverage / no-threshold PlaneMinMax
+template <typename T, bool HAS_B, bool AVERAGE>
+__global__ void __launch_bounds__(NT) stats_kernel(const StatsJob j) {
+    int k, local;
+    const StatsPlane& p = find_plane(j, blockIdx.x, k, local);
+    const int frame = blockIdx.y;
+    const char* a = j.a + (size_t)frame * j.a_fs + p.a_off;
+    const char* b = HAS_B ? j.b + (size_t)frame * j.b_fs + p.b_off : nullptr;
+    int y0, y1;
+    rows_of_cta(p, local, y0, y1);
+
+    Partial acc = empty_partial();
+    unsigned int isum32 = 0, idiff32 = 0;  // flushed to 64 bit once per row
+    const int nex = j.nex;
+    for (int y = y0; y < y1; ++y) {
+        for_each_sample<T, HAS_B>(a, p.a_pitch, b, p.b_pitch, p.w, y, y + 1, [&](T av, T bv) {
+            if constexpr (AVERAGE) {
+                bool found = false;
+                if constexpr (El<T>::flt) {
+                    const float f = as_float<T>(av);
+                    for (int i = 0; i < nex; ++i) found |= (f == (i < 16 ? j.excl_f[i] : j.excl_f_more[i - 16]));
+                    if (found) acc.excluded += 1; else acc.fsum += (double)f;
+                } else {
+                    const int32_t iv = (int32_t)av;
+                    for (int i = 0; i < nex; ++i) found |= (iv == (i < 16 ? j.excl_i[i] : j.excl_i_more[i - 16]));
+                    if (found) acc.excluded += 1; else isum32 += (unsigned)av;
+                }
+            } else {
+                if constexpr (El<T>::flt) {
+                    const float f = as_float<T>(av);
+                    acc.fmin = fminf(acc.fmin, f); acc.fmax = fmaxf(acc.fmax, f);
+                } else {
+                    acc.imin = min(acc.imin, (unsigned)av); acc.imax = max(acc.imax, (unsigned)av);
+                }
+            }
+            if constexpr (HAS_B) acc.fdiff += abs_diff<T>(av, bv, idiff32);
+        });
+        // a thread sees at most ceil(w/NT)+1 samples per row; with w <= 65536 u32 cannot overflow
+        acc.isum += isum32; acc.idiff += idiff32;
+        isum32 = idiff32 = 0;
+    }
+    Partial total;
+    if (block_finish(j, frame, k, local, p.nctas, j.counters + (size_t)frame * j.nplanes + k, acc, total) && threadIdx.x == 0) {
+        StatsRaw r{};
+        r.isum = total.isum; r.idiff = total.idiff; r.fsum = total.fsum; r.fdiff = total.fdiff;
+        r.excluded = total.excluded; r.bin_min = total.imin; r.bin_max = total.imax;
+        r.fmin = total.fmin; r.fmax = total.fmax;
+        j.out[(size_t)frame * j.nplanes + k] = r;
+    }
+}
+
+// --------------------------------------------------------------------------- threshold path, pass 1
+// warp-private 256-bin histograms in shared memory; a warp whose 32 lanes all hit the same bin
+// (flat areas, blank clips) issues one atomic of 32 instead of 32 serialised ones.
+__device__ __forceinline__ void hist_add(unsigned int* h, unsigned int key, bool valid) {
+    const unsigned int active = __ballot_sync(0xffffffffu, valid);
+    if (active == 0u) return;
+    const int leader = __ffs(active) - 1;
+    const unsigned int k0 = __shfl_sync(0xffffffffu, key, leader);
+    const unsigned int same = __ballot_sync(0xffffffffu, valid && key == k0);
+    if (same == active) {
+        if ((int)(threadIdx.x & 31) == leader) atomicAdd(&h[k0], (unsigned)__popc(active));
+    } else if (valid) {
+        atomicAdd(&h[key], 1u);
+    }
+}
+
+template <typename T, bool HAS_B>
+__global__ void __launch_bounds__(NT) hist_coarse_kernel(const StatsJob j) {
+    __shared__ unsigned int s_hist[NT / 32][256];
+    int k, local;
+    const StatsPlane& p = find_plane(j, blockIdx.x, k, local);
+    const int frame = blockIdx.y;
+    const char* a = j.a + (size_t)frame * j.a_fs + p.a_off;
+    const char* b = HAS_B ? j.b + (size_t)frame * j.b_fs + p.b_off : nullptr;
+    int y0, y1;
+    rows_of_cta(p, local, y0, y1);
+    for (int i = threadIdx.x; i < (NT / 32) * 256; i += NT) (&s_hist[0][0])[i] = 0u;
+    __syncthreads();
+
+    unsigned int* mine = s_hist[threadIdx.x >> 5];
+    Partial acc = empty_partial();
+    unsigned int idiff32 = 0;
+    const unsigned int hist_size = j.hist_size;
+    const int shift = j.shift;
+    // whole warps walk the rows together so the ballot in hist_add is always convergent
+    constexpr int V = El<T>::PER16;
+    const int nvec = p.w / V;
+    const int nvec_pad = (nvec + NT - 1) / NT * NT;
+    for (int y = y0; y < y1; ++y) {
+        const uint4* ar = reinterpret_cast<const uint4*>(a + (size_t)y * p.a_pitch);
+        const uint4* br = HAS_B ? reinterpret_cast<const uint4*>(b + (size_t)y * p.b_pitch) : nullptr;
+        for (int v = threadIdx.x; v < nvec_pad; v += NT) {
+            const bool ok = v < nvec;
+            uint4 av = make_uint4(0, 0, 0, 0), bv = av;
+            if (ok) { av = __ldg(ar + v); if constexpr (HAS_B) bv = __ldg(br + v); }
+            const T* ae = reinterpret_cast<const T*>(&av);
+            const T* be = reinterpret_cast<const T*>(&bv);
+#pragma unroll
+            for (int i = 0; i < V; ++i) {
+                const unsigned int bin = bin_of<T>(ae[i]);
+                hist_add(mine, bin >> shift, ok && bin < hist_size);
+                if constexpr (HAS_B) { if (ok) acc.fdiff += abs_diff<T>(ae[i], be[i], idiff32); }
+            }
+        }
+        {
+            const int x = nvec * V + (int)threadIdx.x;
+            const bool ok = x < p.w;
+            if (__any_sync(0xffffffffu, ok)) {
+                T av{}, bv{};
+                if (ok) { av = reinterpret_cast<const T*>(ar)[x]; if constexpr (HAS_B) bv = reinterpret_cast<const T*>(br)[x]; }
+                const unsigned int bin = bin_of<T>(av);
+                hist_add(mine, bin >> shift, ok && bin < hist_size);
+                if constexpr (HAS_B) { if (ok) acc.fdiff += abs_diff<T>(av, bv, idiff32); }
+            }
+        }
+        acc.idiff += idiff32; idiff32 = 0;
+    }
+    __syncthreads();
+    unsigned int* coarse = j.coarse + ((size_t)frame * j.nplanes + k) * 256;
+    for (int i = threadIdx.x; i < 256; i += NT) {
+        unsigned int s = 0;
+#pragma unroll
+        for (int w = 0; w < NT / 32; ++w) s += s_hist[w][i];
+        if (s) atomicAdd(&coarse[i], s);
+    }
+    if constexpr (HAS_B) {
+        Partial total;
+        if (block_finish(j, frame, k, local, p.nctas, j.counters + (size_t)frame * j.nplanes + k, acc, total) && threadIdx.x == 0) {
+            StatsRaw& r = j.out[(size_t)frame * j.nplanes + k];
+            r.idiff = total.idiff; r.fdiff = total.fdiff;
+        }
+    }
+}
+
+// Finds, from a 256-entry histogram with `base` samples already counted before it, the first entry
+// (scanning upward if UP, downward otherwise) at which the running count exceeds `thr`.
+// Returns the entry index or -1; *before = running count before that entry.  Single thread.
+template <bool UP>
+__device__ int scan_rank(const unsigned int* h, int n, unsigned int base, unsigned int thr, unsigned int* before) {
+    unsigned int c = base;
+    for (int s = 0; s < n; ++s) {
+        const int i = UP ? s : n - 1 - s;
+        const unsigned int next = c + h[i];
+        if (next > thr) { *before = c; return i; }
+        c = next;
+    }
+    *before = c;
+    return -1;
+}
+
+// --------------------------------------------------------------------------- threshold path, pass 2
+template <typename T>
+__global__ void __launch_bounds__(NT) hist_fine_kernel(const StatsJob j) {
+    __shared__ unsigned int s_fine[2][256];
+    __shared__ int s_bmin, s_bmax;
+    __shared__ unsigned int s_cmin, s_cmax;
+    __shared__ bool s_last;
+    int k, local;
+    const StatsPlane& p = find_plane(j, blockIdx.x, k, local);
+    const int frame = blockIdx.y;
+    const char* a = j.a + (size_t)frame * j.a_fs + p.a_off;
+    const unsigned int* coarse = j.coarse + ((size_t)frame * j.nplanes + k) * 256;
+    const int shift = j.shift;
+    const int ncoarse = (int)((j.hist_size + (1u << shift) - 1) >> shift);
+    const int nfine = 1 << shift;
+    for (int i = threadIdx.x; i < 512; i += NT) (&s_fine[0][0])[i] = 0u;
+    if (threadIdx.x == 0) s_bmin = scan_rank<true>(coarse, ncoarse, 0u, p.tmin, &s_cmin);
+    if (threadIdx.x == 32) s_bmax = scan_rank<false>(coarse, ncoarse, 0u, p.tmax, &s_cmax);
+    __syncthreads();
+    const int bmin = s_bmin, bmax = s_bmax;
+
+    if (shift > 0 && (bmin >= 0 || bmax >= 0)) {
+        int y0, y1;
+        rows_of_cta(p, local, y0, y1);
+        const unsigned int fmask = (unsigned)nfine - 1u;
+        for_each_sample<T, false>(a, p.a_pitch, nullptr, 0, p.w, y0, y1, [&](T av, T) {
+            const unsigned int bin = bin_of<T>(av);
+            const int c = (int)(bin >> shift);
+            if (bin < j.hist_size) {
+                if (c == bmin) atomicAdd(&s_fine[0][bin & fmask], 1u);
+                if (c == bmax) atomicAdd(&s_fine[1][bin & fmask], 1u);
+            }
+        });
+    }
+    __syncthreads();
+    unsigned int* fine = j.fine + ((size_t)frame * j.nplanes + k) * 512;
+    if (shift > 0) {
+        for (int i = threadIdx.x; i < 512; i += NT) {
+            const unsigned int s = (&s_fine[0][0])[i];
+            if (s) atomicAdd(&fine[i], s);
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int done = atomicAdd(j.counters + (size_t)(gridDim.y + frame) * j.nplanes + k, 1u);
+        s_last = (done == (unsigned)p.nctas - 1u);
+    }
+    __syncthreads();
+    if (!s_last || threadIdx.x != 0) return;
+    __threadfence();
+    const unsigned int peak = j.hist_size - 1u;
+    unsigned int lo = peak, hi = 0u, dummy;
+    if (bmin >= 0) {
+        if (shift == 0) lo = (unsigned)bmin;
+        else {
+            const int f = scan_rank<true>(const_cast<const unsigned int*>(fine), nfine, s_cmin, p.tmin, &dummy);
+            lo = ((unsigned)bmin << shift) + (unsigned)f;  // f >= 0: the coarse bin is known to cross the rank
+        }
+    }
+    if (bmax >= 0) {
+        if (shift == 0) hi = (unsigned)bmax;
+        else {
+            const int f = scan_rank<false>(const_cast<const unsigned int*>(fine + 256), nfine, s_cmax, p.tmax, &dummy);
+            hi = ((unsigned)bmax << shift) + (unsigned)f;
+        }
+    }
+    StatsRaw& r = j.out[(size_t)frame * j.nplanes + k];
+    r.bin_min = lo; r.bin_max = hi;
+}
+
+// =========================================================================== host launchers
+// scratch layout (all zeroed before each call):
+//   counters  [2][count][np] u32 | coarse [count][np][256] u32 | fine [count][np][512] u32 | partials
+static size_t align256(size_t v) { return (v + 255) / 256 * 256; }
+size_t stats_scratch_bytes(int count, int np) {
+    const size_t n = (size_t)count * np;
+    return align256(2 * n * 4) + align256(n * 256 * 4) + align256(n * 512 * 4) + align256(n * MAX_CTAS_PER_PLANE * sizeof(Partial));
+}
+
+static StatsJob make_job(const FrameLayout& l, const bool mask[3], const char* a, size_t a_fs, const char* b, size_t b_fs, int count,
+                         void* scratch, StatsRaw* out, size_t* zero_bytes) {
+    StatsJob j{};
+    j.a = a; j.b = b; j.a_fs = a_fs; j.b_fs = b_fs;
+    int cta = 0, k = 0;
+    for (int p = 0; p < l.nplanes; ++p) {
+        if (!mask[p]) continue;
+        StatsPlane& s = j.pl[k++];
+        s.a_off = s.b_off = l.pl[p].offset;
+        s.a_pitch = s.b_pitch = l.pl[p].pitch;
+        s.w = l.pl[p].w; s.h = l.pl[p].h;
+        // ~32K samples per CTA keeps >= 2 waves on 148 SMs for a single 4K plane and bounds the
+        // per-thread u32 partial sums
+        const long long px = (long long)s.w * s.h;
+        int n = (int)std::min<long long>(MAX_CTAS_PER_PLANE, std::max<long long>(1, (px + 32767) / 32768));
+        n = std::min(n, s.h);
+        s.cta_begin = cta; s.nctas = n;
+        cta += n;
+    }
+    j.nplanes = k; j.ctas_per_frame = cta;
+    const size_t n = (size_t)count * k;
+    char* sp = (char*)scratch;
+    j.counters = (unsigned int*)sp; sp += align256(2 * n * 4);
+    j.coarse = (unsigned int*)sp; sp += align256(n * 256 * 4);
+    j.fine = (unsigned int*)sp; sp += align256(n * 512 * 4);
+    *zero_bytes = (size_t)(sp - (char*)scratch);
+    j.partials = (Partial*)sp;
+    j.out = out;
+    return j;
+}
+
+template <typename T>
+static int launch_minmax_t(StatsJob j, int count, bool no_thr, bool has_b, cudaStream_t st) {
+    for (int f0 = 0; f0 < count; f0 += 32768) {
+        const int nf = std::min(32768, count - f0);
+        if (f0 != 0) { set_error("PlaneMinMax: batches above 32768 frames are not supported"); return -2; }
+        const dim3 grid(j.ctas_per_frame, nf);
+        if (no_thr) {
+            if (has_b) stats_kernel<T, true, false><<<grid, NT, 0, st>>>(j);
+            else stats_kernel<T, false, false><<<grid, NT, 0, st>>>(j);
+            count_launch();
+        } else {
+            if (has_b) hist_coarse_kernel<T, true><<<grid, NT, 0, st>>>(j);
+            else hist_coarse_kernel<T, false><<<grid, NT, 0, st>>>(j);
+            hist_fine_kernel<T><<<grid, NT, 0, st>>>(j);
+            count_launch(2);
+        }
+    }
+    VSZ_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int run_planeminmax(const FrameLayout& l, const bool mask[3], const char* a, size_t a_fs, const char* b, size_t b_fs, int count,
+                    bool no_thr, float minthr, float maxthr, uint32_t hist_size, void* scratch, StatsRaw* out_dev, cudaStream_t st) {
+    size_t zero = 0;
+    StatsJob j = make_job(l, mask, a, a_fs, b, b_fs, count, scratch, out_dev, &zero);
+    if (j.ctas_per_frame == 0) return 0;
+    VSZ_CUDA(cudaMemsetAsync(scratch, 0, zero, st));
+    VSZ_CUDA(cudaMemsetAsync(out_dev, 0, sizeof(StatsRaw) * (size_t)count * j.nplanes, st));
+    j.hist_size = hist_size;
+    int bits = 0;
+    while ((1u << bits) < hist_size) ++bits;
+    j.shift = bits > 8 ? bits - 8 : 0;
+    for (int k = 0; k < j.nplanes; ++k) {
+        const double total = (double)((uint32_t)j.pl[k].w * (uint32_t)j.pl[k].h);
+        j.pl[k].tmin = (unsigned int)(total * (double)minthr);  // trunc (src/filters/planeminmax.zig:40-41)
+        j.pl[k].tmax = (unsigned int)(total * (double)maxthr);
+    }
+    const bool has_b = b != nullptr;
+    switch (l.kind) {
+        case K_U8: return launch_minmax_t<uint8_t>(j, count, no_thr, has_b, st);
+        case K_U16: return launch_minmax_t<uint16_t>(j, count, no_thr, has_b, st);
+        case K_F16: return launch_minmax_t<__half>(j, count, no_thr, has_b, st);
+        case K_F32: return launch_minmax_t<float>(j, count, no_thr, has_b, st);
+    }
+    return -1;
+}
+
+template <typename T>
+static int launch_avg_t(const StatsJob& j, int count, bool has_b, cudaStream_t st) {
+    if (count > 32768) { set_error("PlaneAverage: batches above 32768 frames are not supported"); return -2; }
+    const dim3 grid(j.ctas_per_frame, count);
+    if (has_b) stats_kernel<T, true, true><<<grid, NT, 0, st>>>(j);
+    else stats_kernel<T, false, true><<<grid, NT, 0, st>>>(j);
+    count_launch();
+    VSZ_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int run_planeaverage(const FrameLayout& l, const bool mask[3], const char* a, size_t a_fs, const char* b, size_t b_fs, int count,
+                     const int32_t* excl_i, const float* excl_f, int nex, void* scratch, StatsRaw* out_dev, cudaStream_t st) {
+    size_t zero = 0;
+    StatsJob j = make_job(l, mask, a, a_fs, b, b_fs, count, scratch, out_dev, &zero);
+    if (j.ctas_per_frame == 0) return 0;
+    if (nex > 16) { set_error("PlaneAverage: more than 16 exclude values are not supported by the CUDA path"); return -2; }
+    VSZ_CUDA(cudaMemsetAsync(scratch, 0, zero, st));
+    j.nex = nex;
+    for (int i = 0; i < nex; ++i) { j.excl_i[i] = excl_i[i]; j.excl_f[i] = excl_f[i]; }
+    const bool has_b = b != nullptr;
+    switch (l.kind) {
+        case K_U8: return launch_avg_t<uint8_t>(j, count, has_b, st);
+        case K_U16: return launch_avg_t<uint16_t>(j, count, has_b, st);
+        case K_F16: return launch_avg_t<__half>(j, count, has_b, st);
+        case K_F32: return launch_avg_t<float>(j, count, has_b, st);
+    }
+    return -1;
+}
+
+}  // namespace vsz

@@ -1,0 +1,358 @@
+// runtime.cu — per-GPU contexts (frame pool, pinned staging, one stream per in-flight request),
+// device-resident clips, the noise generator, and the small C-ABI utility entry points.
+#include <cuda_fp16.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "common.h"
+
+namespace vsz {
+
+static thread_local std::string t_error;
+std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    t_error = buf;
+}
+
+// --------------------------------------------------------------------------- formats
+bool select_kind(const vszip_video_info& vi, const char* name, bool enable_u32, SampleKind* out) {
+    if (vi.sample_type == VSZIP_ST_INTEGER) {
+        if (vi.bytes_per_sample == 1) { *out = K_U8; return true; }
+        if (vi.bytes_per_sample == 2) { *out = K_U16; return true; }
+        (void)enable_u32;  // the only caller passing true (PlaneAverage) rejects U32 right after
+        set_error("%s: not supported Int format.", name);
+        return false;
+    }
+    if (vi.bytes_per_sample == 2) { *out = K_F16; return true; }
+    if (vi.bytes_per_sample == 4) { *out = K_F32; return true; }
+    set_error("%s: not supported Float format.", name);
+    return false;
+}
+
+FrameLayout make_layout(const vszip_video_info& vi, SampleKind kind) {
+    FrameLayout l{};
+    l.nplanes = vi.num_planes;
+    l.bps = vi.bytes_per_sample;
+    l.kind = kind;
+    l.bits = vi.bits_per_sample;
+    size_t off = 0;
+    for (int p = 0; p < l.nplanes; ++p) {
+        const int sw = p ? vi.sub_sampling_w : 0, sh = p ? vi.sub_sampling_h : 0;
+        l.pl[p].w = vi.width >> sw;
+        l.pl[p].h = vi.height >> sh;
+        l.pl[p].pitch = (int)(((size_t)l.pl[p].w * l.bps + 127) / 128 * 128);
+        l.pl[p].offset = off;
+        off += (size_t)l.pl[p].pitch * l.pl[p].h;
+        off = (off + 255) / 256 * 256;
+    }
+    l.frame_stride = off;
+    return l;
+}
+
+size_t layout_algorithmic_bytes(const FrameLayout& l) {
+    size_t s = 0;
+    for (int p = 0; p < l.nplanes; ++p) s += (size_t)l.pl[p].w * l.pl[p].h * l.bps;
+    return s;
+}
+
+// --------------------------------------------------------------------------- contexts
+static std::mutex g_init_mu;
+static std::vector<DeviceCtx*> g_devs;
+static constexpr int kSlotsPerDevice = 8;
+
+Slot* DeviceCtx::acquire() {
+    std::unique_lock<std::mutex> lk(mu);
+    cv.wait(lk, [&] { return !idle.empty(); });
+    Slot* s = idle.back();
+    idle.pop_back();
+    return s;
+}
+
+void DeviceCtx::release(Slot* s) {
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        idle.push_back(s);
+    }
+    cv.notify_one();
+}
+
+int num_devices() { return (int)g_devs.size(); }
+DeviceCtx* device_ctx(int index) { return (index >= 0 && index < (int)g_devs.size()) ? g_devs[index] : nullptr; }
+DeviceCtx* device_for_frame(int32_t n) {
+    if (g_devs.empty()) return nullptr;
+    const int k = (int)g_devs.size();
+    return g_devs[((n % k) + k) % k];
+}
+
+int slot_reserve(DeviceCtx* d, Slot* s, int which, size_t bytes) {
+    if (s->cap[which] >= bytes) return 0;
+    VSZ_CUDA(cudaSetDevice(d->ordinal));
+    VSZ_CUDA(cudaStreamSynchronize(s->stream));
+    if (s->pin[which]) cudaFreeHost(s->pin[which]);
+    if (s->dev[which]) cudaFree(s->dev[which]);
+    s->pin[which] = s->dev[which] = nullptr;
+    s->cap[which] = 0;
+    VSZ_CUDA(cudaHostAlloc((void**)&s->pin[which], bytes, cudaHostAllocDefault));
+    VSZ_CUDA(cudaMalloc((void**)&s->dev[which], bytes));
+    s->cap[which] = bytes;
+    return 0;
+}
+
+static void copy_rows(char* dst, ptrdiff_t dpitch, const char* src, ptrdiff_t spitch, size_t row_bytes, int rows) {
+    if (dpitch == spitch && (size_t)spitch == row_bytes) {
+        memcpy(dst, src, row_bytes * (size_t)rows);
+        return;
+    }
+    for (int y = 0; y < rows; ++y) memcpy(dst + dpitch * y, src + spitch * y, row_bytes);
+}
+
+int stage_in(Slot* s, int which, const FrameLayout& l, const vszip_frame* host, const bool mask[3]) {
+    for (int p = 0; p < l.nplanes; ++p) {
+        if (!mask[p]) continue;
+        const PlaneGeom& g = l.pl[p];
+        const size_t row_bytes = (size_t)g.w * l.bps;
+        // pageable VapourSynth memory -> pinned staging (same layout as the device frame)
+        copy_rows(s->pin[which] + g.offset, g.pitch, (const char*)host->data[p], host->stride[p], row_bytes, g.h);
+        VSZ_CUDA(cudaMemcpyAsync(s->dev[which] + g.offset, s->pin[which] + g.offset, (size_t)g.pitch * g.h,
+                                 cudaMemcpyHostToDevice, s->stream));
+    }
+    return 0;
+}
+
+int stage_out_begin(Slot* s, const FrameLayout& l, const bool mask[3]) {
+    for (int p = 0; p < l.nplanes; ++p) {
+        if (!mask[p]) continue;
+        const PlaneGeom& g = l.pl[p];
+        VSZ_CUDA(cudaMemcpyAsync(s->pin[2] + g.offset, s->dev[2] + g.offset, (size_t)g.pitch * g.h,
+                                 cudaMemcpyDeviceToHost, s->stream));
+    }
+    return 0;
+}
+
+void stage_out_finish(Slot* s, const FrameLayout& l, vszip_frame* host, const bool mask[3]) {
+    for (int p = 0; p < l.nplanes; ++p) {
+        if (!mask[p]) continue;
+        const PlaneGeom& g = l.pl[p];
+        copy_rows((char*)host->data[p], host->stride[p], s->pin[2] + g.offset, g.pitch, (size_t)g.w * l.bps, g.h);
+    }
+}
+
+// --------------------------------------------------------------------------- noise generator
+__device__ __forceinline__ uint32_t mix64to32(uint64_t z) {  // splitmix64 finaliser
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return (uint32_t)(z >> 32);
+}
+
+template <typename T>
+__global__ void noise_kernel(char* base, size_t frame_stride, size_t plane_off, int pitch, int w, int h, int plane,
+                             uint64_t seed, int first_frame_no, int kind, int bits, int chroma_centered) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    const int f = blockIdx.z;
+    if (x >= w) return;
+    const uint64_t key = (seed * 0x100000001B3ull) ^ ((uint64_t)(uint32_t)(first_frame_no + f) << 40) ^
+                         ((uint64_t)plane << 36) ^ ((uint64_t)y << 18) ^ (uint64_t)x;
+    const uint32_t u = mix64to32(key);
+    T* row = reinterpret_cast<T*>(base + (size_t)f * frame_stride + plane_off + (size_t)y * pitch);
+    if constexpr (std::is_same<T, uint8_t>::value || std::is_same<T, uint16_t>::value) {
+        row[x] = (T)(u >> (32 - bits));
+    } else {
+        float v = (float)(u >> 8) * (1.0f / 16777216.0f);  // [0,1)
+        if (chroma_centered) v -= 0.5f;
+        if constexpr (std::is_same<T, __half>::value) row[x] = __float2half_rn(v);
+        else row[x] = v;
+    }
+}
+
+}  // namespace vsz
+
+using namespace vsz;
+
+// =========================================================================== C ABI: runtime
+extern "C" {
+
+int vszip_cuda_abi_version(void) { return VSZIP_CUDA_ABI_VERSION; }
+const char* vszip_cuda_last_error(void) { return t_error.c_str(); }
+uint64_t vszip_cuda_kernel_launches(void) { return g_launches.load(); }
+int vszip_cuda_device_count(void) { return num_devices(); }
+
+int vszip_cuda_init(const int32_t* device_ids, int32_t n) {
+    std::lock_guard<std::mutex> lk(g_init_mu);
+    if (!g_devs.empty()) return (int)g_devs.size();
+    int visible = 0;
+    cudaError_t e = cudaGetDeviceCount(&visible);
+    if (e != cudaSuccess || visible <= 0) {
+        set_error("vszip_cuda_init: no CUDA device available (%s); there is no CPU fallback",
+                  e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        return -1;
+    }
+    std::vector<int> ids;
+    if (n <= 0 || device_ids == nullptr) for (int i = 0; i < visible; ++i) ids.push_back(i);
+    else for (int i = 0; i < n; ++i) ids.push_back(device_ids[i]);
+    for (int id : ids) {
+        if (id < 0 || id >= visible) { set_error("vszip_cuda_init: device ordinal %d out of range (0..%d)", id, visible - 1); return -1; }
+        cudaDeviceProp prop;
+        VSZ_CUDA(cudaGetDeviceProperties(&prop, id));
+        if (prop.major < 10) {
+            set_error("vszip_cuda_init: device %d (%s, sm_%d%d) is not a Blackwell sm_100 GPU; kernels are built for sm_100a only",
+                      id, prop.name, prop.major, prop.minor);
+            return -1;
+        }
+    }
+    for (int id : ids) {
+        VSZ_CUDA(cudaSetDevice(id));
+        DeviceCtx* d = new DeviceCtx();
+        d->ordinal = id;
+        VSZ_CUDA(cudaDeviceGetAttribute(&d->sm_count, cudaDevAttrMultiProcessorCount, id));
+        VSZ_CUDA(cudaStreamCreateWithFlags(&d->batch_stream, cudaStreamNonBlocking));
+        cudaMemPool_t pool;  // keep stream-ordered scratch cached between calls
+        if (cudaDeviceGetDefaultMemPool(&pool, id) == cudaSuccess) {
+            uint64_t thr = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+        for (int i = 0; i < kSlotsPerDevice; ++i) {
+            Slot* s = new Slot();
+            VSZ_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+            VSZ_CUDA(cudaHostAlloc(&s->pin_small, 4096, cudaHostAllocDefault));
+            VSZ_CUDA(cudaMalloc(&s->dev_small, 1 << 16));
+            d->all.push_back(s);
+            d->idle.push_back(s);
+        }
+        g_devs.push_back(d);
+    }
+    return (int)g_devs.size();
+}
+
+void vszip_cuda_shutdown(void) {
+    std::lock_guard<std::mutex> lk(g_init_mu);
+    for (DeviceCtx* d : g_devs) {
+        cudaSetDevice(d->ordinal);
+        cudaDeviceSynchronize();
+        for (Slot* s : d->all) {
+            for (int i = 0; i < 3; ++i) { if (s->pin[i]) cudaFreeHost(s->pin[i]); if (s->dev[i]) cudaFree(s->dev[i]); }
+            if (s->pin_small) cudaFreeHost(s->pin_small);
+            if (s->dev_small) cudaFree(s->dev_small);
+            cudaStreamDestroy(s->stream);
+            delete s;
+        }
+        cudaStreamDestroy(d->batch_stream);
+        delete d;
+    }
+    g_devs.clear();
+}
+
+int vszip_cuda_stream_sync(int32_t device, void* stream) {
+    DeviceCtx* d = device_ctx(device);
+    if (!d) { set_error("vszip_cuda_stream_sync: bad device index %d", device); return -1; }
+    VSZ_CUDA(cudaSetDevice(d->ordinal));
+    VSZ_CUDA(cudaStreamSynchronize(stream ? (cudaStream_t)stream : d->batch_stream));
+    return 0;
+}
+
+// --------------------------------------------------------------------------- device clips
+vszip_dev_clip* vszip_dev_clip_alloc(const vszip_video_info* vi, int32_t num_frames, int32_t device) {
+    DeviceCtx* d = device_ctx(device);
+    if (!d) { set_error("vszip_dev_clip_alloc: library not initialised or bad device index %d", device); return nullptr; }
+    SampleKind kind;
+    if (!select_kind(*vi, "vszip_dev_clip_alloc", false, &kind)) return nullptr;
+    if (num_frames <= 0 || vi->width <= 0 || vi->height <= 0 || vi->num_planes < 1 || vi->num_planes > 3) {
+        set_error("vszip_dev_clip_alloc: bad geometry");
+        return nullptr;
+    }
+    vszip_dev_clip* c = new vszip_dev_clip();
+    c->device_index = device;
+    c->ordinal = d->ordinal;
+    c->vi = *vi;
+    c->layout = make_layout(*vi, kind);
+    c->num_frames = num_frames;
+    if (cudaSetDevice(d->ordinal) != cudaSuccess ||
+        cudaMalloc((void**)&c->base, c->layout.frame_stride * (size_t)num_frames) != cudaSuccess) {
+        set_error("vszip_dev_clip_alloc: cudaMalloc of %zu bytes failed", c->layout.frame_stride * (size_t)num_frames);
+        delete c;
+        return nullptr;
+    }
+    // padding bytes are never read as pixels, but keep them defined
+    cudaMemset(c->base, 0, c->layout.frame_stride * (size_t)num_frames);
+    return c;
+}
+
+void vszip_dev_clip_free(vszip_dev_clip* c) {
+    if (!c) return;
+    cudaSetDevice(c->ordinal);
+    cudaFree(c->base);
+    delete c;
+}
+
+size_t vszip_dev_clip_frame_bytes(const vszip_dev_clip* c) { return layout_algorithmic_bytes(c->layout); }
+
+void* vszip_dev_clip_plane_ptr(const vszip_dev_clip* c, int32_t frame, int32_t plane, ptrdiff_t* pitch) {
+    if (frame < 0 || frame >= c->num_frames || plane < 0 || plane >= c->layout.nplanes) return nullptr;
+    if (pitch) *pitch = c->layout.pl[plane].pitch;
+    return c->base + (size_t)frame * c->layout.frame_stride + c->layout.pl[plane].offset;
+}
+
+int vszip_dev_clip_upload(vszip_dev_clip* c, int32_t frame, const vszip_frame* host) {
+    if (frame < 0 || frame >= c->num_frames) { set_error("vszip_dev_clip_upload: frame out of range"); return -1; }
+    VSZ_CUDA(cudaSetDevice(c->ordinal));
+    for (int p = 0; p < c->layout.nplanes; ++p) {
+        const PlaneGeom& g = c->layout.pl[p];
+        VSZ_CUDA(cudaMemcpy2D(c->base + (size_t)frame * c->layout.frame_stride + g.offset, g.pitch, host->data[p],
+                              host->stride[p], (size_t)g.w * c->layout.bps, g.h, cudaMemcpyHostToDevice));
+    }
+    return 0;
+}
+
+int vszip_dev_clip_download(const vszip_dev_clip* c, int32_t frame, vszip_frame* host) {
+    if (frame < 0 || frame >= c->num_frames) { set_error("vszip_dev_clip_download: frame out of range"); return -1; }
+    VSZ_CUDA(cudaSetDevice(c->ordinal));
+    VSZ_CUDA(cudaDeviceSynchronize());
+    for (int p = 0; p < c->layout.nplanes; ++p) {
+        const PlaneGeom& g = c->layout.pl[p];
+        VSZ_CUDA(cudaMemcpy2D(host->data[p], host->stride[p], c->base + (size_t)frame * c->layout.frame_stride + g.offset,
+                              g.pitch, (size_t)g.w * c->layout.bps, g.h, cudaMemcpyDeviceToHost));
+    }
+    return 0;
+}
+
+int vszip_dev_clip_fill_noise(vszip_dev_clip* c, uint64_t seed, int32_t first_frame_no) {
+    DeviceCtx* d = device_ctx(c->device_index);
+    if (!d) { set_error("vszip_dev_clip_fill_noise: library not initialised"); return -1; }
+    VSZ_CUDA(cudaSetDevice(c->ordinal));
+    const FrameLayout& l = c->layout;
+    for (int p = 0; p < l.nplanes; ++p) {
+        const PlaneGeom& g = l.pl[p];
+        const dim3 grid((g.w + 255) / 256, g.h, 1);
+        const int centered = (p > 0 && c->vi.color_family == VSZIP_CF_YUV) ? 1 : 0;
+        // grid.z is limited to 65535 frames per launch
+        for (int f0 = 0; f0 < c->num_frames; f0 += 32768) {
+            dim3 gz = grid;
+            gz.z = (unsigned)std::min(32768, c->num_frames - f0);
+            char* base = c->base + (size_t)f0 * l.frame_stride;
+            switch (l.kind) {
+                case K_U8: noise_kernel<uint8_t><<<gz, 256, 0, d->batch_stream>>>(base, l.frame_stride, g.offset, g.pitch, g.w, g.h, p, seed, first_frame_no + f0, l.kind, l.bits, centered); break;
+                case K_U16: noise_kernel<uint16_t><<<gz, 256, 0, d->batch_stream>>>(base, l.frame_stride, g.offset, g.pitch, g.w, g.h, p, seed, first_frame_no + f0, l.kind, l.bits, centered); break;
+                case K_F16: noise_kernel<__half><<<gz, 256, 0, d->batch_stream>>>(base, l.frame_stride, g.offset, g.pitch, g.w, g.h, p, seed, first_frame_no + f0, l.kind, l.bits, centered); break;
+                case K_F32: noise_kernel<float><<<gz, 256, 0, d->batch_stream>>>(base, l.frame_stride, g.offset, g.pitch, g.w, g.h, p, seed, first_frame_no + f0, l.kind, l.bits, centered); break;
+            }
+            count_launch();
+        }
+    }
+    VSZ_CUDA(cudaGetLastError());
+    VSZ_CUDA(cudaStreamSynchronize(d->batch_stream));
+    return 0;
+}
+
+}  // extern "C"
