@@ -1,0 +1,38 @@
+"""Small driver for ncu captures: runs one filter over a device-resident noise batch a few times.
+usage: python scripts/prof_run.py boxblur|boxblur_ct|bilateral|minmax|average [frames] [reps]"""
+import sys
+from pathlib import Path
+
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+import vapoursynth_zip_b200 as vz
+
+what = sys.argv[1] if len(sys.argv) > 1 else "boxblur"
+frames = int(sys.argv[2]) if len(sys.argv) > 2 else 64
+reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+vz.core.init([0])
+if what in ("minmax", "average"):
+    fmt, w, h = "GRAY16", 3840, 2160
+else:
+    fmt, w, h = "YUV420P16", 1920, 1080
+src = vz.DeviceClip(fmt, w, h, frames)
+dst = vz.DeviceClip(fmt, w, h, frames)
+src.fill_noise(seed=1234)
+if what == "boxblur":
+    f = vz.BoxBlurFilter(src.info(), hradius=13, hpasses=5, vradius=13, vpasses=5)
+    run = lambda: f.run_device(src, dst)
+elif what == "boxblur_ct":
+    f = vz.BoxBlurFilter(src.info(), hradius=13, hpasses=1, vradius=13, vpasses=1)
+    run = lambda: f.run_device(src, dst)
+elif what == "bilateral":
+    f = vz.BilateralFilter(src.info(), sigmaS=2, sigmaR=2)
+    run = lambda: f.run_device(src, dst)
+elif what == "minmax":
+    f = vz.PlaneMinMaxFilter(src.info(), minthr=0.1, maxthr=0.1)
+    run = lambda: f.run_device(src)
+else:
+    f = vz.PlaneAverageFilter(src.info(), exclude=[0, 32768])
+    run = lambda: f.run_device(src)
+for _ in range(reps):
+    run()
+vz.core.sync()
+print("done", what, frames, reps, vz.core.kernel_launches)

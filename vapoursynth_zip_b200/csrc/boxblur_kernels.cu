@@ -151,72 +151,100 @@ struct StageOps {
 };
 
 // --------------------------------------------------------------------------- the per-thread pipeline
-// ring layout: word index ((slot * P + q) * NT + tid): stage offsets are compile-time immediates.
+// Skewed schedule: stage p (1..P) works at time t on position x = t - p*D, D = r+1.  Its operands are
+// what stage p-1 published one step earlier: a = v_{p-1}(t-1) (position x+r) and b = the ring entry that
+// publication displaced (position x-r-1, written 2r+1 steps before).  Both are carried in registers, so
+// within one step all P stages (x NL packed lines) are independent instruction chains.
+//
+// Edges cost nothing in the steady state because the mirrors are materialised in the rings:
+//   low edge : when stage p starts (x = 0) it seeds its state from positions 0..r of ring p-1 and writes
+//              the mirrored samples into the ring slots of the virtual positions -r..-1, so the b operands
+//              of x = 1..r come out of the ordinary exchange;
+//   high edge: after its last real sample a stage keeps publishing r mirrored samples (virtual positions
+//              n..n+r-1, read back from its own ring), so the a operands of x >= n-r are ordinary too.
+// Idle or drained stages just compute on don't-care values.  Ring layout: word ((slot*P + q)*NT + tid),
+// slot = t mod (2r+1) shared by all stages, so stage offsets are compile-time immediates.
 template <typename T, int P, int MODE, int NT>
 struct LinePipe {
     using Ops = StageOps<T, MODE>;
     using Acc = typename Px<T>::Acc;
     static constexpr int NL = Px<T>::NL;
+    static constexpr int SLOT_WORDS = P * NT;
 
     Acc S[P][NL];
-    uint32_t* ring;  // &ring_base[tid]
-    int n;
+    uint32_t va[P], vb[P];  // operands of stage q+1 for the next step
+    uint32_t* ring;         // &ring_base[tid]
+    int n, D;               // line length, stage delay r+1
     AxisParams ap;
 
-    __device__ __forceinline__ uint32_t& cell(int slot, int q) { return ring[(slot * P + q) * NT]; }
-    __device__ __forceinline__ int slot_of(int pos, int q) const { return (pos + q * ap.r) % ap.ring; }
-
-    // all stages strictly interior: r < x_p < n - r for every p.  `slot` = t mod ring.
-    __device__ __forceinline__ uint32_t step_fast(int slot, uint32_t v) {
-        uint32_t* base = ring + slot * (P * NT);
+    __device__ __forceinline__ void reset() {
 #pragma unroll
         for (int q = 0; q < P; ++q) {
-            const uint32_t old = base[q * NT];
-            base[q * NT] = v;
-            v = Ops::update(S[q], v, old, ap);
+            va[q] = 0u; vb[q] = 0u;
+#pragma unroll
+            for (int l = 0; l < NL; ++l) S[q][l] = Acc(0);
         }
-        return v;
+    }
+    __device__ __forceinline__ int lag() const { return P * D; }
+    __device__ __forceinline__ int fast_begin() const { return P * D + 1; }  // first t with every stage at x >= 1
+    __device__ __forceinline__ uint32_t& cell(int slot, int q) { return ring[(slot * P + q) * NT]; }
+    // slot k steps behind `slot` (0 <= k <= ring)
+    __device__ __forceinline__ int back(int slot, int k) const { const int s = slot - k; return s < 0 ? s + ap.ring : s; }
+    // steady state, t in [fast_begin, n).  `cur` = ring + (t mod ring) * SLOT_WORDS.
+    // Returns stage P's output for position t - P*D.
+    __device__ __forceinline__ uint32_t step_fast(uint32_t* cur, uint32_t v_in) {
+        uint32_t nv[P];
+#pragma unroll
+        for (int q = 0; q < P; ++q) nv[q] = Ops::update(S[q], va[q], vb[q], ap);
+#pragma unroll
+        for (int q = 0; q < P; ++q) {
+            const uint32_t v = (q == 0) ? v_in : nv[q - 1];
+            vb[q] = cur[q * NT];
+            cur[q * NT] = v;
+            va[q] = v;
+        }
+        return nv[P - 1];
     }
 
-    // any t in [0, n + P*r): handles start-up, mirrored edges and drain.  Returns true when the last
-    // stage produced position t - P*r (value in `out`).
-    __device__ __forceinline__ bool step_edge(int t, int slot, uint32_t v_in, uint32_t& out) {
-        bool act_prev = t < n;  // "stage 0" = the input stream
-        uint32_t v = v_in;
+    // any t: also seeds stages that start at this step and publishes mirrored tails.  v_in must be the
+    // input sample for time t (ignored once t >= n).  The result is meaningful iff 0 <= t - P*D < n.
+    __device__ __forceinline__ uint32_t step_edge(int t, int slot, uint32_t* cur, uint32_t v_in) {
+        uint32_t nv[P];
+        const int r = ap.r;
 #pragma unroll
         for (int q = 0; q < P; ++q) {
-            uint32_t old = 0;
-            if (act_prev) {  // stage q publishes its value of this step into its delay ring
-                old = cell(slot, q);
-                cell(slot, q) = v;
-            }
-            const int x = t - (q + 1) * ap.r;  // position of stage q+1
-            const bool act = (x >= 0) && (x < n);
-            if (act) {
-                if (x == 0) {
-                    Ops::init(S[q], ap, [&](int pos) { return cell(slot_of(pos, q), q); });
-                    if constexpr (MODE == MODE_CTV) {
-                        v = Ops::emit(S[q], ap);
-                    } else {
-                        const uint32_t c = cell(slot_of(ap.r, q), q);
-                        v = Ops::update(S[q], c, c, ap);  // the reference's x = 0 step adds in[r] - in[r]
-                    }
-                } else {
-                    uint32_t a, b;
-                    if constexpr (MODE == MODE_CTV) {
-                        a = (x + ap.r < n) ? v : cell(slot_of(x - 1, q), q);
-                        b = (x <= ap.r) ? cell(slot_of(ap.r - x + 1, q), q) : (act_prev ? old : cell(slot, q));
-                    } else {
-                        a = (x + ap.r < n) ? v : cell(slot_of(2 * n - ap.r - x - 1, q), q);
-                        b = (x <= ap.r) ? cell(slot_of(ap.r - x, q), q) : (act_prev ? old : cell(slot, q));
-                    }
-                    v = Ops::update(S[q], a, b, ap);
+            const int x = t - (q + 1) * D;  // position of stage q+1
+            if (x == 0) {
+                // ring q holds positions -r..r of stage q; position p sits (r - p + 1) slots behind slot(t)
+                Ops::init(S[q], ap, [&](int pos) { return cell(back(slot, r - pos + 1), q); });
+                for (int k = 1; k <= r; ++k) {  // virtual position -k: SYM -> k-1, reflect-101 (comptime V) -> k
+                    const int from = (MODE == MODE_CTV) ? k : k - 1;
+                    cell(back(slot, r + k + 1), q) = cell(back(slot, r - from + 1), q);
                 }
+                if constexpr (MODE == MODE_CTV) {
+                    nv[q] = Ops::emit(S[q], ap);
+                } else {
+                    const uint32_t c = cell(back(slot, 1), q);
+                    nv[q] = Ops::update(S[q], c, c, ap);  // the reference's x = 0 step adds in[r] - in[r]
+                }
+            } else {
+                nv[q] = Ops::update(S[q], va[q], vb[q], ap);
             }
-            act_prev = act;
         }
-        out = v;
-        return act_prev;
+#pragma unroll
+        for (int q = 0; q < P; ++q) {
+            uint32_t v = (q == 0) ? v_in : nv[q - 1];
+            const int y = t - q * D;  // position stage q publishes now
+            if (y >= n && y < n + r) {
+                // mirrored tail, re-read from the stage's own ring (never from global memory: the kernels run
+                // in place).  SYM: position 2n-1-y; comptime V (R101q): position y-r-1.
+                v = cell(back(slot, (MODE == MODE_CTV) ? 1 + r : 1 + 2 * (y - n)), q);
+            }
+            vb[q] = cur[q * NT];
+            cur[q * NT] = v;
+            va[q] = v;
+        }
+        return nv[P - 1];
     }
 };
 
@@ -232,6 +260,7 @@ template <typename T, int P, int MODE, int NT>
 __global__ void __launch_bounds__(NT) blur_v_kernel(const BatchJob job, const AxisParams ap) {
     extern __shared__ uint32_t smem[];
     constexpr int NL = Px<T>::NL;
+    using Pipe = LinePipe<T, P, MODE, NT>;
     int local;
     const PlaneJob& pj = find_plane(job, blockIdx.x, local);
     const int g = local * NT + threadIdx.x;  // 32-bit column group
@@ -240,57 +269,56 @@ __global__ void __launch_bounds__(NT) blur_v_kernel(const BatchJob job, const Ax
     char* dst = job.dst + (size_t)blockIdx.y * job.dst_fs + pj.dst_off + (size_t)g * 4;
     const int sp = pj.src_pitch, dp = pj.dst_pitch;
 
-    LinePipe<T, P, MODE, NT> pipe;
+    Pipe pipe;
     pipe.ring = smem + threadIdx.x;
     pipe.n = pj.h;
     pipe.ap = ap;
-    const int n = pj.h, lag = P * ap.r, total = n + lag;
-    int t_lo = lag + ap.r + 1, t_hi = n;
-    if (t_lo >= t_hi) { t_lo = total; t_hi = total; }
+    pipe.D = ap.r + 1;
+    pipe.reset();
+    const int n = pj.h, lag = pipe.lag(), total = n + lag;
+    const int t_fast = min(pipe.fast_begin(), n);
 
     int slot = 0;
-    auto load = [&](int t) { return *reinterpret_cast<const uint32_t*>(src + (size_t)t * sp); };
+    uint32_t* cur = pipe.ring;
+    auto load = [&](int y) { return *reinterpret_cast<const uint32_t*>(src + (size_t)y * sp); };
     auto store = [&](int x, uint32_t v) { *reinterpret_cast<uint32_t*>(dst + (size_t)x * dp) = v; };
-    auto bump = [&]() { slot = (slot + 1 == ap.ring) ? 0 : slot + 1; };
+    auto bump = [&]() {
+        ++slot; cur += Pipe::SLOT_WORDS;
+        if (slot == ap.ring) { slot = 0; cur = pipe.ring; }
+    };
+    auto edge = [&](int t) {
+        const uint32_t o = pipe.step_edge(t, slot, cur, load(min(t, n - 1)));
+        const int x = t - lag;
+        if (x >= 0 && x < n) store(x, o);
+        bump();
+    };
 
     int t = 0;
-    for (; t < t_lo; ++t) {
-        uint32_t o;
-        const uint32_t v = (t < n) ? load(t) : 0u;
-        if (pipe.step_edge(t, slot, v, o)) store(t - lag, o);
-        bump();
-    }
-    // steady state: 4 rows per iteration, next rows' loads issued before the dependent math
-    constexpr int U = 4;
-    if (t < t_hi) {
+    for (; t < t_fast; ++t) edge(t);
+    // steady state: U rows per iteration; the loads of the next U rows are in flight during the math
+    constexpr int U = 8;
+    if (t < n) {
         uint32_t nxt[U];
 #pragma unroll
         for (int i = 0; i < U; ++i) nxt[i] = load(min(t + i, n - 1));
-        for (; t + U <= t_hi; t += U) {
-            uint32_t cur[U];
+        for (; t + U <= n; t += U) {
+            uint32_t now[U];
 #pragma unroll
-            for (int i = 0; i < U; ++i) cur[i] = nxt[i];
+            for (int i = 0; i < U; ++i) now[i] = nxt[i];
 #pragma unroll
             for (int i = 0; i < U; ++i) nxt[i] = load(min(t + U + i, n - 1));
 #pragma unroll
             for (int i = 0; i < U; ++i) {
-                const uint32_t o = pipe.step_fast(slot, cur[i]);
-                store(t + i - lag, o);
+                store(t + i - lag, pipe.step_fast(cur, now[i]));
                 bump();
             }
         }
-        for (; t < t_hi; ++t) {
-            const uint32_t o = pipe.step_fast(slot, load(t));
-            store(t - lag, o);
+        for (; t < n; ++t) {
+            store(t - lag, pipe.step_fast(cur, load(t)));
             bump();
         }
     }
-    for (; t < total; ++t) {
-        uint32_t o;
-        const uint32_t v = (t < n) ? load(t) : 0u;
-        if (pipe.step_edge(t, slot, v, o)) store(t - lag, o);
-        bump();
-    }
+    for (; t < total; ++t) edge(t);
 }
 
 // --------------------------------------------------------------------------- H: lines are rows
@@ -310,6 +338,7 @@ template <typename T, int P, int NT>
 __global__ void __launch_bounds__(NT) blur_h_kernel(const BatchJob job, const AxisParams ap) {
     extern __shared__ uint32_t smem[];
     using TL = HTile<T, NT>;
+    using Pipe = LinePipe<T, P, MODE_RT, NT>;
     constexpr int NL = Px<T>::NL;
     constexpr int ROWS = NT * NL;
     constexpr int NWARP = NT / 32;
@@ -327,16 +356,18 @@ __global__ void __launch_bounds__(NT) blur_h_kernel(const BatchJob job, const Ax
     T* in_t = reinterpret_cast<T*>(in_tile);
     T* out_t = reinterpret_cast<T*>(out_tile);
 
-    LinePipe<T, P, MODE_RT, NT> pipe;
+    Pipe pipe;
     pipe.ring = ring + threadIdx.x;
     pipe.n = pj.w;
     pipe.ap = ap;
-    const int n = pj.w, lag = P * ap.r, total = n + lag;
-    int t_lo = lag + ap.r + 1, t_hi = n;
-    if (t_lo >= t_hi) { t_lo = total; t_hi = total; }
+    pipe.D = ap.r + 1;
+    pipe.reset();
+    const int n = pj.w, lag = pipe.lag(), total = n + lag;
+    const int t_fast = min(pipe.fast_begin(), n);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int slot = 0;
+    uint32_t* cur = pipe.ring;
     int flushed = 0;  // output positions [0, flushed) are already in global memory
     const int nchunks = (total + TL::CH - 1) / TL::CH;
 
@@ -356,11 +387,12 @@ __global__ void __launch_bounds__(NT) blur_h_kernel(const BatchJob job, const Ax
         for (int t = t0; t < t1; ++t) {
             const uint32_t v = in_tile[(t - t0) * TL::PITCH_W + threadIdx.x];
             uint32_t o;
-            bool have;
-            if (t >= t_lo && t < t_hi) { o = pipe.step_fast(slot, v); have = true; }
-            else have = pipe.step_edge(t, slot, v, o);
-            if (have) out_tile[((t - lag) & (TL::OUT - 1)) * TL::PITCH_W + threadIdx.x] = o;
-            slot = (slot + 1 == ap.ring) ? 0 : slot + 1;
+            if (t >= t_fast && t < n) o = pipe.step_fast(cur, v);
+            else o = pipe.step_edge(t, slot, cur, v);
+            const int x = t - lag;
+            if (x >= 0 && x < n) out_tile[(x & (TL::OUT - 1)) * TL::PITCH_W + threadIdx.x] = o;
+            ++slot; cur += Pipe::SLOT_WORDS;
+            if (slot == ap.ring) { slot = 0; cur = pipe.ring; }
         }
         __syncthreads();
         // ---- flush every complete 32-position output block (and the tail at the very end)
