@@ -173,42 +173,65 @@ struct LinePipe {
 
     Acc S[P][NL];
     uint32_t va[P], vb[P];  // operands of stage q+1 for the next step
+    uint32_t pa[P], pb[P];  // ring words of slot(t) and slot(t+1), fetched two / one step(s) ahead of their exchange
     uint32_t* ring;         // &ring_base[tid]
+    uint32_t* cur;          // ring + slot(t) * SLOT_WORDS
+    uint32_t* cur2;         // ring + slot(t+2) * SLOT_WORDS
+    int slot;               // t mod (2r+1)
     int n, D;               // line length, stage delay r+1
     AxisParams ap;
 
-    __device__ __forceinline__ void reset() {
+    __device__ __forceinline__ void start(uint32_t* ring_, int n_, const AxisParams& ap_) {
+        ring = ring_; n = n_; ap = ap_; D = ap_.r + 1;
+        slot = 0; cur = ring; cur2 = ring + 2 * SLOT_WORDS;  // ring >= 3 slots
 #pragma unroll
         for (int q = 0; q < P; ++q) {
-            va[q] = 0u; vb[q] = 0u;
+            va[q] = vb[q] = pa[q] = pb[q] = 0u;
 #pragma unroll
             for (int l = 0; l < NL; ++l) S[q][l] = Acc(0);
         }
     }
     __device__ __forceinline__ int lag() const { return P * D; }
     __device__ __forceinline__ int fast_begin() const { return P * D + 1; }  // first t with every stage at x >= 1
-    __device__ __forceinline__ uint32_t& cell(int slot, int q) { return ring[(slot * P + q) * NT]; }
-    // slot k steps behind `slot` (0 <= k <= ring)
-    __device__ __forceinline__ int back(int slot, int k) const { const int s = slot - k; return s < 0 ? s + ap.ring : s; }
-    // steady state, t in [fast_begin, n).  `cur` = ring + (t mod ring) * SLOT_WORDS.
-    // Returns stage P's output for position t - P*D.
-    __device__ __forceinline__ uint32_t step_fast(uint32_t* cur, uint32_t v_in) {
+    __device__ __forceinline__ uint32_t& cell(int s, int q) { return ring[(s * P + q) * NT]; }
+    // slot k steps behind slot(t) (0 <= k <= ring)
+    __device__ __forceinline__ int back(int k) const { const int s = slot - k; return s < 0 ? s + ap.ring : s; }
+    __device__ __forceinline__ void advance() {
+        ++slot; cur += SLOT_WORDS;
+        if (slot == ap.ring) { slot = 0; cur = ring; }
+        cur2 += SLOT_WORDS;
+        if (cur2 == ring + ap.ring * SLOT_WORDS) cur2 = ring;
+    }
+
+    // publish v as stage q's value of this step: exchange with the ring word of slot(t) (already in pa[q],
+    // loaded two steps ago so no shared-memory latency sits on the critical path) and keep the look-ahead going.
+    __device__ __forceinline__ void publish(int q, uint32_t v) {
+        vb[q] = pa[q];
+        va[q] = v;
+        cur[q * NT] = v;
+    }
+    __device__ __forceinline__ void rotate(int q) {
+        pa[q] = pb[q];
+        pb[q] = cur2[q * NT];
+    }
+
+    // steady state, t in [fast_begin, n).  Returns stage P's output for position t - P*D.
+    __device__ __forceinline__ uint32_t step_fast(uint32_t v_in) {
         uint32_t nv[P];
 #pragma unroll
         for (int q = 0; q < P; ++q) nv[q] = Ops::update(S[q], va[q], vb[q], ap);
 #pragma unroll
         for (int q = 0; q < P; ++q) {
-            const uint32_t v = (q == 0) ? v_in : nv[q - 1];
-            vb[q] = cur[q * NT];
-            cur[q * NT] = v;
-            va[q] = v;
+            publish(q, (q == 0) ? v_in : nv[q - 1]);
+            rotate(q);
         }
+        advance();
         return nv[P - 1];
     }
 
-    // any t: also seeds stages that start at this step and publishes mirrored tails.  v_in must be the
-    // input sample for time t (ignored once t >= n).  The result is meaningful iff 0 <= t - P*D < n.
-    __device__ __forceinline__ uint32_t step_edge(int t, int slot, uint32_t* cur, uint32_t v_in) {
+    // any t: also seeds stages that start at this step and publishes mirrored tails.  v_in is the input
+    // sample for time t (ignored once t >= n).  The result is meaningful iff 0 <= t - P*D < n.
+    __device__ __forceinline__ uint32_t step_edge(int t, uint32_t v_in) {
         uint32_t nv[P];
         const int r = ap.r;
 #pragma unroll
@@ -216,34 +239,41 @@ struct LinePipe {
             const int x = t - (q + 1) * D;  // position of stage q+1
             if (x == 0) {
                 // ring q holds positions -r..r of stage q; position p sits (r - p + 1) slots behind slot(t)
-                Ops::init(S[q], ap, [&](int pos) { return cell(back(slot, r - pos + 1), q); });
+                Ops::init(S[q], ap, [&](int pos) { return cell(back(r - pos + 1), q); });
                 for (int k = 1; k <= r; ++k) {  // virtual position -k: SYM -> k-1, reflect-101 (comptime V) -> k
                     const int from = (MODE == MODE_CTV) ? k : k - 1;
-                    cell(back(slot, r + k + 1), q) = cell(back(slot, r - from + 1), q);
+                    cell(back(r + k + 1), q) = cell(back(r - from + 1), q);
                 }
+                // the seeding rewrote slot(t) and slot(t+1) of ring q: refresh the look-ahead registers
+                pa[q] = cell(slot, q);
+                pb[q] = cell(slot + 1 == ap.ring ? 0 : slot + 1, q);
                 if constexpr (MODE == MODE_CTV) {
                     nv[q] = Ops::emit(S[q], ap);
                 } else {
-                    const uint32_t c = cell(back(slot, 1), q);
+                    const uint32_t c = cell(back(1), q);
                     nv[q] = Ops::update(S[q], c, c, ap);  // the reference's x = 0 step adds in[r] - in[r]
                 }
-            } else {
+            } else if (x > 0 && x < n) {
                 nv[q] = Ops::update(S[q], va[q], vb[q], ap);
+            } else {
+                nv[q] = 0u;  // not started yet / already drained: nothing to compute
             }
         }
 #pragma unroll
         for (int q = 0; q < P; ++q) {
-            uint32_t v = (q == 0) ? v_in : nv[q - 1];
             const int y = t - q * D;  // position stage q publishes now
-            if (y >= n && y < n + r) {
-                // mirrored tail, re-read from the stage's own ring (never from global memory: the kernels run
-                // in place).  SYM: position 2n-1-y; comptime V (R101q): position y-r-1.
-                v = cell(back(slot, (MODE == MODE_CTV) ? 1 + r : 1 + 2 * (y - n)), q);
+            if (y >= 0 && y < n + r) {
+                uint32_t v = (q == 0) ? v_in : nv[q - 1];
+                if (y >= n) {
+                    // mirrored tail, re-read from the stage's own ring (never from global memory: the kernels
+                    // run in place).  SYM: position 2n-1-y; comptime V (R101q): position y-r-1.
+                    v = cell(back((MODE == MODE_CTV) ? 1 + r : 1 + 2 * (y - n)), q);
+                }
+                publish(q, v);
             }
-            vb[q] = cur[q * NT];
-            cur[q * NT] = v;
-            va[q] = v;
+            rotate(q);
         }
+        advance();
         return nv[P - 1];
     }
 };
@@ -255,12 +285,23 @@ __device__ __forceinline__ const PlaneJob& find_plane(const BatchJob& b, int cta
     return b.pl[k];
 }
 
+// 4-byte asynchronous global->shared copies (LDGSTS): their completion is tracked by commit groups, not
+// by the register scoreboards the ring traffic uses, so deep input prefetch never stalls the math.
+__device__ __forceinline__ void cp_async4(uint32_t* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
 // --------------------------------------------------------------------------- V: lines are columns
+template <int NT> struct VStage { static constexpr int AHEAD = 8, SLOTS = 16, WORDS = SLOTS * NT; };
+
 template <typename T, int P, int MODE, int NT>
 __global__ void __launch_bounds__(NT) blur_v_kernel(const BatchJob job, const AxisParams ap) {
     extern __shared__ uint32_t smem[];
     constexpr int NL = Px<T>::NL;
     using Pipe = LinePipe<T, P, MODE, NT>;
+    using ST = VStage<NT>;
     int local;
     const PlaneJob& pj = find_plane(job, blockIdx.x, local);
     const int g = local * NT + threadIdx.x;  // 32-bit column group
@@ -269,56 +310,61 @@ __global__ void __launch_bounds__(NT) blur_v_kernel(const BatchJob job, const Ax
     char* dst = job.dst + (size_t)blockIdx.y * job.dst_fs + pj.dst_off + (size_t)g * 4;
     const int sp = pj.src_pitch, dp = pj.dst_pitch;
 
+    uint32_t* stage = smem + threadIdx.x;                 // [SLOTS][NT] input rows in flight
     Pipe pipe;
-    pipe.ring = smem + threadIdx.x;
-    pipe.n = pj.h;
-    pipe.ap = ap;
-    pipe.D = ap.r + 1;
-    pipe.reset();
+    pipe.start(smem + ST::WORDS + threadIdx.x, pj.h, ap);
     const int n = pj.h, lag = pipe.lag(), total = n + lag;
     const int t_fast = min(pipe.fast_begin(), n);
 
-    int slot = 0;
-    uint32_t* cur = pipe.ring;
-    auto load = [&](int y) { return *reinterpret_cast<const uint32_t*>(src + (size_t)y * sp); };
+    // one commit group per input row, AHEAD rows in flight
+    auto fetch = [&](int row) {
+        cp_async4(stage + (row & (ST::SLOTS - 1)) * NT, src + (size_t)min(row, n - 1) * sp);
+        cp_async_commit();
+    };
     auto store = [&](int x, uint32_t v) { *reinterpret_cast<uint32_t*>(dst + (size_t)x * dp) = v; };
-    auto bump = [&]() {
-        ++slot; cur += Pipe::SLOT_WORDS;
-        if (slot == ap.ring) { slot = 0; cur = pipe.ring; }
-    };
-    auto edge = [&](int t) {
-        const uint32_t o = pipe.step_edge(t, slot, cur, load(min(t, n - 1)));
-        const int x = t - lag;
-        if (x >= 0 && x < n) store(x, o);
-        bump();
-    };
+#pragma unroll
+    for (int i = 0; i < ST::AHEAD; ++i) fetch(i);
 
     int t = 0;
-    for (; t < t_fast; ++t) edge(t);
-    // steady state: U rows per iteration; the loads of the next U rows are in flight during the math
-    constexpr int U = 8;
-    if (t < n) {
-        uint32_t nxt[U];
-#pragma unroll
-        for (int i = 0; i < U; ++i) nxt[i] = load(min(t + i, n - 1));
-        for (; t + U <= n; t += U) {
-            uint32_t now[U];
-#pragma unroll
-            for (int i = 0; i < U; ++i) now[i] = nxt[i];
-#pragma unroll
-            for (int i = 0; i < U; ++i) nxt[i] = load(min(t + U + i, n - 1));
+    for (; t < t_fast; ++t) {  // start-up: stages come alive one after the other
+        fetch(t + ST::AHEAD);
+        cp_async_wait<ST::AHEAD>();
+        const uint32_t o = pipe.step_edge(t, stage[(t & (ST::SLOTS - 1)) * NT]);
+        const int x = t - lag;
+        if (x >= 0 && x < n) store(x, o);
+    }
+    // steady state: U steps per iteration with running pointers (no per-step 64-bit multiplies, no
+    // clamping: every prefetched row is < n here).  U = 4 keeps the loop body inside the L0 i-cache.
+    constexpr int U = 4;
+    {
+        const char* fsrc = src + (size_t)(t + ST::AHEAD) * sp;  // next row to prefetch
+        char* fdst = dst + (size_t)(t - lag) * dp;              // next row to store
+        for (; t + ST::AHEAD + U <= n; t += U) {
 #pragma unroll
             for (int i = 0; i < U; ++i) {
-                store(t + i - lag, pipe.step_fast(cur, now[i]));
-                bump();
+                cp_async4(stage + ((t + ST::AHEAD + i) & (ST::SLOTS - 1)) * NT, fsrc);
+                cp_async_commit();
+                fsrc += sp;
+            }
+            cp_async_wait<ST::AHEAD>();
+#pragma unroll
+            for (int i = 0; i < U; ++i) {
+                *reinterpret_cast<uint32_t*>(fdst) = pipe.step_fast(stage[((t + i) & (ST::SLOTS - 1)) * NT]);
+                fdst += dp;
             }
         }
-        for (; t < n; ++t) {
-            store(t - lag, pipe.step_fast(cur, load(t)));
-            bump();
-        }
     }
-    for (; t < total; ++t) edge(t);
+    for (; t < n; ++t) {
+        fetch(t + ST::AHEAD);
+        cp_async_wait<ST::AHEAD>();
+        store(t - lag, pipe.step_fast(stage[(t & (ST::SLOTS - 1)) * NT]));
+    }
+    cp_async_wait<0>();
+    for (; t < total; ++t) {  // drain: no more input, mirrored tails come from the rings
+        const uint32_t o = pipe.step_edge(t, 0u);
+        const int x = t - lag;
+        if (x >= 0 && x < n) store(x, o);
+    }
 }
 
 // --------------------------------------------------------------------------- H: lines are rows
@@ -357,42 +403,62 @@ __global__ void __launch_bounds__(NT) blur_h_kernel(const BatchJob job, const Ax
     T* out_t = reinterpret_cast<T*>(out_tile);
 
     Pipe pipe;
-    pipe.ring = ring + threadIdx.x;
-    pipe.n = pj.w;
-    pipe.ap = ap;
-    pipe.D = ap.r + 1;
-    pipe.reset();
+    pipe.start(ring + threadIdx.x, pj.w, ap);
     const int n = pj.w, lag = pipe.lag(), total = n + lag;
     const int t_fast = min(pipe.fast_begin(), n);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int slot = 0;
-    uint32_t* cur = pipe.ring;
     int flushed = 0;  // output positions [0, flushed) are already in global memory
     const int nchunks = (total + TL::CH - 1) / TL::CH;
 
+    // Input staging: 32-bit coalesced loads of the NEXT 32-position tile are issued before the current
+    // tile's math and parked in registers, so their latency is covered by a whole chunk of work; they are
+    // scattered (transposed) into shared memory at the top of the next iteration.
+    constexpr int EPW = 4 / (int)sizeof(T);      // samples per 32-bit word
+    constexpr int WPR = TL::CH / EPW;            // words per row per tile: 8 / 16 / 32
+    constexpr int RPI = 32 / WPR;                // rows covered by one warp-wide load
+    constexpr int NLD = ROWS / (RPI * NWARP);    // loads per thread per tile
+    const int lw = lane % WPR, lr = lane / WPR;
+    uint32_t pre[NLD];
+    auto issue_loads = [&](int t0) {
+        const int x = t0 + lw * EPW;
+#pragma unroll
+        for (int i = 0; i < NLD; ++i) {
+            const int rr = (i * NWARP + warp) * RPI + lr;
+            pre[i] = (rr < nrows && x < n) ? *reinterpret_cast<const uint32_t*>(src + (size_t)rr * sp + (size_t)x * sizeof(T)) : 0u;
+        }
+    };
+    issue_loads(0);
+
     for (int c = 0; c < nchunks; ++c) {
         const int t0 = c * TL::CH;
-        // ---- cooperative, coalesced load of positions [t0, t0+32) of every row of this CTA
-        {
-            const int x = t0 + lane;
-            if (x < n) {
-                for (int rr = warp; rr < nrows; rr += NWARP)
-                    in_t[(lane * TL::PITCH_W) * NL + rr] = *reinterpret_cast<const T*>(src + (size_t)rr * sp + (size_t)x * sizeof(T));
-            }
+        // ---- scatter the prefetched tile (positions [t0, t0+32) of every row) and prefetch the next one
+#pragma unroll
+        for (int i = 0; i < NLD; ++i) {
+            const int rr = (i * NWARP + warp) * RPI + lr;
+            const T* e = reinterpret_cast<const T*>(&pre[i]);
+#pragma unroll
+            for (int k = 0; k < EPW; ++k) in_t[((lw * EPW + k) * TL::PITCH_W) * NL + rr] = e[k];
         }
+        if (t0 + TL::CH < n) issue_loads(t0 + TL::CH);
         __syncthreads();
         // ---- every thread advances its own rows by up to 32 steps
         const int t1 = min(t0 + TL::CH, total);
-        for (int t = t0; t < t1; ++t) {
-            const uint32_t v = in_tile[(t - t0) * TL::PITCH_W + threadIdx.x];
-            uint32_t o;
-            if (t >= t_fast && t < n) o = pipe.step_fast(cur, v);
-            else o = pipe.step_edge(t, slot, cur, v);
-            const int x = t - lag;
-            if (x >= 0 && x < n) out_tile[(x & (TL::OUT - 1)) * TL::PITCH_W + threadIdx.x] = o;
-            ++slot; cur += Pipe::SLOT_WORDS;
-            if (slot == ap.ring) { slot = 0; cur = pipe.ring; }
+        if (t0 >= t_fast && t1 <= n) {
+            // whole tile in the steady state: no per-step branches, unrolled so the look-ahead rotation is free
+            const int x0 = t0 - lag;  // >= 1
+#pragma unroll 4
+            for (int i = 0; i < TL::CH; ++i)
+                out_tile[((x0 + i) & (TL::OUT - 1)) * TL::PITCH_W + threadIdx.x] = pipe.step_fast(in_tile[i * TL::PITCH_W + threadIdx.x]);
+        } else {
+            for (int t = t0; t < t1; ++t) {
+                const uint32_t v = in_tile[(t - t0) * TL::PITCH_W + threadIdx.x];
+                uint32_t o;
+                if (t >= t_fast && t < n) o = pipe.step_fast(v);
+                else o = pipe.step_edge(t, v);
+                const int x = t - lag;
+                if (x >= 0 && x < n) out_tile[(x & (TL::OUT - 1)) * TL::PITCH_W + threadIdx.x] = o;
+            }
         }
         __syncthreads();
         // ---- flush every complete 32-position output block (and the tail at the very end)
@@ -473,7 +539,7 @@ static int launch_v(const FrameLayout& l, const bool mask[3], const char* src, s
                     int count, int r, cudaStream_t st) {
     constexpr int NL = Px<T>::NL;
     const AxisParams ap = axis_params(r);
-    const size_t smem = (size_t)ap.ring * P * NT_V * 4;
+    const size_t smem = ((size_t)ap.ring * P * NT_V + VStage<NT_V>::WORDS) * 4;
     if (smem > (size_t)kMaxSmem) { set_error("BoxBlur: vradius %d with %d fused passes exceeds the shared-memory delay ring", r, P); return -2; }
     auto kern = blur_v_kernel<T, P, MODE, NT_V>;
     VSZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -518,7 +584,7 @@ static int launch_h(const FrameLayout& l, const bool mask[3], const char* src, s
 // largest number of passes one launch can fuse for this radius (shared-memory bound), at most 5
 static int max_fused(int r, bool horizontal) {
     const size_t per_pass = (size_t)(2 * r + 1) * (horizontal ? NT_H : NT_V) * 4;
-    const size_t fixed = horizontal ? (size_t)(HTile<uint16_t, NT_H>::IN_WORDS + HTile<uint16_t, NT_H>::OUT_WORDS) * 4 : 0;
+    const size_t fixed = horizontal ? (size_t)(HTile<uint16_t, NT_H>::IN_WORDS + HTile<uint16_t, NT_H>::OUT_WORDS) * 4 : (size_t)VStage<NT_V>::WORDS * 4;
     int p = (int)((kMaxSmem - fixed) / per_pass);
     return p > 5 ? 5 : p;
 }
