@@ -20,6 +20,12 @@ src.fill_noise(seed=1234)
 if what == "boxblur":
     f = vz.BoxBlurFilter(src.info(), hradius=13, hpasses=5, vradius=13, vpasses=5)
     run = lambda: f.run_device(src, dst)
+elif what == "boxblur_h1":
+    f = vz.BoxBlurFilter(src.info(), hradius=13, hpasses=1, vradius=0, vpasses=0)
+    run = lambda: f.run_device(src, dst)
+elif what == "boxblur_v1":
+    f = vz.BoxBlurFilter(src.info(), hradius=0, hpasses=0, vradius=13, vpasses=1)
+    run = lambda: f.run_device(src, dst)
 elif what == "boxblur_ct":
     f = vz.BoxBlurFilter(src.info(), hradius=13, hpasses=1, vradius=13, vpasses=1)
     run = lambda: f.run_device(src, dst)

@@ -20,7 +20,7 @@ import numpy as np
 __all__ = ["Error", "core", "VideoFormat", "VideoFrame", "VideoNode", "DeviceClip", "GRAY", "RGB", "YUV", "INTEGER", "FLOAT"]
 
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "lib" / "libvszip_cuda.so"
+LIB_PATH = Path(os.environ.get("VSZIP_CUDA_LIB") or (_PKG / "lib" / "libvszip_cuda.so"))  # override: A/B builds only
 
 GRAY, RGB, YUV = 1, 2, 3          # VapourSynth4.h VSColorFamily
 INTEGER, FLOAT = 0, 1             # VSSampleType

@@ -420,14 +420,27 @@ __global__ void __launch_bounds__(NT) blur_h_kernel(const BatchJob job, const Ax
     constexpr int NLD = ROWS / (RPI * NWARP);    // loads per thread per tile
     const int lw = lane % WPR, lr = lane / WPR;
     uint32_t pre[NLD];
+    // row rr_i = (i*NWARP + warp)*RPI + lr, word lw: running 64-bit pointers, one add per load
+    const bool full = (nrows == ROWS);
+    const char* lsrc = src + (size_t)(warp * RPI + lr) * sp + (size_t)lw * 4;
+    char* ldst = dst + (size_t)(warp * RPI + lr) * dp + (size_t)lw * 4;
+    const size_t lstep_s = (size_t)(NWARP * RPI) * sp, lstep_d = (size_t)(NWARP * RPI) * dp;
     auto issue_loads = [&](int t0) {
-        const int x = t0 + lw * EPW;
+        const char* p = lsrc + (size_t)t0 * sizeof(T);
+        if (t0 + lw * EPW >= n) return;  // this lane's word lies beyond the line: keeps stale data, never consumed
+        if (full) {
 #pragma unroll
-        for (int i = 0; i < NLD; ++i) {
-            const int rr = (i * NWARP + warp) * RPI + lr;
-            pre[i] = (rr < nrows && x < n) ? *reinterpret_cast<const uint32_t*>(src + (size_t)rr * sp + (size_t)x * sizeof(T)) : 0u;
+            for (int i = 0; i < NLD; ++i) { pre[i] = *reinterpret_cast<const uint32_t*>(p); p += lstep_s; }
+        } else {
+#pragma unroll
+            for (int i = 0; i < NLD; ++i) {
+                if ((i * NWARP + warp) * RPI + lr < nrows) pre[i] = *reinterpret_cast<const uint32_t*>(p);
+                p += lstep_s;
+            }
         }
     };
+#pragma unroll
+    for (int i = 0; i < NLD; ++i) pre[i] = 0u;
     issue_loads(0);
 
     for (int c = 0; c < nchunks; ++c) {
@@ -465,11 +478,26 @@ __global__ void __launch_bounds__(NT) blur_h_kernel(const BatchJob job, const Ax
         const int produced = min(max(t1 - lag, 0), n);
         const int upto = (t1 == total) ? n : (produced / 32) * 32;
         for (int xb = flushed; xb < upto; xb += 32) {
-            const int x = xb + lane;
+            // one 32-bit store per EPW samples, same lane->(row, word) mapping as the loads
+            const int x = xb + lw * EPW;
             if (x < upto) {
-                for (int rr = warp; rr < nrows; rr += NWARP)
-                    *reinterpret_cast<T*>(dst + (size_t)rr * dp + (size_t)x * sizeof(T)) =
-                        out_t[((x & (TL::OUT - 1)) * TL::PITCH_W) * NL + rr];
+                char* q = ldst + (size_t)xb * sizeof(T);
+                const bool whole = (x + EPW <= upto);
+#pragma unroll
+                for (int i = 0; i < NLD; ++i) {
+                    const int rr = (i * NWARP + warp) * RPI + lr;
+                    if (full || rr < nrows) {
+                        T e[EPW];
+#pragma unroll
+                        for (int k = 0; k < EPW; ++k) e[k] = out_t[(((x + k) & (TL::OUT - 1)) * TL::PITCH_W) * NL + rr];
+                        if (whole) {
+                            *reinterpret_cast<uint32_t*>(q) = *reinterpret_cast<const uint32_t*>(e);
+                        } else {
+                            for (int k = 0; k < EPW && x + k < upto; ++k) reinterpret_cast<T*>(q)[k] = e[k];
+                        }
+                    }
+                    q += lstep_d;
+                }
             }
         }
         flushed = max(flushed, upto);
@@ -531,8 +559,14 @@ static AxisParams axis_params(int r) {
 }
 
 static constexpr int kMaxSmem = 227 * 1024;
-static constexpr int NT_V = 64;
-static constexpr int NT_H = 32;
+#ifndef VSZ_NT_V
+#define VSZ_NT_V 64
+#endif
+#ifndef VSZ_NT_H
+#define VSZ_NT_H 32
+#endif
+static constexpr int NT_V = VSZ_NT_V;
+static constexpr int NT_H = VSZ_NT_H;
 
 template <typename T, int P, int MODE>
 static int launch_v(const FrameLayout& l, const bool mask[3], const char* src, size_t src_fs, char* dst, size_t dst_fs,
