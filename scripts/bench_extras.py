@@ -1,0 +1,93 @@
+"""Secondary measurements: the other BASELINE.json configs, device-resident, CUDA-event timed.
+Not the contract line (bench.py prints that); results go to stdout as JSON and, with --out, to a file.
+usage: python scripts/bench_extras.py [--frames N] [--reps R] [--out profiles/bench_extras_rXX.json]"""
+import argparse
+import json
+import sys
+from pathlib import Path
+
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+import torch
+
+import vapoursynth_zip_b200 as vz
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--frames", type=int, default=128)
+ap.add_argument("--reps", type=int, default=5)
+ap.add_argument("--out", default=None)
+args = ap.parse_args()
+
+vz.core.init([0])
+st = torch.cuda.Stream()
+torch.cuda.set_stream(st)
+PEAK = json.loads((Path(__file__).resolve().parents[1] / "MEASURED_PEAKS.json").read_text())["hbm_gbs"] if (Path(__file__).resolve().parents[1] / "MEASURED_PEAKS.json").exists() else 6650.0
+
+
+def timed(fn, reps):
+    for _ in range(2):
+        fn()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps
+
+
+results = []
+
+
+def record(name, fmt, w, h, frames, algo_bytes_per_frame, ms):
+    fps = frames / (ms * 1e-3)
+    gbs = algo_bytes_per_frame * fps / 1e9
+    results.append({"config": name, "format": fmt, "size": f"{w}x{h}", "frames_per_launch": frames, "ms_per_launch": ms, "fps": fps,
+                    "us_per_frame": ms * 1e3 / frames, "algorithmic_bytes_per_frame": algo_bytes_per_frame, "algorithmic_GBps": gbs,
+                    "frac_of_measured_hbm_peak": gbs / PEAK})
+    print(f"{name:58s} {fps:12.0f} fps  {ms * 1e3 / frames:8.2f} us/frame  {gbs:8.1f} GB/s  {100 * gbs / PEAK:5.1f}% of {PEAK:.0f}", file=sys.stderr)
+
+
+def pixel_cfg(name, fmt, w, h, frames, make_filter, noise=True):
+    src, dst = vz.DeviceClip(fmt, w, h, frames), vz.DeviceClip(fmt, w, h, frames)
+    if noise:
+        src.fill_noise(1234)
+    f = make_filter(src)
+    ms = timed(lambda: f.run_device(src, dst, first=0, count=frames, stream=st.cuda_stream), args.reps)
+    record(name, fmt, w, h, frames, 2 * src.frame_bytes, ms)
+    src.free(); dst.free()
+
+
+def stats_cfg(name, fmt, w, h, frames, make_filter):
+    src = vz.DeviceClip(fmt, w, h, frames)
+    src.fill_noise(1234)
+    f = make_filter(src)
+    lib = vz.load_library()
+    import ctypes as C
+    # time the kernels only: results stay on the device (out = NULL), the stream is not synchronised per call
+    ms = timed(lambda: vz._check(lib.vszip_planeminmax_device(f.handle, src.handle, None, 0, frames, None, st.cuda_stream))
+               if isinstance(f, vz.PlaneMinMaxFilter) else
+               vz._check(lib.vszip_planeaverage_device(f.handle, src.handle, None, 0, frames, None, st.cuda_stream)), args.reps)
+    record(name, fmt, w, h, frames, src.frame_bytes, ms)
+    src.free()
+
+
+N = args.frames
+pixel_cfg("C1 BoxBlur(13,1,13,1) comptime path", "YUV420P16", 1920, 1080, N, lambda s: vz.BoxBlurFilter(s.info(), hradius=13, hpasses=1, vradius=13, vpasses=1))
+pixel_cfg("C2 BoxBlur(13,5,13,5) runtime path [headline]", "YUV420P16", 1920, 1080, N, lambda s: vz.BoxBlurFilter(s.info(), hradius=13, hpasses=5, vradius=13, vpasses=5))
+pixel_cfg("C2 on constant frames (README BlankClip)", "YUV420P16", 1920, 1080, N, lambda s: vz.BoxBlurFilter(s.info(), hradius=13, hpasses=5, vradius=13, vpasses=5), noise=False)
+pixel_cfg("C3 Bilateral(sigmaS=2,sigmaR=2) all planes", "YUV420P16", 1920, 1080, N, lambda s: vz.BilateralFilter(s.info(), sigmaS=2, sigmaR=2, planes=[0, 1, 2]))
+pixel_cfg("C3' Bilateral default sigmaR=0.02 (exact smem LUT)", "YUV420P16", 1920, 1080, N, lambda s: vz.BilateralFilter(s.info(), sigmaS=2, sigmaR=0.02, planes=[0, 1, 2]))
+M = max(8, N // 4)
+stats_cfg("C4 PlaneMinMax(minthr=.1,maxthr=.1) GRAY16 4K", "GRAY16", 3840, 2160, M, lambda s: vz.PlaneMinMaxFilter(s.info(), minthr=0.1, maxthr=0.1))
+stats_cfg("C4 PlaneMinMax(minthr=.1,maxthr=.1) GRAYS 4K", "GRAYS", 3840, 2160, M, lambda s: vz.PlaneMinMaxFilter(s.info(), minthr=0.1, maxthr=0.1))
+stats_cfg("C4 PlaneMinMax no threshold GRAY16 4K", "GRAY16", 3840, 2160, M, lambda s: vz.PlaneMinMaxFilter(s.info()))
+stats_cfg("C4 PlaneAverage(exclude=[0,32768]) GRAY16 4K", "GRAY16", 3840, 2160, M, lambda s: vz.PlaneAverageFilter(s.info(), exclude=[0, 32768]))
+stats_cfg("C4 PlaneAverage(exclude=[0,1]) GRAYS 4K", "GRAYS", 3840, 2160, M, lambda s: vz.PlaneAverageFilter(s.info(), exclude=[0, 1]))
+K = max(4, N // 16)
+pixel_cfg("C5a BoxBlur(13,1,13,1) YUV444PS 4K (comptime float)", "YUV444PS", 3840, 2160, K, lambda s: vz.BoxBlurFilter(s.info(), hradius=13, vradius=13))
+pixel_cfg("C5b Bilateral(2,2) YUV444PS 4K", "YUV444PS", 3840, 2160, K, lambda s: vz.BilateralFilter(s.info(), sigmaS=2, sigmaR=2))
+out = {"peak_GBps": PEAK, "results": results}
+print(json.dumps(out))
+if args.out:
+    Path(args.out).write_text(json.dumps(out, indent=1) + "\n")

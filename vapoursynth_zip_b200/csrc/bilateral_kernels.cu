@@ -24,7 +24,7 @@ namespace vsz {
 
 enum WeightMode { W_SMEM = 0, W_COMPUTE = 1, W_GLOBAL = 2 };
 
-static constexpr int TW = 32, TH = 8;
+static constexpr int TW = 32, TH = 8, TILE = 32;
 
 struct BilateralPlaneParams {
     const float* gs;   // (radius+1)^2, device
@@ -38,7 +38,9 @@ struct BilateralPlaneParams {
 struct BilateralParams {
     BilateralPlaneParams pl[3];  // indexed by PlaneJob::aux (the real plane number)
     float peak;
-    int tiles_x[3];              // tiles per row, indexed like job.pl[]
+    int tiles_x[3];              // 32x32 tiles per row, indexed like job.pl[]
+    int strips_x[3];             // CTAs per tile row
+    int strip;                   // tiles per CTA
 };
 
 template <typename T> __device__ __forceinline__ float widen(T v) { return (float)v; }
@@ -48,29 +50,42 @@ template <typename T> struct BTr { static constexpr bool flt = false; };
 template <> struct BTr<__half> { static constexpr bool flt = true; };
 template <> struct BTr<float> { static constexpr bool flt = true; };
 
-// range index (src/filters/bilateral.zig:15-22) from widened samples
-template <typename T> __device__ __forceinline__ int range_index(float a, float b) {
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// Range index (src/filters/bilateral.zig:15-22) as an exact non-negative integer held in a float:
+// integer clips |a-b| (both < 2^16, exact); float clips trunc(min(1,|a-b|)*65535 + 0.5) with the
+// subtraction rounded in T.  Keeping it in a float avoids an int<->float conversion pair per tap.
+template <typename T> __device__ __forceinline__ float range_index_f(float a, float b) {
+    float d = __fsub_rn(a, b);
     if constexpr (BTr<T>::flt) {
-        float d = __fsub_rn(a, b);
         if constexpr (sizeof(T) == 2) d = __half2float(__float2half_rn(d));  // the subtraction is rounded in f16
         const float m = fminf(1.0f, fabsf(d));
-        return (int)__fadd_rn(__fmul_rn(m, 65535.0f), 0.5f);
+        return truncf(__fadd_rn(__fmul_rn(m, 65535.0f), 0.5f));
     } else {
-        return (int)fabsf(__fsub_rn(a, b));  // exact: both are integers below 2^16
+        return fabsf(d);
     }
 }
 
+// weight of range index `fi` (an integer-valued float); `top` = lut_len - 1
 template <int WM>
-__device__ __forceinline__ float range_weight(int idx, const BilateralPlaneParams& pp, const float* s_lut) {
-    idx = min(idx, pp.lut_len - 1);
-    if constexpr (WM == W_SMEM) return s_lut[idx];
-    else if constexpr (WM == W_GLOBAL) return __ldg(pp.gr + idx);
-    else {
-        const float f = (float)idx;
-        return pp.cnorm * exp2f(pp.c2 * f * f);
+__device__ __forceinline__ float range_weight(float fi, float top, const BilateralPlaneParams& pp, const float* s_lut) {
+    fi = fminf(fi, top);
+    if constexpr (WM == W_COMPUTE) {
+        return ex2_approx(__fmul_rn(__fmul_rn(fi, fi), pp.c2));  // un-normalised: the constant cancels in sum/wsum
+    } else {
+        const int idx = __float_as_int(__fadd_rn(fi, 8388608.0f)) & 0x7fffff;  // exact: fi is an integer < 2^23
+        if constexpr (WM == W_SMEM) return s_lut[idx];
+        else return __ldg(pp.gr + idx);
     }
 }
 
+// One CTA (32x8 threads) walks a horizontal strip of `prm.strip` 32x32-pixel tiles; every thread produces
+// 4 pixels per tile (rows ty, ty+8, ty+16, ty+24).  The spatial table and - in W_SMEM mode - the range
+// LUT are loaded once per CTA and reused by every tile of the strip.
 template <typename T, bool JOINT, int WM>
 __global__ void __launch_bounds__(TW * TH) bilateral_kernel(const BatchJob job, const BilateralParams prm) {
     extern __shared__ float smem_f[];
@@ -79,58 +94,73 @@ __global__ void __launch_bounds__(TW * TH) bilateral_kernel(const BatchJob job, 
     const PlaneJob& pj = job.pl[k];
     const BilateralPlaneParams& pp = prm.pl[pj.aux];
     const int local = blockIdx.x - pj.cta_begin;
-    const int tx = local % prm.tiles_x[k], ty = local / prm.tiles_x[k];
-    const int x0 = tx * TW, y0 = ty * TH;
+    const int strips_x = prm.strips_x[k];
+    const int sx = local % strips_x, ty0 = local / strips_x;
+    const int y0 = ty0 * TILE;
     const int r = pp.radius, step = pp.step, r2 = r + 1;
-    const int tw = TW + 2 * r, th = TH + 2 * r;
+    const int tw = TILE + 2 * r, th = TILE + 2 * r, tsize = tw * th;
+    const uint32_t inv_tw = ((1u << 20) + (uint32_t)tw - 1u) / (uint32_t)tw;  // exact e / tw for e < 2^12
 
     float* s_src = smem_f;
-    float* s_ref = JOINT ? s_src + tw * th : s_src;
-    float* s_gs = s_ref + tw * th;
+    float* s_ref = JOINT ? s_src + tsize : s_src;
+    float* s_gs = s_ref + tsize;
     float* s_lut = s_gs + r2 * r2;
 
     const char* src = job.src + (size_t)blockIdx.y * job.src_fs + pj.src_off;
     const char* ref = JOINT ? job.ref + (size_t)blockIdx.y * job.ref_fs + pj.ref_off : nullptr;
+    char* dst = job.dst + (size_t)blockIdx.y * job.dst_fs + pj.dst_off;
     const int tid = threadIdx.y * TW + threadIdx.x;
-    for (int i = tid; i < tw * th; i += TW * TH) {
-        const int lx = i % tw, ly = i / tw;
-        const int gx = min(max(x0 + lx - r, 0), pj.w - 1);
-        const int gy = min(max(y0 + ly - r, 0), pj.h - 1);
-        s_src[i] = widen<T>(reinterpret_cast<const T*>(src + (size_t)gy * pj.src_pitch)[gx]);
-        if constexpr (JOINT) s_ref[i] = widen<T>(reinterpret_cast<const T*>(ref + (size_t)gy * pj.ref_pitch)[gx]);
-    }
     for (int i = tid; i < r2 * r2; i += TW * TH) s_gs[i] = pp.gs[i];
     if constexpr (WM == W_SMEM)
         for (int i = tid; i < pp.smem_lut; i += TW * TH) s_lut[i] = pp.gr[i];
-    __syncthreads();
+    const float top = (float)(pp.lut_len - 1);
 
-    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
-    if (x >= pj.w || y >= pj.h) return;
-    const int cxy = (threadIdx.y + r) * tw + threadIdx.x + r;
-    const float cref = s_ref[cxy];
-    float wsum = __fmul_rn(s_gs[0], range_weight<WM>(0, pp, s_lut));
-    float sum = __fmul_rn(s_src[cxy], wsum);
-    for (int yy = 1; yy < r2; yy += step) {
-        const int up = cxy - yy * tw, dn = cxy + yy * tw;
-        for (int xx = 1; xx < r2; xx += step) {
-            const float sw = s_gs[yy * r2 + xx];
-            const float g1 = range_weight<WM>(range_index<T>(cref, s_ref[up + xx]), pp, s_lut);
-            const float g2 = range_weight<WM>(range_index<T>(cref, s_ref[dn + xx]), pp, s_lut);
-            const float g3 = range_weight<WM>(range_index<T>(cref, s_ref[up - xx]), pp, s_lut);
-            const float g4 = range_weight<WM>(range_index<T>(cref, s_ref[dn - xx]), pp, s_lut);
-            const float gsum = __fadd_rn(__fadd_rn(__fadd_rn(g1, g2), g3), g4);
-            wsum = __fadd_rn(wsum, __fmul_rn(sw, gsum));
-            const float p1 = __fmul_rn(s_src[up + xx], g1), p2 = __fmul_rn(s_src[dn + xx], g2);
-            const float p3 = __fmul_rn(s_src[up - xx], g3), p4 = __fmul_rn(s_src[dn - xx], g4);
-            const float psum = __fadd_rn(__fadd_rn(__fadd_rn(p1, p2), p3), p4);
-            sum = __fadd_rn(sum, __fmul_rn(sw, psum));
+    const int tile_end = min((sx + 1) * prm.strip, prm.tiles_x[k]);
+    for (int tx = sx * prm.strip; tx < tile_end; ++tx) {
+        const int x0 = tx * TILE;
+        __syncthreads();  // previous tile fully consumed (and the tables visible on the first pass)
+        // tile + halo, widened to f32, replicate edges (src/filters/bilateral.zig:281-289)
+        for (int e = tid; e < tsize; e += TW * TH) {
+            const int ly = (int)(((uint32_t)e * inv_tw) >> 20), lx = e - ly * tw;
+            const int gy = min(max(y0 + ly - r, 0), pj.h - 1), gx = min(max(x0 + lx - r, 0), pj.w - 1);
+            s_src[e] = widen<T>(reinterpret_cast<const T*>(src + (size_t)gy * pj.src_pitch)[gx]);
+            if constexpr (JOINT) s_ref[e] = widen<T>(reinterpret_cast<const T*>(ref + (size_t)gy * pj.ref_pitch)[gx]);
+        }
+        __syncthreads();
+        const int x = x0 + threadIdx.x;
+#pragma unroll
+        for (int sub = 0; sub < TILE / TH; ++sub) {
+            const int lyo = threadIdx.y + sub * TH, y = y0 + lyo;
+            if (x >= pj.w || y >= pj.h) continue;
+            const int cxy = (lyo + r) * tw + threadIdx.x + r;
+            const float cref = s_ref[cxy];
+            float wsum = __fmul_rn(s_gs[0], range_weight<WM>(0.0f, top, pp, s_lut));
+            float sum = __fmul_rn(s_src[cxy], wsum);
+            for (int yy = 1; yy < r2; yy += step) {
+                const int up = cxy - yy * tw, dn = cxy + yy * tw;
+                for (int xx = 1; xx < r2; xx += step) {
+                    const float sw = s_gs[yy * r2 + xx];
+                    const float r1 = s_ref[up + xx], r2v = s_ref[dn + xx], r3 = s_ref[up - xx], r4 = s_ref[dn - xx];
+                    const float v1 = JOINT ? s_src[up + xx] : r1, v2 = JOINT ? s_src[dn + xx] : r2v;
+                    const float v3 = JOINT ? s_src[up - xx] : r3, v4 = JOINT ? s_src[dn - xx] : r4;
+                    const float g1 = range_weight<WM>(range_index_f<T>(cref, r1), top, pp, s_lut);
+                    const float g2 = range_weight<WM>(range_index_f<T>(cref, r2v), top, pp, s_lut);
+                    const float g3 = range_weight<WM>(range_index_f<T>(cref, r3), top, pp, s_lut);
+                    const float g4 = range_weight<WM>(range_index_f<T>(cref, r4), top, pp, s_lut);
+                    const float gsum = __fadd_rn(__fadd_rn(__fadd_rn(g1, g2), g3), g4);
+                    wsum = __fadd_rn(wsum, __fmul_rn(sw, gsum));
+                    const float p1 = __fmul_rn(v1, g1), p2 = __fmul_rn(v2, g2), p3 = __fmul_rn(v3, g3), p4 = __fmul_rn(v4, g4);
+                    const float psum = __fadd_rn(__fadd_rn(__fadd_rn(p1, p2), p3), p4);
+                    sum = __fadd_rn(sum, __fmul_rn(sw, psum));
+                }
+            }
+            const float q = __fdiv_rn(sum, wsum);
+            T* out = reinterpret_cast<T*>(dst + (size_t)y * pj.dst_pitch) + x;
+            if constexpr (std::is_same<T, float>::value) *out = q;
+            else if constexpr (std::is_same<T, __half>::value) *out = __float2half_rn(q);
+            else *out = (T)fminf(fmaxf(__fadd_rn(q, 0.5f), 0.0f), prm.peak);  // trunc(clamp(q + 0.5, 0, peak))
         }
     }
-    const float q = __fdiv_rn(sum, wsum);
-    T* out = reinterpret_cast<T*>(job.dst + (size_t)blockIdx.y * job.dst_fs + pj.dst_off + (size_t)y * pj.dst_pitch) + x;
-    if constexpr (std::is_same<T, float>::value) *out = q;
-    else if constexpr (std::is_same<T, __half>::value) *out = __float2half_rn(q);
-    else *out = (T)fminf(fmaxf(__fadd_rn(q, 0.5f), 0.0f), prm.peak);  // trunc(clamp(q + 0.5, 0, peak))
 }
 
 // =========================================================================== host
@@ -179,9 +209,16 @@ static int run_bilateral_t(const FrameLayout& l, const bool mask[3], const char*
         pp.smem_lut = wm == W_SMEM ? pp.lut_len : 0;
         pp.c2 = bp.c2[p]; pp.cnorm = bp.cnorm[p];
         const int r = pp.radius;
-        BatchJob j = make_batch(l, one, src, sfs, ref, rfs, dst, dfs, [](int w, int h) { return ((w + TW - 1) / TW) * ((h + TH - 1) / TH); });
-        prm.tiles_x[0] = (l.pl[p].w + TW - 1) / TW;
-        const size_t tile = (size_t)(TW + 2 * r) * (TH + 2 * r);
+        // strip length: whole tile rows when the batch alone fills the GPU, shorter strips for single frames
+        const int tiles_x = (l.pl[p].w + TILE - 1) / TILE, tiles_y = (l.pl[p].h + TILE - 1) / TILE;
+        int strip = tiles_x;
+        while (strip > 1 && (long long)((tiles_x + strip - 1) / strip) * tiles_y * count < 4 * 148) strip = (strip + 1) / 2;
+        const int strips_x = (tiles_x + strip - 1) / strip;
+        prm.strip = strip;
+        prm.tiles_x[0] = tiles_x;
+        prm.strips_x[0] = strips_x;
+        BatchJob j = make_batch(l, one, src, sfs, ref, rfs, dst, dfs, [&](int, int) { return strips_x * tiles_y; });
+        const size_t tile = (size_t)(TILE + 2 * r) * (TILE + 2 * r);
         const size_t smem = (tile * (ref ? 2 : 1) + (size_t)(r + 1) * (r + 1) + (size_t)pp.smem_lut) * sizeof(float);
         if (smem > 227 * 1024) { set_error("Bilateral: spatial radius %d does not fit the shared-memory tile", r); return -2; }
         for (int f0 = 0; f0 < count; f0 += 65535) {
