@@ -37,6 +37,22 @@ METRIC = "fps @1080p YUV420P16, vszip.BoxBlur(hradius=13,hpasses=5,vradius=13,vp
 WORKLOAD = "configs[1]: BoxBlur 13/5/13/5 on 1920x1080 YUV420P16 uniform-noise frames"
 
 
+def frames_of_rank(rank, world, per_rank):
+    """Frame numbers rank `rank` of `world` processes: frame n runs on GPU n mod k."""
+    return [rank + world * i for i in range(per_rank)]
+
+
+def max_over_ranks(x, world, device=None):
+    """Slowest rank's value (the job is as slow as its slowest GPU); works with nccl (cuda) and gloo (cpu)."""
+    if world == 1:
+        return x
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device=device if device is not None else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
 def peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -99,7 +115,7 @@ class ClockSampler:
     def __init__(self, gpu_index):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except FileNotFoundError:
             self.p = None
@@ -153,17 +169,14 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+    def max_ranks(x):
+        return max_over_ranks(x, world, dev)
 
     n = FRAMES_PER_STEP
     src = vz.DeviceClip(FMT, W, H, n)
     dst = vz.DeviceClip(FMT, W, H, n)
-    src.fill_noise(seed=1234, first_frame_no=rank * n)       # rank r owns frames r*n .. r*n+n-1 of the synthetic clip
+    mine = frames_of_rank(rank, world, n)                    # frame numbers n with n mod world == rank
+    src.fill_noise(seed=1234, first_frame_no=mine[0], frame_no_stride=world)
     flt = vz.BoxBlurFilter(src.info(), **ARGS)
     # launch on a torch-owned stream so torch's CUDA events bracket exactly the kernels (a NULL stream would
     # select the library's own stream, which torch events on the default stream do not see)
@@ -187,7 +200,7 @@ def run_ours(args):
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
         barrier()
-        return max_over_ranks(ms) / steps
+        return max_ranks(ms) / steps
 
     # ---- headline: device-resident
     sampler = ClockSampler(local) if rank == 0 else None
@@ -205,6 +218,11 @@ def run_ours(args):
     peak, peak_src = peaks()
     dom_name, dom_ms = ("blur_h_kernel<u16,P=5>", ms_h) if ms_h >= ms_v else ("blur_v_kernel<u16,P=5>", ms_v)
     achieved = ALGO_BYTES * n / (dom_ms * 1e-3) / 1e9
+    traffic = None  # DRAM bytes per launch of that kernel, from the committed ncu --set full capture
+    tfiles = sorted((ROOT / "profiles").glob("traffic_r*.json"))
+    if tfiles:
+        per_frame = json.loads(tfiles[-1].read_text())["dram_bytes_per_frame"].get(dom_name.split("<")[0])
+        traffic = per_frame * n if per_frame else None
     path_gbs = ALGO_BYTES * n / (ms_step * 1e-3) / 1e9
 
     # ---- end to end: pinned host frames -> vszip_boxblur_get_frame (H2D + kernels + D2H per frame), 8 requests in flight
@@ -230,7 +248,7 @@ def run_ours(args):
     frames_out = [vz._cframe(planes_of(t)) for t in host_out]
 
     def one(i):
-        rc = lib.vszip_boxblur_get_frame(flt.handle, rank + world * i, C.byref(frames_in[i]), C.byref(frames_out[i]))
+        rc = lib.vszip_boxblur_get_frame(flt.handle, mine[i], C.byref(frames_in[i]), C.byref(frames_out[i]))
         if rc:
             raise RuntimeError(vz._last_error())
 
@@ -247,7 +265,7 @@ def run_ours(args):
     for _ in range(e2e_steps):
         e2e_step()
     torch.cuda.synchronize()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_s = max_ranks(time.perf_counter() - t0)
     barrier()
     e2e_fps = world * ne * e2e_steps / e2e_s
     pool.shutdown()
@@ -270,7 +288,7 @@ def run_ours(args):
                     "frames_per_step_per_gpu": ne, "in_flight": 8, "api": "vszip_boxblur_get_frame on pinned host frames"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": traffic, "algorithmic_bytes": ALGO_BYTES * n, "peak_source": peak_src,
                          "note": "algorithmic bytes = 12,441,600 B per frame (read once + write once) x frames per launch / launch duration"},
             "path": {"h_kernel_ms": ms_h, "v_kernel_ms": ms_v, "step_ms": ms_step, "algorithmic_GBps": path_gbs, "frac_of_peak": path_gbs / peak},
             "cpu_baseline": cpu,
@@ -283,7 +301,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=int(os.environ.get("WORLD_SIZE", "1")))
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

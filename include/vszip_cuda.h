@@ -173,9 +173,11 @@ vszip_dev_clip* vszip_dev_clip_alloc(const vszip_video_info* vi, int32_t num_fra
 void vszip_dev_clip_free(vszip_dev_clip* c);
 int vszip_dev_clip_upload(vszip_dev_clip* c, int32_t frame, const vszip_frame* host);
 int vszip_dev_clip_download(const vszip_dev_clip* c, int32_t frame, vszip_frame* host);
-/* Counter-based uniform noise keyed by (seed, first_frame_no + i, plane, y, x): integer samples over
- * the full [0, 2^bits) range, float luma/RGB in [0,1), float chroma in [-0.5,0.5). */
-int vszip_dev_clip_fill_noise(vszip_dev_clip* c, uint64_t seed, int32_t first_frame_no);
+/* Counter-based uniform noise keyed by (seed, frame number, plane, y, x): integer samples over the full
+ * [0, 2^bits) range, float luma/RGB in [0,1), float chroma in [-0.5,0.5).  Frame i of the clip is frame number
+ * first_frame_no + i*frame_no_stride of the synthetic source, so rank r of k can hold exactly the frames
+ * n with n mod k == r (first = r, stride = k). */
+int vszip_dev_clip_fill_noise(vszip_dev_clip* c, uint64_t seed, int32_t first_frame_no, int32_t frame_no_stride);
 /* Sum over planes of width*height*bytes_per_sample (the algorithmic bytes of one frame). */
 size_t vszip_dev_clip_frame_bytes(const vszip_dev_clip* c);
 /* Raw device pointer / pitch of one plane (for interop with other CUDA code). */

@@ -1,0 +1,16 @@
+#!/bin/bash
+# One GPU-box visit: parity suite, contract bench line, secondary configs, ncu launch list + full captures.
+# usage (from the repo root, under gpurun): bash scripts/gpu_round.sh r01
+R=${1:-r01}
+O=gpurun_out
+mkdir -p $O
+timeout 900 python -m pytest tests -m gpu -q --timeout 300 2>&1 | tail -5 > $O/pytest_gpu_$R.log
+timeout 600 python bench.py > $O/bench_$R.json 2> $O/bench_$R.err
+timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > $O/bench_ref_$R.json 2>> $O/bench_$R.err
+timeout 600 python scripts/bench_extras.py --frames 128 --out $O/bench_extras_$R.json > /dev/null 2> $O/bench_extras_$R.txt
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_$R.csv python bench.py --steps 2 --warmup 1 --no-cpu > $O/launches_bench_$R.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:blur_ -s 2 -c 2 -o $O/ncu_boxblur_$R python scripts/prof_run.py boxblur 128 2 > /dev/null 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:bilateral -s 3 -c 1 -o $O/ncu_bilateral_$R python scripts/prof_run.py bilateral 32 2 > /dev/null 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:stats_kernel -s 1 -c 1 -o $O/ncu_average_$R python scripts/prof_run.py average 32 2 > /dev/null 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:hist_ -s 2 -c 2 -o $O/ncu_minmax_$R python scripts/prof_run.py minmax 32 2 > /dev/null 2>&1
+cat $O/pytest_gpu_$R.log; cat $O/bench_$R.json | cut -c1-400; tail -3 $O/bench_$R.err

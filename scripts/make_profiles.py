@@ -1,0 +1,43 @@
+"""Turns one GPU visit's raw output (gpurun_out/*_<round>.*) into the tracked evidence under profiles/.
+usage: python scripts/make_profiles.py r01"""
+import csv
+import json
+import shutil
+import subprocess
+import sys
+from collections import OrderedDict
+from pathlib import Path
+
+R = sys.argv[1] if len(sys.argv) > 1 else "r01"
+ROOT = Path(__file__).resolve().parents[1]
+G, P = ROOT / "gpurun_out", ROOT / "profiles"
+P.mkdir(exist_ok=True)
+
+for name in (f"bench_{R}.json", f"bench_ref_{R}.json", f"bench_extras_{R}.json", f"bench_extras_{R}.txt", f"pytest_gpu_{R}.log"):
+    if (G / name).exists():
+        shutil.copy(G / name, P / name)
+
+# ---- launch list of `bench.py --steps 2 --warmup 1` (ncu --metrics gpu__time_duration.sum): per-kernel shares
+lf = G / f"launches_{R}.csv"
+if lf.exists():
+    rows = [r for r in csv.reader(lf.read_text().splitlines()) if len(r) > 14 and r[0].isdigit()]
+    agg = OrderedDict()
+    for r in rows:
+        k = r[4].split("(")[0].replace("void ", "")
+        a = agg.setdefault(k, [0, 0.0])
+        a[0] += 1
+        a[1] += float(r[14]) / 1e3
+    tot = sum(v[1] for v in agg.values())
+    lines = [f"# ncu launch list, `python bench.py --steps 2 --warmup 1 --no-cpu` ({R})", "",
+             "Per-launch times under ncu are cold-cache and serialised: compare SHARES, not absolutes.", "",
+             "| kernel | launches | total us | share |", "|---|---:|---:|---:|"]
+    for k, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        lines.append(f"| `{k}` | {n} | {us:.1f} | {100 * us / tot:.1f}% |")
+    (P / f"launches_{R}.md").write_text("\n".join(lines) + "\n")
+    shutil.copy(lf, P / f"launches_{R}.csv")
+
+# ---- ncu --set full summaries
+for rep in sorted(G.glob(f"ncu_*_{R}.ncu-rep")):
+    out = subprocess.run([sys.executable, str(ROOT / "scripts" / "ncu_summary.py"), str(rep)], capture_output=True, text=True).stdout
+    (P / (rep.stem + ".md")).write_text(f"# {rep.name} (ncu --set full --clock-control none)\n\n" + out)
+print("profiles updated:", sorted(p.name for p in P.iterdir()))

@@ -105,7 +105,7 @@ ABI = {
     "vszip_dev_clip_free": (None, [_P]),
     "vszip_dev_clip_upload": (C.c_int, [_P, C.c_int32, C.POINTER(_Frame)]),
     "vszip_dev_clip_download": (C.c_int, [_P, C.c_int32, C.POINTER(_Frame)]),
-    "vszip_dev_clip_fill_noise": (C.c_int, [_P, C.c_uint64, C.c_int32]),
+    "vszip_dev_clip_fill_noise": (C.c_int, [_P, C.c_uint64, C.c_int32, C.c_int32]),
     "vszip_dev_clip_frame_bytes": (C.c_size_t, [_P]),
     "vszip_dev_clip_plane_ptr": (_P, [_P, C.c_int32, C.c_int32, C.POINTER(C.c_ssize_t)]),
 }
@@ -489,8 +489,8 @@ class DeviceClip:
     def frame_bytes(self) -> int:
         return int(load_library().vszip_dev_clip_frame_bytes(self.handle))
 
-    def fill_noise(self, seed=1234, first_frame_no=0):
-        _check(load_library().vszip_dev_clip_fill_noise(self.handle, seed, first_frame_no))
+    def fill_noise(self, seed=1234, first_frame_no=0, frame_no_stride=1):
+        _check(load_library().vszip_dev_clip_fill_noise(self.handle, seed, first_frame_no, frame_no_stride))
 
     def upload(self, frame: int, planes):
         keep = [np.ascontiguousarray(p) for p in planes]

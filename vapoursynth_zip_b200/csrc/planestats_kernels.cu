@@ -209,32 +209,71 @@ __global__ void __launch_bounds__(NT) stats_kernel(const StatsJob j) {
     rows_of_cta(p, local, y0, y1);
 
     Partial acc = empty_partial();
-    unsigned int isum32 = 0, idiff32 = 0;  // flushed to 64 bit once per row
+    unsigned int isum32 = 0, idiff32 = 0;  // flushed to 64 bit after every group of rows
     const int nex = j.nex;
-    for (int y = y0; y < y1; ++y) {
-        for_each_sample<T, HAS_B>(a, p.a_pitch, b, p.b_pitch, p.w, y, y + 1, [&](T av, T bv) {
-            if constexpr (AVERAGE) {
-                bool found = false;
-                if constexpr (El<T>::flt) {
-                    const float f = as_float<T>(av);
-                    for (int i = 0; i < nex; ++i) found |= (f == (i < 16 ? j.excl_f[i] : j.excl_f_more[i - 16]));
-                    if (found) acc.excluded += 1; else acc.fsum += (double)f;
-                } else {
-                    const int32_t iv = (int32_t)av;
-                    for (int i = 0; i < nex; ++i) found |= (iv == (i < 16 ? j.excl_i[i] : j.excl_i_more[i - 16]));
-                    if (found) acc.excluded += 1; else isum32 += (unsigned)av;
-                }
+    // the exclude list lives in registers for the usual short lists (unused slots repeat the first value)
+    int32_t xi[4];
+    float xf[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { xi[i] = j.excl_i[i < nex ? i : 0]; xf[i] = j.excl_f[i < nex ? i : 0]; }
+
+    auto visit = [&](T av, T bv) {
+        if constexpr (AVERAGE) {
+            bool found = false;
+            if constexpr (El<T>::flt) {
+                const float f = as_float<T>(av);
+                if (nex > 0) found = (f == xf[0]) | (f == xf[1]) | (f == xf[2]) | (f == xf[3]);
+                for (int i = 4; i < nex; ++i) found |= (f == j.excl_f[i]);
+                if (found) acc.excluded += 1; else acc.fsum += (double)f;
             } else {
-                if constexpr (El<T>::flt) {
-                    const float f = as_float<T>(av);
-                    acc.fmin = fminf(acc.fmin, f); acc.fmax = fmaxf(acc.fmax, f);
-                } else {
-                    acc.imin = min(acc.imin, (unsigned)av); acc.imax = max(acc.imax, (unsigned)av);
+                const int32_t iv = (int32_t)av;
+                if (nex > 0) found = (iv == xi[0]) | (iv == xi[1]) | (iv == xi[2]) | (iv == xi[3]);
+                for (int i = 4; i < nex; ++i) found |= (iv == j.excl_i[i]);
+                if (found) acc.excluded += 1; else isum32 += (unsigned)av;
+            }
+        } else {
+            if constexpr (El<T>::flt) {
+                const float f = as_float<T>(av);
+                acc.fmin = fminf(acc.fmin, f); acc.fmax = fmaxf(acc.fmax, f);
+            } else {
+                acc.imin = min(acc.imin, (unsigned)av); acc.imax = max(acc.imax, (unsigned)av);
+            }
+        }
+        if constexpr (HAS_B) acc.fdiff += abs_diff<T>(av, bv, idiff32);
+    };
+
+    // G rows per step: G independent 16-byte loads per clip are in flight before any sample is consumed
+    constexpr int V = El<T>::PER16, G = HAS_B ? 2 : 4;
+    const int nvec = p.w / V;
+    for (int y = y0; y < y1; y += G) {
+        for (int v = threadIdx.x; v < nvec; v += NT) {
+            uint4 av[G], bv[G];
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                const int yy = min(y + g, y1 - 1);  // duplicates past the end are loaded but not visited
+                av[g] = __ldg(reinterpret_cast<const uint4*>(a + (size_t)yy * p.a_pitch) + v);
+                if constexpr (HAS_B) bv[g] = __ldg(reinterpret_cast<const uint4*>(b + (size_t)yy * p.b_pitch) + v);
+                else bv[g] = av[g];
+            }
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                if (y + g < y1) {
+                    const T* ae = reinterpret_cast<const T*>(&av[g]);
+                    const T* be = reinterpret_cast<const T*>(&bv[g]);
+#pragma unroll
+                    for (int i = 0; i < V; ++i) visit(ae[i], be[i]);
                 }
             }
-            if constexpr (HAS_B) acc.fdiff += abs_diff<T>(av, bv, idiff32);
-        });
-        // a thread sees at most ceil(w/NT)+1 samples per row; with w <= 65536 u32 cannot overflow
+        }
+        const int x = nvec * V + threadIdx.x;  // scalar tail of each row
+        if (x < p.w) {
+            for (int g = 0; g < G && y + g < y1; ++g) {
+                const T at = reinterpret_cast<const T*>(a + (size_t)(y + g) * p.a_pitch)[x];
+                const T bt = HAS_B ? reinterpret_cast<const T*>(b + (size_t)(y + g) * p.b_pitch)[x] : at;
+                visit(at, bt);
+            }
+        }
+        // per group a thread sees at most G*(ceil(w/NT)+1) samples: with w <= 65536 the u32 partials cannot overflow
         acc.isum += isum32; acc.idiff += idiff32;
         isum32 = idiff32 = 0;
     }

@@ -158,12 +158,12 @@ __device__ __forceinline__ uint32_t mix64to32(uint64_t z) {  // splitmix64 final
 
 template <typename T>
 __global__ void noise_kernel(char* base, size_t frame_stride, size_t plane_off, int pitch, int w, int h, int plane,
-                             uint64_t seed, int first_frame_no, int kind, int bits, int chroma_centered) {
+                             uint64_t seed, int first_frame_no, int frame_no_stride, int kind, int bits, int chroma_centered) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y;
     const int f = blockIdx.z;
     if (x >= w) return;
-    const uint64_t key = (seed * 0x100000001B3ull) ^ ((uint64_t)(uint32_t)(first_frame_no + f) << 40) ^
+    const uint64_t key = (seed * 0x100000001B3ull) ^ ((uint64_t)(uint32_t)(first_frame_no + f * frame_no_stride) << 40) ^
                          ((uint64_t)plane << 36) ^ ((uint64_t)y << 18) ^ (uint64_t)x;
     const uint32_t u = mix64to32(key);
     T* row = reinterpret_cast<T*>(base + (size_t)f * frame_stride + plane_off + (size_t)y * pitch);
@@ -327,7 +327,7 @@ int vszip_dev_clip_download(const vszip_dev_clip* c, int32_t frame, vszip_frame*
     return 0;
 }
 
-int vszip_dev_clip_fill_noise(vszip_dev_clip* c, uint64_t seed, int32_t first_frame_no) {
+int vszip_dev_clip_fill_noise(vszip_dev_clip* c, uint64_t seed, int32_t first_frame_no, int32_t frame_no_stride) {
     DeviceCtx* d = device_ctx(c->device_index);
     if (!d) { set_error("vszip_dev_clip_fill_noise: library not initialised"); return -1; }
     VSZ_CUDA(cudaSetDevice(c->ordinal));
@@ -342,10 +342,10 @@ int vszip_dev_clip_fill_noise(vszip_dev_clip* c, uint64_t seed, int32_t first_fr
             gz.z = (unsigned)std::min(32768, c->num_frames - f0);
             char* base = c->base + (size_t)f0 * l.frame_stride;
             switch (l.kind) {
-                case K_U8: noise_kernel<uint8_t><<<gz, 256, 0, d->batch_stream>>>(base, l.frame_stride, g.offset, g.pitch, g.w, g.h, p, seed, first_frame_no + f0, l.kind, l.bits, centered); break;
-                case K_U16: noise_kernel<uint16_t><<<gz, 256, 0, d->batch_stream>>>(base, l.frame_stride, g.offset, g.pitch, g.w, g.h, p, seed, first_frame_no + f0, l.kind, l.bits, centered); break;
-                case K_F16: noise_kernel<__half><<<gz, 256, 0, d->batch_stream>>>(base, l.frame_stride, g.offset, g.pitch, g.w, g.h, p, seed, first_frame_no + f0, l.kind, l.bits, centered); break;
-                case K_F32: noise_kernel<float><<<gz, 256, 0, d->batch_stream>>>(base, l.frame_stride, g.offset, g.pitch, g.w, g.h, p, seed, first_frame_no + f0, l.kind, l.bits, centered); break;
+                case K_U8: noise_kernel<uint8_t><<<gz, 256, 0, d->batch_stream>>>(base, l.frame_stride, g.offset, g.pitch, g.w, g.h, p, seed, first_frame_no + f0 * frame_no_stride, frame_no_stride, l.kind, l.bits, centered); break;
+                case K_U16: noise_kernel<uint16_t><<<gz, 256, 0, d->batch_stream>>>(base, l.frame_stride, g.offset, g.pitch, g.w, g.h, p, seed, first_frame_no + f0 * frame_no_stride, frame_no_stride, l.kind, l.bits, centered); break;
+                case K_F16: noise_kernel<__half><<<gz, 256, 0, d->batch_stream>>>(base, l.frame_stride, g.offset, g.pitch, g.w, g.h, p, seed, first_frame_no + f0 * frame_no_stride, frame_no_stride, l.kind, l.bits, centered); break;
+                case K_F32: noise_kernel<float><<<gz, 256, 0, d->batch_stream>>>(base, l.frame_stride, g.offset, g.pitch, g.w, g.h, p, seed, first_frame_no + f0 * frame_no_stride, frame_no_stride, l.kind, l.bits, centered); break;
             }
             count_launch();
         }
