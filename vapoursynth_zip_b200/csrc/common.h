@@ -84,8 +84,8 @@ int slot_reserve(DeviceCtx* d, Slot* s, int which, size_t bytes);  // grow pin[w
 
 // host <-> slot staging of the selected planes of one frame (async on s->stream)
 int stage_in(Slot* s, int which, const FrameLayout& l, const vszip_frame* host, const bool mask[3]);
-int stage_out_begin(Slot* s, const FrameLayout& l, const bool mask[3]);  // D2H into pinned, async
-void stage_out_finish(Slot* s, const FrameLayout& l, vszip_frame* host, const bool mask[3]);  // after sync
+int stage_out_begin(Slot* s, const FrameLayout& l, vszip_frame* host, const bool mask[3], bool direct[3]);  // async D2H
+void stage_out_finish(Slot* s, const FrameLayout& l, vszip_frame* host, const bool mask[3], const bool direct[3]);  // after sync
 
 }  // namespace vsz
 

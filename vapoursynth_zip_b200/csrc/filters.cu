@@ -172,9 +172,10 @@ int vszip_boxblur_get_frame(const vszip_filter* f, int32_t n, const vszip_frame*
     if (stage_in(s, 0, f->layout, src, f->process)) return -1;
     int rc = run_boxblur(f->layout, f->process, s->dev[0], 0, s->dev[2], 0, 1, (int)f->hradius, f->hpasses, (int)f->vradius, f->vpasses, s->stream);
     if (rc) return rc;
-    if (stage_out_begin(s, f->layout, f->process)) return -1;
+    bool direct[3];
+    if (stage_out_begin(s, f->layout, dst, f->process, direct)) return -1;
     VSZ_CUDA(cudaStreamSynchronize(s->stream));
-    stage_out_finish(s, f->layout, dst, f->process);
+    stage_out_finish(s, f->layout, dst, f->process, direct);
     return 0;
 }
 
@@ -370,9 +371,10 @@ int vszip_bilateral_get_frame(const vszip_filter* f, int32_t n, const vszip_fram
     const BilateralLaunch bp = bilateral_launch(f, device_index_of(d));
     int rc = run_bilateral(f->layout, f->process, s->dev[0], 0, ref ? s->dev[1] : nullptr, 0, s->dev[2], 0, 1, bp, s->stream);
     if (rc) return rc;
-    if (stage_out_begin(s, f->layout, f->process)) return -1;
+    bool direct[3];
+    if (stage_out_begin(s, f->layout, dst, f->process, direct)) return -1;
     VSZ_CUDA(cudaStreamSynchronize(s->stream));
-    stage_out_finish(s, f->layout, dst, f->process);
+    stage_out_finish(s, f->layout, dst, f->process, direct);
     return 0;
 }
 

@@ -48,7 +48,8 @@ struct StatsJob {
     StatsPlane pl[3];
     // scratch
     Partial* partials;        // [frame][plane][MAX_CTAS_PER_PLANE]
-    unsigned int* counters;   // [frame][plane] completed-CTA counters (two sets: pass1/avg, pass2)
+    unsigned int* counters;   // [frame][plane] completed-CTA counters of pass 1 / the single-pass kernels
+    unsigned int* counters2;  // [frame][plane] completed-CTA counters of pass 2
     unsigned int* coarse;     // [frame][plane][256]
     unsigned int* fine;       // [frame][plane][2][256]
     StatsRaw* out;            // [frame][plane]
@@ -432,7 +433,7 @@ __global__ void __launch_bounds__(NT) hist_fine_kernel(const StatsJob j) {
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
-        const unsigned int done = atomicAdd(j.counters + (size_t)(gridDim.y + frame) * j.nplanes + k, 1u);
+        const unsigned int done = atomicAdd(j.counters2 + (size_t)frame * j.nplanes + k, 1u);
         s_last = (done == (unsigned)p.nctas - 1u);
     }
     __syncthreads();
@@ -489,7 +490,7 @@ static StatsJob make_job(const FrameLayout& l, const bool mask[3], const char* a
     j.nplanes = k; j.ctas_per_frame = cta;
     const size_t n = (size_t)count * k;
     char* sp = (char*)scratch;
-    j.counters = (unsigned int*)sp; sp += align256(2 * n * 4);
+    j.counters = (unsigned int*)sp; j.counters2 = j.counters + n; sp += align256(2 * n * 4);
     j.coarse = (unsigned int*)sp; sp += align256(n * 256 * 4);
     j.fine = (unsigned int*)sp; sp += align256(n * 512 * 4);
     *zero_bytes = (size_t)(sp - (char*)scratch);
@@ -499,19 +500,33 @@ static StatsJob make_job(const FrameLayout& l, const bool mask[3], const char* a
 }
 
 template <typename T>
-static int launch_minmax_t(StatsJob j, int count, bool no_thr, bool has_b, cudaStream_t st) {
-    for (int f0 = 0; f0 < count; f0 += 32768) {
-        const int nf = std::min(32768, count - f0);
-        if (f0 != 0) { set_error("PlaneMinMax: batches above 32768 frames are not supported"); return -2; }
-        const dim3 grid(j.ctas_per_frame, nf);
-        if (no_thr) {
-            if (has_b) stats_kernel<T, true, false><<<grid, NT, 0, st>>>(j);
-            else stats_kernel<T, false, false><<<grid, NT, 0, st>>>(j);
-            count_launch();
-        } else {
-            if (has_b) hist_coarse_kernel<T, true><<<grid, NT, 0, st>>>(j);
-            else hist_coarse_kernel<T, false><<<grid, NT, 0, st>>>(j);
-            hist_fine_kernel<T><<<grid, NT, 0, st>>>(j);
+static int launch_minmax_t(StatsJob j, int count, bool no_thr, bool has_b, size_t bytes_per_frame, cudaStream_t st) {
+    if (count > 32768) { set_error("PlaneMinMax: batches above 32768 frames are not supported"); return -2; }
+    if (no_thr) {
+        const dim3 grid(j.ctas_per_frame, count);
+        if (has_b) stats_kernel<T, true, false><<<grid, NT, 0, st>>>(j);
+        else stats_kernel<T, false, false><<<grid, NT, 0, st>>>(j);
+        count_launch();
+    } else {
+        // Pass 2 re-reads what pass 1 read.  Running the pair on L2-sized chunks (<= 64 MB) was measured SLOWER on
+        // B200 (3-frame launches leave the GPU under-filled and add launch gaps: 42 k vs 77 k fps on 4K GRAY16), so the
+        // whole batch goes through each pass; single frames (<= 64 MB) still hit L2 on the second read.
+        (void)bytes_per_frame;
+        const int chunk = count;
+        const int np = j.nplanes;
+        for (int f0 = 0; f0 < count; f0 += chunk) {
+            const int nf = std::min(chunk, count - f0);
+            StatsJob c = j;
+            c.a += (size_t)f0 * j.a_fs;
+            if (has_b) c.b += (size_t)f0 * j.b_fs;
+            c.partials += (size_t)f0 * np * MAX_CTAS_PER_PLANE;
+            c.counters += (size_t)f0 * np; c.counters2 += (size_t)f0 * np;
+            c.coarse += (size_t)f0 * np * 256; c.fine += (size_t)f0 * np * 512;
+            c.out += (size_t)f0 * np;
+            const dim3 grid(j.ctas_per_frame, nf);
+            if (has_b) hist_coarse_kernel<T, true><<<grid, NT, 0, st>>>(c);
+            else hist_coarse_kernel<T, false><<<grid, NT, 0, st>>>(c);
+            hist_fine_kernel<T><<<grid, NT, 0, st>>>(c);
             count_launch(2);
         }
     }
@@ -536,11 +551,13 @@ int run_planeminmax(const FrameLayout& l, const bool mask[3], const char* a, siz
         j.pl[k].tmax = (unsigned int)(total * (double)maxthr);
     }
     const bool has_b = b != nullptr;
+    size_t fb = 0;
+    for (int k = 0; k < j.nplanes; ++k) fb += (size_t)j.pl[k].w * j.pl[k].h * l.bps * (has_b ? 2 : 1);
     switch (l.kind) {
-        case K_U8: return launch_minmax_t<uint8_t>(j, count, no_thr, has_b, st);
-        case K_U16: return launch_minmax_t<uint16_t>(j, count, no_thr, has_b, st);
-        case K_F16: return launch_minmax_t<__half>(j, count, no_thr, has_b, st);
-        case K_F32: return launch_minmax_t<float>(j, count, no_thr, has_b, st);
+        case K_U8: return launch_minmax_t<uint8_t>(j, count, no_thr, has_b, fb, st);
+        case K_U16: return launch_minmax_t<uint16_t>(j, count, no_thr, has_b, fb, st);
+        case K_F16: return launch_minmax_t<__half>(j, count, no_thr, has_b, fb, st);
+        case K_F32: return launch_minmax_t<float>(j, count, no_thr, has_b, fb, st);
     }
     return -1;
 }

@@ -116,11 +116,24 @@ static void copy_rows(char* dst, ptrdiff_t dpitch, const char* src, ptrdiff_t sp
     for (int y = 0; y < rows; ++y) memcpy(dst + dpitch * y, src + spitch * y, row_bytes);
 }
 
+// true when `p` is page-locked host memory the DMA engines can reach directly (cudaHostAlloc /
+// cudaHostRegister, e.g. a frame buffer the application pinned): the staging memcpy is skipped then.
+static bool is_pinned_host(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
 int stage_in(Slot* s, int which, const FrameLayout& l, const vszip_frame* host, const bool mask[3]) {
     for (int p = 0; p < l.nplanes; ++p) {
         if (!mask[p]) continue;
         const PlaneGeom& g = l.pl[p];
         const size_t row_bytes = (size_t)g.w * l.bps;
+        if (is_pinned_host(host->data[p])) {
+            VSZ_CUDA(cudaMemcpy2DAsync(s->dev[which] + g.offset, g.pitch, host->data[p], host->stride[p], row_bytes, g.h,
+                                       cudaMemcpyHostToDevice, s->stream));
+            continue;
+        }
         // pageable VapourSynth memory -> pinned staging (same layout as the device frame)
         copy_rows(s->pin[which] + g.offset, g.pitch, (const char*)host->data[p], host->stride[p], row_bytes, g.h);
         VSZ_CUDA(cudaMemcpyAsync(s->dev[which] + g.offset, s->pin[which] + g.offset, (size_t)g.pitch * g.h,
@@ -129,19 +142,28 @@ int stage_in(Slot* s, int which, const FrameLayout& l, const vszip_frame* host, 
     return 0;
 }
 
-int stage_out_begin(Slot* s, const FrameLayout& l, const bool mask[3]) {
+// D2H of the result planes: straight into the destination when it is pinned, else into the slot's
+// pinned buffer (stage_out_finish then copies it out after the stream has been synchronised).
+int stage_out_begin(Slot* s, const FrameLayout& l, vszip_frame* host, const bool mask[3], bool direct[3]) {
     for (int p = 0; p < l.nplanes; ++p) {
+        direct[p] = false;
         if (!mask[p]) continue;
         const PlaneGeom& g = l.pl[p];
+        if (is_pinned_host(host->data[p])) {
+            direct[p] = true;
+            VSZ_CUDA(cudaMemcpy2DAsync(host->data[p], host->stride[p], s->dev[2] + g.offset, g.pitch, (size_t)g.w * l.bps, g.h,
+                                       cudaMemcpyDeviceToHost, s->stream));
+            continue;
+        }
         VSZ_CUDA(cudaMemcpyAsync(s->pin[2] + g.offset, s->dev[2] + g.offset, (size_t)g.pitch * g.h,
                                  cudaMemcpyDeviceToHost, s->stream));
     }
     return 0;
 }
 
-void stage_out_finish(Slot* s, const FrameLayout& l, vszip_frame* host, const bool mask[3]) {
+void stage_out_finish(Slot* s, const FrameLayout& l, vszip_frame* host, const bool mask[3], const bool direct[3]) {
     for (int p = 0; p < l.nplanes; ++p) {
-        if (!mask[p]) continue;
+        if (!mask[p] || direct[p]) continue;
         const PlaneGeom& g = l.pl[p];
         copy_rows((char*)host->data[p], host->stride[p], s->pin[2] + g.offset, g.pitch, (size_t)g.w * l.bps, g.h);
     }
