@@ -150,6 +150,12 @@ struct StageOps {
     }
 };
 
+// compile-time loop: f(std::integral_constant<int, 0>{}), ..., f(std::integral_constant<int, N-1>{})
+template <class F, int... Is>
+__device__ __forceinline__ void static_for_impl(std::integer_sequence<int, Is...>, F& f) { (f(std::integral_constant<int, Is>{}), ...); }
+template <int N, class F>
+__device__ __forceinline__ void static_for(F&& f) { static_for_impl(std::make_integer_sequence<int, N>{}, f); }
+
 // --------------------------------------------------------------------------- the per-thread pipeline
 // Skewed schedule: stage p (1..P) works at time t on position x = t - p*D, D = r+1.  Its operands are
 // what stage p-1 published one step earlier: a = v_{p-1}(t-1) (position x+r) and b = the ring entry that
@@ -227,6 +233,91 @@ struct LinePipe {
         }
         advance();
         return nv[P - 1];
+    }
+
+    // ---- edge steps with a compile-time set of live stages (no per-stage branching) -------------------------
+    // Start-up phase k (t in [kD, (k+1)D)): stages 1..k are live, stage k itself starts (x = 0) on the first
+    // step of the phase; producers 0..k publish.  Requires n >= fast_begin().
+    template <int Q> __device__ __forceinline__ uint32_t seed_stage() {
+        const int r = ap.r;
+        // ring Q holds positions -r..r of stage Q; position p sits (r - p + 1) slots behind slot(t)
+        Ops::init(S[Q], ap, [&](int pos) { return cell(back(r - pos + 1), Q); });
+        for (int k = 1; k <= r; ++k) {  // virtual position -k: SYM -> k-1, reflect-101 (comptime V) -> k
+            const int from = (MODE == MODE_CTV) ? k : k - 1;
+            cell(back(r + k + 1), Q) = cell(back(r - from + 1), Q);
+        }
+        pa[Q] = cell(slot, Q);  // the seeding rewrote slot(t) and slot(t+1) of ring Q
+        pb[Q] = cell(slot + 1 == ap.ring ? 0 : slot + 1, Q);
+        if constexpr (MODE == MODE_CTV) return Ops::emit(S[Q], ap);
+        const uint32_t c = cell(back(1), Q);
+        return Ops::update(S[Q], c, c, ap);  // the reference's x = 0 step adds in[r] - in[r]
+    }
+
+    template <int ACT, bool INIT>
+    __device__ __forceinline__ uint32_t step_start(uint32_t v_in) {
+        uint32_t nv[P];
+        static_for<P>([&](auto qc) {
+            constexpr int q = decltype(qc)::value;
+            if constexpr (INIT && q == ACT - 1) nv[q] = seed_stage<q>();
+            else if constexpr (q < ACT) nv[q] = Ops::update(S[q], va[q], vb[q], ap);
+            else nv[q] = 0u;
+        });
+        static_for<P>([&](auto qc) {
+            constexpr int q = decltype(qc)::value;
+            if constexpr (q <= ACT) publish(q, (q == 0) ? v_in : nv[q > 0 ? q - 1 : 0]);
+            if constexpr (q < ACT) rotate(q);
+        });
+        advance();
+        return nv[P - 1];
+    }
+
+    // Drain phase K (t in [n + KD, n + (K+1)D)): producer K is in its mirrored tail (first r steps of the phase,
+    // j = step index inside the phase), producers > K still publish real samples, consumers K+1..P are live.
+    template <int K, bool MIRROR>
+    __device__ __forceinline__ uint32_t step_drain(int j) {
+        uint32_t nv[P];
+        static_for<P>([&](auto qc) {
+            constexpr int q = decltype(qc)::value;
+            if constexpr (q >= K) nv[q] = Ops::update(S[q], va[q], vb[q], ap);
+            else nv[q] = 0u;
+        });
+        static_for<P>([&](auto qc) {
+            constexpr int q = decltype(qc)::value;
+            if constexpr (q == K) {
+                if constexpr (MIRROR) publish(q, cell(back((MODE == MODE_CTV) ? 1 + ap.r : 1 + 2 * j), q));
+                rotate(q);
+            } else if constexpr (q > K) {
+                publish(q, nv[q - 1]);
+                rotate(q);
+            }
+        });
+        advance();
+        return nv[P - 1];
+    }
+
+    // Dispatcher for callers that cannot structure their loops by phase (the tiled H kernel): phase counters
+    // live in the pipe.  Requires n >= fast_begin().
+    int ek = 0, ej = 0;
+    __device__ __forceinline__ uint32_t step_any(int t, uint32_t v_in) {
+        if (t >= fast_begin() && t < n) return step_fast(v_in);
+        uint32_t o = 0u;
+        if (t < n) {
+            static_for<P + 1>([&](auto kc) {
+                constexpr int k = decltype(kc)::value;
+                if (ek == k) {
+                    if (ej == 0 && k >= 1) o = step_start<k, (k >= 1)>(v_in);
+                    else o = step_start<k, false>(v_in);
+                }
+            });
+        } else {
+            if (t == n) { ek = 0; ej = 0; }
+            static_for<P>([&](auto kc) {
+                constexpr int k = decltype(kc)::value;
+                if (ek == k) o = (ej < ap.r) ? step_drain<k, true>(ej) : step_drain<k, false>(0);
+            });
+        }
+        if (++ej == D) { ej = 0; ++ek; }
+        return o;
     }
 
     // any t: also seeds stages that start at this step and publishes mirrored tails.  v_in is the input
@@ -326,12 +417,30 @@ __global__ void __launch_bounds__(NT) blur_v_kernel(const BatchJob job, const Ax
     for (int i = 0; i < ST::AHEAD; ++i) fetch(i);
 
     int t = 0;
-    for (; t < t_fast; ++t) {  // start-up: stages come alive one after the other
-        fetch(t + ST::AHEAD);
-        cp_async_wait<ST::AHEAD>();
-        const uint32_t o = pipe.step_edge(t, stage[(t & (ST::SLOTS - 1)) * NT]);
-        const int x = t - lag;
-        if (x >= 0 && x < n) store(x, o);
+    const bool phased = (n >= pipe.fast_begin());
+    if (phased) {
+        // start-up: phase k has exactly k live stages (compile-time), stage k is seeded on the phase's first step
+        static_for<P + 1>([&](auto kc) {
+            constexpr int k = decltype(kc)::value;
+            const int steps = (k == P) ? 1 : pipe.D;
+            for (int j = 0; j < steps; ++j, ++t) {
+                fetch(t + ST::AHEAD);
+                cp_async_wait<ST::AHEAD>();
+                const uint32_t v = stage[(t & (ST::SLOTS - 1)) * NT];
+                uint32_t o;
+                if (j == 0 && k >= 1) o = pipe.template step_start<k, (k >= 1)>(v);
+                else o = pipe.template step_start<k, false>(v);
+                if (k == P) store(0, o);
+            }
+        });
+    } else {
+        for (; t < t_fast; ++t) {  // tiny lines: generic edge step
+            fetch(t + ST::AHEAD);
+            cp_async_wait<ST::AHEAD>();
+            const uint32_t o = pipe.step_edge(t, stage[(t & (ST::SLOTS - 1)) * NT]);
+            const int x = t - lag;
+            if (x >= 0 && x < n) store(x, o);
+        }
     }
     // steady state: U steps per iteration with running pointers (no per-step 64-bit multiplies, no
     // clamping: every prefetched row is < n here).  U = 4 keeps the loop body inside the L0 i-cache.
@@ -360,10 +469,21 @@ __global__ void __launch_bounds__(NT) blur_v_kernel(const BatchJob job, const Ax
         store(t - lag, pipe.step_fast(stage[(t & (ST::SLOTS - 1)) * NT]));
     }
     cp_async_wait<0>();
-    for (; t < total; ++t) {  // drain: no more input, mirrored tails come from the rings
-        const uint32_t o = pipe.step_edge(t, 0u);
-        const int x = t - lag;
-        if (x >= 0 && x < n) store(x, o);
+    if (phased) {
+        // drain: phase k has producer k in its mirrored tail and stages k+1..P live
+        static_for<P>([&](auto kc) {
+            constexpr int k = decltype(kc)::value;
+            for (int j = 0; j < pipe.D; ++j, ++t) {
+                const uint32_t o = (j < ap.r) ? pipe.template step_drain<k, true>(j) : pipe.template step_drain<k, false>(0);
+                store(t - lag, o);
+            }
+        });
+    } else {
+        for (; t < total; ++t) {
+            const uint32_t o = pipe.step_edge(t, 0u);
+            const int x = t - lag;
+            if (x >= 0 && x < n) store(x, o);
+        }
     }
 }
 
@@ -406,6 +526,7 @@ __global__ void __launch_bounds__(NT) blur_h_kernel(const BatchJob job, const Ax
     pipe.start(ring + threadIdx.x, pj.w, ap);
     const int n = pj.w, lag = pipe.lag(), total = n + lag;
     const int t_fast = min(pipe.fast_begin(), n);
+    const bool phased = (n >= pipe.fast_begin());
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int flushed = 0;  // output positions [0, flushed) are already in global memory
@@ -467,7 +588,8 @@ __global__ void __launch_bounds__(NT) blur_h_kernel(const BatchJob job, const Ax
             for (int t = t0; t < t1; ++t) {
                 const uint32_t v = in_tile[(t - t0) * TL::PITCH_W + threadIdx.x];
                 uint32_t o;
-                if (t >= t_fast && t < n) o = pipe.step_fast(v);
+                if (phased) o = pipe.step_any(t, v);
+                else if (t >= t_fast && t < n) o = pipe.step_fast(v);
                 else o = pipe.step_edge(t, v);
                 const int x = t - lag;
                 if (x >= 0 && x < n) out_tile[(x & (TL::OUT - 1)) * TL::PITCH_W + threadIdx.x] = o;
