@@ -602,13 +602,26 @@ __global__ void __launch_bounds__(NT) blur_h_kernel(const BatchJob job, const Ax
         for (int xb = flushed; xb < upto; xb += 32) {
             // one 32-bit store per EPW samples, same lane->(row, word) mapping as the loads
             const int x = xb + lw * EPW;
-            if (x < upto) {
-                char* q = ldst + (size_t)xb * sizeof(T);
-                const bool whole = (x + EPW <= upto);
+            char* q = ldst + (size_t)xb * sizeof(T);
+            if (full && xb + 32 <= upto) {
+                // common case (full CTA, complete block): branch-free, all shared-memory reads issued before the stores
+                uint32_t wv[NLD];
 #pragma unroll
                 for (int i = 0; i < NLD; ++i) {
                     const int rr = (i * NWARP + warp) * RPI + lr;
-                    if (full || rr < nrows) {
+                    T e[EPW];
+#pragma unroll
+                    for (int k = 0; k < EPW; ++k) e[k] = out_t[(((x + k) & (TL::OUT - 1)) * TL::PITCH_W) * NL + rr];
+                    wv[i] = *reinterpret_cast<const uint32_t*>(e);
+                }
+#pragma unroll
+                for (int i = 0; i < NLD; ++i) { *reinterpret_cast<uint32_t*>(q) = wv[i]; q += lstep_d; }
+            } else if (x < upto) {
+                const bool whole = (x + EPW <= upto);
+#pragma unroll 4
+                for (int i = 0; i < NLD; ++i) {
+                    const int rr = (i * NWARP + warp) * RPI + lr;
+                    if (rr < nrows) {
                         T e[EPW];
 #pragma unroll
                         for (int k = 0; k < EPW; ++k) e[k] = out_t[(((x + k) & (TL::OUT - 1)) * TL::PITCH_W) * NL + rr];
@@ -645,27 +658,118 @@ template <typename T> __device__ __forceinline__ T st_f(float v);
 template <> __device__ __forceinline__ float st_f<float>(float v) { return v; }
 template <> __device__ __forceinline__ __half st_f<__half>(float v) { return __float2half_rn(v); }
 
-template <typename T, bool VERTICAL>
-__global__ void __launch_bounds__(256) ctf_kernel(const BatchJob job, int r, float div) {
+// Tiled version.  "Line axis" = the blurred direction (y for the V pass, x for the H pass), "cross axis" the
+// other one.  A CTA of 128 threads owns 128 cross positions x TL line positions.  The products div*v of the
+// TL + 2r line positions it needs are staged once in shared memory as [line][cross] (pitch 129: the H pass
+// fills it with lanes along the line axis, every pass reads it with lanes along the cross axis, both
+// conflict-free).  A thread then produces its line in groups of 4 outputs that share one sweep over 2r+4
+// products, each output adding its 2r+1 products in tap order (acc = 0 + m0 + m1 + ...): bit-exact.
+// Edge outputs (within r of either end) take the generic R101q tap loop.
+static constexpr int CTF_NT = 128, CTF_TL = 32, CTF_PITCH = 129;
+
+template <typename T, bool HORIZ>
+__global__ void __launch_bounds__(CTF_NT) ctf_kernel(const BatchJob job, int r, float div, int3 line_blocks) {
+    extern __shared__ float ctf_smem[];
     int local;
     const PlaneJob& pj = find_plane(job, blockIdx.x, local);
-    // each CTA covers 256 consecutive samples of one row
-    const int ctas_per_row = (pj.w + 255) / 256;
-    const int y = local / ctas_per_row;
-    const int x = (local % ctas_per_row) * 256 + threadIdx.x;
-    if (x >= pj.w) return;
+    const int k = (int)(&pj - job.pl);
+    const int nlb = k == 0 ? line_blocks.x : (k == 1 ? line_blocks.y : line_blocks.z);
+    const int lb = local % nlb, cb = local / nlb;
+    const int n = HORIZ ? pj.w : pj.h, ncross = HORIZ ? pj.h : pj.w;
+    const int l0 = lb * CTF_TL, l1 = min(l0 + CTF_TL, n);
+    const int c0 = cb * CTF_NT;
+    const int lo = max(l0 - r, 0), hi = min(l1 - 1 + r, n - 1), cnt = hi - lo + 1;
     const char* src = job.src + (size_t)blockIdx.y * job.src_fs + pj.src_off;
     char* dst = job.dst + (size_t)blockIdx.y * job.dst_fs + pj.dst_off;
-    float acc = 0.0f;
-    const int i = VERTICAL ? y : x, n = VERTICAL ? pj.h : pj.w;
-    const bool interior = (i >= r) && (i + r < n);
-    for (int k = 0; k <= 2 * r; ++k) {
-        const int idx = interior ? (i - r + k) : r101q(i, k, r, n);
-        const T* p = VERTICAL ? reinterpret_cast<const T*>(src + (size_t)idx * pj.src_pitch) + x
-                              : reinterpret_cast<const T*>(src + (size_t)y * pj.src_pitch) + idx;
-        acc = __fadd_rn(acc, __fmul_rn(div, ld_f<T>(p)));
+    float* P = ctf_smem;                               // [cnt][129] products
+    float* O = ctf_smem + (CTF_TL + 2 * r) * CTF_PITCH;  // [TL][129] outputs (H pass only)
+    const int c = threadIdx.x;
+    const bool live = (c0 + c) < ncross;
+
+    if constexpr (!HORIZ) {
+        // every thread stages (and later reads) only its own column: no barrier needed
+        if (live) {
+            const char* col = src + (size_t)lo * pj.src_pitch + (size_t)(c0 + c) * sizeof(T);
+            int j = 0;
+            for (; j + 8 <= cnt; j += 8) {  // 8 independent loads in flight per thread
+                float v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = ld_f<T>(reinterpret_cast<const T*>(col + (size_t)(j + u) * pj.src_pitch));
+#pragma unroll
+                for (int u = 0; u < 8; ++u) P[(j + u) * CTF_PITCH + c] = __fmul_rn(div, v[u]);
+            }
+            for (; j < cnt; ++j) P[j * CTF_PITCH + c] = __fmul_rn(div, ld_f<T>(reinterpret_cast<const T*>(col + (size_t)j * pj.src_pitch)));
+        }
+    } else {
+        const int lane = c & 31, warp = c >> 5;
+        // 4 rows x up to 4 lane-strided segments = up to 16 independent loads in flight per thread
+        for (int rr0 = warp * 4; rr0 < CTF_NT; rr0 += CTF_NT / 8) {
+            float v[4][4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int rr = min(rr0 + u, CTF_NT - 1);
+                const T* row = reinterpret_cast<const T*>(src + (size_t)min(c0 + rr, ncross - 1) * pj.src_pitch) + lo;
+#pragma unroll
+                for (int s2 = 0; s2 < 4; ++s2) v[u][s2] = ld_f<T>(row + min(lane + 32 * s2, cnt - 1));
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int s2 = 0; s2 < 4; ++s2)
+                    if (lane + 32 * s2 < cnt) P[(lane + 32 * s2) * CTF_PITCH + rr0 + u] = __fmul_rn(div, v[u][s2]);
+        }
+        __syncthreads();
     }
-    reinterpret_cast<T*>(dst + (size_t)y * pj.dst_pitch)[x] = st_f<T>(acc);
+
+    if (live) {
+        const float* Pc = P + c;
+        for (int i0 = l0; i0 < l1; i0 += 4) {
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+            const bool interior4 = (i0 >= r) && (i0 + 3 + r < n) && (i0 + 3 < l1);
+            if (interior4) {
+                const float* q = Pc + (i0 - r - lo) * CTF_PITCH;
+                const int m = 2 * r;  // output g adds products g .. g + 2r of this sweep
+                float v = q[0]; a0 = __fadd_rn(a0, v);
+                v = q[CTF_PITCH]; a0 = __fadd_rn(a0, v); a1 = __fadd_rn(a1, v);
+                v = q[2 * CTF_PITCH]; a0 = __fadd_rn(a0, v); a1 = __fadd_rn(a1, v); a2 = __fadd_rn(a2, v);
+                q += 3 * CTF_PITCH;
+                for (int t = 3; t <= m; ++t, q += CTF_PITCH) {
+                    v = q[0];
+                    a0 = __fadd_rn(a0, v); a1 = __fadd_rn(a1, v); a2 = __fadd_rn(a2, v); a3 = __fadd_rn(a3, v);
+                }
+                // t = m+1, m+2, m+3 (for r == 1, m = 2: the loop above did not run and a0 is already complete)
+                v = q[0]; a1 = __fadd_rn(a1, v); a2 = __fadd_rn(a2, v); a3 = __fadd_rn(a3, v);
+                v = q[CTF_PITCH]; a2 = __fadd_rn(a2, v); a3 = __fadd_rn(a3, v);
+                v = q[2 * CTF_PITCH]; a3 = __fadd_rn(a3, v);
+            } else {
+                float* acc[4] = {&a0, &a1, &a2, &a3};
+                for (int g = 0; g < 4 && i0 + g < l1; ++g) {
+                    float a = 0.f;
+                    const int i = i0 + g;
+                    for (int t = 0; t <= 2 * r; ++t) a = __fadd_rn(a, Pc[(r101q(i, t, r, n) - lo) * CTF_PITCH]);
+                    *acc[g] = a;
+                }
+            }
+            const float res[4] = {a0, a1, a2, a3};
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const int i = i0 + g;
+                if (i < l1) {
+                    if constexpr (HORIZ) O[(i - l0) * CTF_PITCH + c] = res[g];
+                    else reinterpret_cast<T*>(dst + (size_t)i * pj.dst_pitch)[c0 + c] = st_f<T>(res[g]);
+                }
+            }
+        }
+    }
+    if constexpr (HORIZ) {
+        __syncthreads();
+        const int lane = c & 31, warp = c >> 5;
+        for (int rr = warp; rr < CTF_NT; rr += CTF_NT / 32) {
+            if (c0 + rr >= ncross) break;
+            T* row = reinterpret_cast<T*>(dst + (size_t)(c0 + rr) * pj.dst_pitch) + l0;
+            for (int j = lane; j < l1 - l0; j += 32) row[j] = st_f<T>(O[j * CTF_PITCH + rr]);
+        }
+    }
 }
 
 // =========================================================================== host-side launchers
@@ -786,17 +890,27 @@ template <typename T>
 static int run_ct_float(const FrameLayout& l, const bool mask[3], const char* src, size_t sfs, char* tmp, size_t tfs, char* dst,
                         size_t dfs, int count, int r, cudaStream_t st) {
     const float div = 1.0f / (float)(2 * r + 1);
-    auto ctas = [](int w, int h) { return ((w + 255) / 256) * h; };
-    BatchJob jv = make_batch(l, mask, src, sfs, nullptr, 0, tmp, tfs, ctas);
-    BatchJob jh = make_batch(l, mask, tmp, tfs, nullptr, 0, dst, dfs, ctas);
+    auto blocks = [](int len) { return (len + CTF_TL - 1) / CTF_TL; };
+    auto cross = [](int len) { return (len + CTF_NT - 1) / CTF_NT; };
+    BatchJob jv = make_batch(l, mask, src, sfs, nullptr, 0, tmp, tfs, [&](int w, int h) { return blocks(h) * cross(w); });
+    BatchJob jh = make_batch(l, mask, tmp, tfs, nullptr, 0, dst, dfs, [&](int w, int h) { return blocks(w) * cross(h); });
     if (jv.ctas_per_frame == 0) return 0;
+    int3 lbv = make_int3(1, 1, 1), lbh = make_int3(1, 1, 1);
+    for (int k = 0; k < jv.nplanes; ++k) {
+        (k == 0 ? lbv.x : (k == 1 ? lbv.y : lbv.z)) = blocks(jv.pl[k].h);
+        (k == 0 ? lbh.x : (k == 1 ? lbh.y : lbh.z)) = blocks(jh.pl[k].w);
+    }
+    const size_t smem_v = (size_t)(CTF_TL + 2 * r) * CTF_PITCH * sizeof(float);
+    const size_t smem_h = smem_v + (size_t)CTF_TL * CTF_PITCH * sizeof(float);
+    VSZ_CUDA(cudaFuncSetAttribute(ctf_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v));
+    VSZ_CUDA(cudaFuncSetAttribute(ctf_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h));
     for (int f0 = 0; f0 < count; f0 += 65535) {
         const int nf = std::min(65535, count - f0);
         BatchJob a = jv, b = jh;
         a.src += (size_t)f0 * sfs; a.dst += (size_t)f0 * tfs;
         b.src += (size_t)f0 * tfs; b.dst += (size_t)f0 * dfs;
-        ctf_kernel<T, true><<<dim3(jv.ctas_per_frame, nf), 256, 0, st>>>(a, r, div);
-        ctf_kernel<T, false><<<dim3(jh.ctas_per_frame, nf), 256, 0, st>>>(b, r, div);
+        ctf_kernel<T, false><<<dim3(jv.ctas_per_frame, nf), CTF_NT, smem_v, st>>>(a, r, div, lbv);
+        ctf_kernel<T, true><<<dim3(jh.ctas_per_frame, nf), CTF_NT, smem_h, st>>>(b, r, div, lbh);
         count_launch(2);
     }
     VSZ_CUDA(cudaGetLastError());
