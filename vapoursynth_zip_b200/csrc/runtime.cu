@@ -68,7 +68,7 @@ size_t layout_algorithmic_bytes(const FrameLayout& l) {
 // --------------------------------------------------------------------------- contexts
 static std::mutex g_init_mu;
 static std::vector<DeviceCtx*> g_devs;
-static constexpr int kSlotsPerDevice = 8;
+static constexpr int kSlotsPerDevice = 16;
 
 Slot* DeviceCtx::acquire() {
     std::unique_lock<std::mutex> lk(mu);
