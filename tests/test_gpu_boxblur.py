@@ -77,6 +77,15 @@ def test_tiny_and_minimum_sizes():
 
 
 @pytest.mark.parametrize("fmt", ["GRAY8", "GRAY16", "GRAYS"])
+def test_very_large_radius_uses_global_fallback(fmt):
+    """Radii whose 2r+1-slot delay ring cannot fit in shared memory still work (and stay bit-exact)."""
+    clip = noise_clip(fmt, 1900, 1000, seed=4)
+    for args in (dict(hradius=900, hpasses=2, vradius=480, vpasses=1), dict(hradius=0, hpasses=0, vradius=499, vpasses=2),
+                 dict(hradius=940, vradius=0, vpasses=0)):
+        assert_same_planes(run(clip, **args)["planes"], oa.boxblur(clip, **args)["planes"], f"{fmt} {args}")
+
+
+@pytest.mark.parametrize("fmt", ["GRAY8", "GRAY16", "GRAYS"])
 def test_pass_composition(fmt):
     """Two passes in one call == two chained single-pass calls, bit-identical (reference test_pass_composition)."""
     src = to_node(fx.make_clip(fmt))

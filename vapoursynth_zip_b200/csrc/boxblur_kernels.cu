@@ -863,6 +863,66 @@ static int launch_axis_p(int P, const FrameLayout& l, const bool mask[3], const 
     return -3;
 }
 
+// --------------------------------------------------------------------------- very large radii
+// When even one 2r+1-slot delay ring per line does not fit in shared memory (r in the hundreds), a pass is
+// run straight from global memory: one thread per packed line group, the reference's own index rules
+// (src/filters/boxblur_runtime.zig:24-40), out of place.  Slow (two dependent global reads per step, the
+// H direction uncoalesced) but bit-exact; it only exists so that no legal radius is rejected.
+template <typename T, bool HORIZ>
+__global__ void __launch_bounds__(128) blur_global_kernel(const BatchJob job, const AxisParams ap) {
+    using Ops = StageOps<T, MODE_RT>;
+    using Acc = typename Px<T>::Acc;
+    constexpr int NL = Px<T>::NL;
+    int local;
+    const PlaneJob& pj = find_plane(job, blockIdx.x, local);
+    const int g = local * 128 + threadIdx.x;  // packed line group
+    const int n = HORIZ ? pj.w : pj.h, nlines = HORIZ ? pj.h : pj.w;
+    if (g * NL >= nlines) return;
+    const char* src = job.src + (size_t)blockIdx.y * job.src_fs + pj.src_off;
+    char* dst = job.dst + (size_t)blockIdx.y * job.dst_fs + pj.dst_off;
+    auto load = [&](int pos) -> uint32_t {
+        if constexpr (!HORIZ) return *reinterpret_cast<const uint32_t*>(src + (size_t)pos * pj.src_pitch + (size_t)g * 4);
+        T e[NL];
+#pragma unroll
+        for (int l = 0; l < NL; ++l) e[l] = reinterpret_cast<const T*>(src + (size_t)min(g * NL + l, nlines - 1) * pj.src_pitch)[pos];
+        uint32_t w; memcpy(&w, e, 4); return w;
+    };
+    auto store = [&](int pos, uint32_t w) {
+        if constexpr (!HORIZ) { *reinterpret_cast<uint32_t*>(dst + (size_t)pos * pj.dst_pitch + (size_t)g * 4) = w; return; }
+        T e[NL]; memcpy(e, &w, 4);
+#pragma unroll
+        for (int l = 0; l < NL; ++l) if (g * NL + l < nlines) reinterpret_cast<T*>(dst + (size_t)(g * NL + l) * pj.dst_pitch)[pos] = e[l];
+    };
+    Acc S[NL];
+    const int r = ap.r;
+    Ops::init(S, ap, load);
+    for (int x = 0; x < n; ++x) {
+        int ia, ib;
+        if (x <= r) { ia = r + x; ib = r - x; }
+        else if (x < n - r) { ia = r + x; ib = x - r - 1; }
+        else { ia = 2 * n - r - x - 1; ib = x - r - 1; }
+        store(x, Ops::update(S, load(ia), load(ib), ap));
+    }
+}
+
+template <typename T, bool H>
+static int launch_global(const FrameLayout& l, const bool mask[3], const char* src, size_t sfs, char* dst, size_t dfs, int count, int r, cudaStream_t st) {
+    constexpr int NL = Px<T>::NL;
+    BatchJob job = make_batch(l, mask, src, sfs, nullptr, 0, dst, dfs,
+                              [](int w, int h) { return (((H ? h : w) + NL - 1) / NL + 127) / 128; });
+    if (job.ctas_per_frame == 0) return 0;
+    const AxisParams ap = axis_params(r);
+    for (int f0 = 0; f0 < count; f0 += 65535) {
+        const int nf = std::min(65535, count - f0);
+        BatchJob j = job;
+        j.src += (size_t)f0 * sfs; j.dst += (size_t)f0 * dfs;
+        blur_global_kernel<T, H><<<dim3(job.ctas_per_frame, nf), 128, 0, st>>>(j, ap);
+        count_launch();
+    }
+    VSZ_CUDA(cudaGetLastError());
+    return 0;
+}
+
 // `passes` runtime-path passes along one axis.  The first launch reads src, later ones run in place on
 // dst (a line is owned by one thread and outputs trail inputs, so in-place is race-free).
 template <typename T, bool H>
@@ -870,9 +930,28 @@ static int run_axis(const FrameLayout& l, const bool mask[3], const char* src, s
                     int r, int passes, cudaStream_t st) {
     const int cap = max_fused(r, H);
     if (cap < 1) {
-        set_error("BoxBlur: %s %d is too large for the shared-memory delay ring (limit %d)", H ? "hradius" : "vradius", r,
-                  (int)((kMaxSmem / ((H ? NT_H : NT_V) * 4) - 1) / 2) - (H ? 100 : 0));
-        return -2;
+        // out-of-place passes from global memory, ping-ponging two scratch clips so the last pass lands in dst
+        char* t1 = nullptr;
+        const size_t bytes = l.frame_stride * (size_t)count, tfs = l.frame_stride;
+        VSZ_CUDA(cudaMallocAsync((void**)&t1, 2 * bytes, st));
+        char* t2 = t1 + bytes;
+        const char* cur = src;
+        size_t cur_fs = sfs;
+        int rc = 0;
+        for (int p = 1; p <= passes && !rc; ++p) {
+            char* out = (p == passes && cur != dst) ? dst : ((p & 1) ? t1 : t2);
+            const size_t ofs = (out == dst) ? dfs : tfs;
+            rc = launch_global<T, H>(l, mask, cur, cur_fs, out, ofs, count, r, st);
+            cur = out; cur_fs = ofs;
+        }
+        if (!rc && cur != dst) {  // single pass whose input was dst itself: copy the result back plane by plane
+            for (int f = 0; f < count && !rc; ++f)
+                for (int pl = 0; pl < l.nplanes; ++pl)
+                    if (mask[pl] && cudaMemcpyAsync(dst + (size_t)f * dfs + l.pl[pl].offset, cur + (size_t)f * cur_fs + l.pl[pl].offset,
+                                                    (size_t)l.pl[pl].pitch * l.pl[pl].h, cudaMemcpyDeviceToDevice, st) != cudaSuccess) rc = -1;
+        }
+        VSZ_CUDA(cudaFreeAsync(t1, st));
+        return rc;
     }
     const char* cur = src;
     size_t cur_fs = sfs;
