@@ -170,36 +170,45 @@ __device__ __forceinline__ void static_for(F&& f) { static_for_impl(std::make_in
 //              n..n+r-1, read back from its own ring), so the a operands of x >= n-r are ordinary too.
 // Idle or drained stages just compute on don't-care values.  Ring layout: word ((slot*P + q)*NT + tid),
 // slot = t mod (2r+1) shared by all stages, so stage offsets are compile-time immediates.
-template <typename T, int P, int MODE, int NT>
+// W = 32-bit words per thread and ring cell (1 or 2): with W = 2 a thread owns twice as many lines, ring and
+// global accesses are 64-bit, and the per-step bookkeeping is amortised over twice the pixels.
+template <int W> struct alignas(4 * W) Vec { uint32_t v[W]; };
+
+template <typename T, int P, int MODE, int NT, int W = 1>
 struct LinePipe {
     using Ops = StageOps<T, MODE>;
     using Acc = typename Px<T>::Acc;
+    using V = Vec<W>;
     static constexpr int NL = Px<T>::NL;
-    static constexpr int SLOT_WORDS = P * NT;
+    static constexpr int SLOT_WORDS = P * NT * W;
 
-    Acc S[P][NL];
-    uint32_t va[P], vb[P];  // operands of stage q+1 for the next step
-    uint32_t pa[P], pb[P];  // ring words of slot(t) and slot(t+1), fetched two / one step(s) ahead of their exchange
-    uint32_t* ring;         // &ring_base[tid]
-    uint32_t* cur;          // ring + slot(t) * SLOT_WORDS
-    uint32_t* cur2;         // ring + slot(t+2) * SLOT_WORDS
-    int slot;               // t mod (2r+1)
-    int n, D;               // line length, stage delay r+1
+    Acc S[P][W][NL];
+    V va[P], vb[P];   // operands of stage q+1 for the next step
+    V pa[P], pb[P];   // ring cells of slot(t) and slot(t+1), fetched two / one step(s) ahead of their exchange
+    uint32_t* ring;   // &ring_base[tid * W]
+    uint32_t* cur;    // ring + slot(t) * SLOT_WORDS
+    uint32_t* cur2;   // ring + slot(t+2) * SLOT_WORDS
+    int slot;         // t mod (2r+1)
+    int n, D;         // line length, stage delay r+1
+    int ek = 0, ej = 0;  // phase counters of step_any
     AxisParams ap;
 
     __device__ __forceinline__ void start(uint32_t* ring_, int n_, const AxisParams& ap_) {
         ring = ring_; n = n_; ap = ap_; D = ap_.r + 1;
         slot = 0; cur = ring; cur2 = ring + 2 * SLOT_WORDS;  // ring >= 3 slots
 #pragma unroll
-        for (int q = 0; q < P; ++q) {
-            va[q] = vb[q] = pa[q] = pb[q] = 0u;
+        for (int q = 0; q < P; ++q)
 #pragma unroll
-            for (int l = 0; l < NL; ++l) S[q][l] = Acc(0);
-        }
+            for (int w = 0; w < W; ++w) {
+                va[q].v[w] = vb[q].v[w] = pa[q].v[w] = pb[q].v[w] = 0u;
+#pragma unroll
+                for (int l = 0; l < NL; ++l) S[q][w][l] = Acc(0);
+            }
     }
     __device__ __forceinline__ int lag() const { return P * D; }
     __device__ __forceinline__ int fast_begin() const { return P * D + 1; }  // first t with every stage at x >= 1
-    __device__ __forceinline__ uint32_t& cell(int s, int q) { return ring[(s * P + q) * NT]; }
+    __device__ __forceinline__ V& cell(int s, int q) { return *reinterpret_cast<V*>(ring + (s * P + q) * (NT * W)); }
+    static __device__ __forceinline__ V& at(uint32_t* base, int q) { return *reinterpret_cast<V*>(base + q * (NT * W)); }
     // slot k steps behind slot(t) (0 <= k <= ring)
     __device__ __forceinline__ int back(int k) const { const int s = slot - k; return s < 0 ? s + ap.ring : s; }
     __device__ __forceinline__ void advance() {
@@ -208,27 +217,33 @@ struct LinePipe {
         cur2 += SLOT_WORDS;
         if (cur2 == ring + ap.ring * SLOT_WORDS) cur2 = ring;
     }
+    __device__ __forceinline__ V update(int q, const V& a, const V& b) {
+        V o;
+#pragma unroll
+        for (int w = 0; w < W; ++w) o.v[w] = Ops::update(S[q][w], a.v[w], b.v[w], ap);
+        return o;
+    }
 
-    // publish v as stage q's value of this step: exchange with the ring word of slot(t) (already in pa[q],
+    // publish v as stage q's value of this step: exchange with the ring cell of slot(t) (already in pa[q],
     // loaded two steps ago so no shared-memory latency sits on the critical path) and keep the look-ahead going.
-    __device__ __forceinline__ void publish(int q, uint32_t v) {
+    __device__ __forceinline__ void publish(int q, const V& v) {
         vb[q] = pa[q];
         va[q] = v;
-        cur[q * NT] = v;
+        at(cur, q) = v;
     }
     __device__ __forceinline__ void rotate(int q) {
         pa[q] = pb[q];
-        pb[q] = cur2[q * NT];
+        pb[q] = at(cur2, q);
     }
 
     // steady state, t in [fast_begin, n).  Returns stage P's output for position t - P*D.
-    __device__ __forceinline__ uint32_t step_fast(uint32_t v_in) {
-        uint32_t nv[P];
+    __device__ __forceinline__ V step_fast(const V& v_in) {
+        V nv[P];
 #pragma unroll
-        for (int q = 0; q < P; ++q) nv[q] = Ops::update(S[q], va[q], vb[q], ap);
+        for (int q = 0; q < P; ++q) nv[q] = update(q, va[q], vb[q]);
 #pragma unroll
         for (int q = 0; q < P; ++q) {
-            publish(q, (q == 0) ? v_in : nv[q - 1]);
+            publish(q, (q == 0) ? v_in : nv[q > 0 ? q - 1 : 0]);
             rotate(q);
         }
         advance();
@@ -238,29 +253,37 @@ struct LinePipe {
     // ---- edge steps with a compile-time set of live stages (no per-stage branching) -------------------------
     // Start-up phase k (t in [kD, (k+1)D)): stages 1..k are live, stage k itself starts (x = 0) on the first
     // step of the phase; producers 0..k publish.  Requires n >= fast_begin().
-    template <int Q> __device__ __forceinline__ uint32_t seed_stage() {
+    __device__ __forceinline__ V seed(int Q) {
         const int r = ap.r;
-        // ring Q holds positions -r..r of stage Q; position p sits (r - p + 1) slots behind slot(t)
-        Ops::init(S[Q], ap, [&](int pos) { return cell(back(r - pos + 1), Q); });
+        V out;
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+            // ring Q holds positions -r..r of stage Q; position p sits (r - p + 1) slots behind slot(t)
+            Ops::init(S[Q][w], ap, [&](int pos) { return cell(back(r - pos + 1), Q).v[w]; });
+        }
         for (int k = 1; k <= r; ++k) {  // virtual position -k: SYM -> k-1, reflect-101 (comptime V) -> k
             const int from = (MODE == MODE_CTV) ? k : k - 1;
             cell(back(r + k + 1), Q) = cell(back(r - from + 1), Q);
         }
         pa[Q] = cell(slot, Q);  // the seeding rewrote slot(t) and slot(t+1) of ring Q
         pb[Q] = cell(slot + 1 == ap.ring ? 0 : slot + 1, Q);
-        if constexpr (MODE == MODE_CTV) return Ops::emit(S[Q], ap);
-        const uint32_t c = cell(back(1), Q);
-        return Ops::update(S[Q], c, c, ap);  // the reference's x = 0 step adds in[r] - in[r]
+        const V c = cell(back(1), Q);
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+            if constexpr (MODE == MODE_CTV) out.v[w] = Ops::emit(S[Q][w], ap);
+            else out.v[w] = Ops::update(S[Q][w], c.v[w], c.v[w], ap);  // the reference's x = 0 step adds in[r] - in[r]
+        }
+        return out;
     }
 
     template <int ACT, bool INIT>
-    __device__ __forceinline__ uint32_t step_start(uint32_t v_in) {
-        uint32_t nv[P];
+    __device__ __forceinline__ V step_start(const V& v_in) {
+        V nv[P];
         static_for<P>([&](auto qc) {
             constexpr int q = decltype(qc)::value;
-            if constexpr (INIT && q == ACT - 1) nv[q] = seed_stage<q>();
-            else if constexpr (q < ACT) nv[q] = Ops::update(S[q], va[q], vb[q], ap);
-            else nv[q] = 0u;
+            if constexpr (INIT && q == ACT - 1) nv[q] = seed(q);
+            else if constexpr (q < ACT) nv[q] = update(q, va[q], vb[q]);
+            else nv[q] = V{};
         });
         static_for<P>([&](auto qc) {
             constexpr int q = decltype(qc)::value;
@@ -274,12 +297,12 @@ struct LinePipe {
     // Drain phase K (t in [n + KD, n + (K+1)D)): producer K is in its mirrored tail (first r steps of the phase,
     // j = step index inside the phase), producers > K still publish real samples, consumers K+1..P are live.
     template <int K, bool MIRROR>
-    __device__ __forceinline__ uint32_t step_drain(int j) {
-        uint32_t nv[P];
+    __device__ __forceinline__ V step_drain(int j) {
+        V nv[P];
         static_for<P>([&](auto qc) {
             constexpr int q = decltype(qc)::value;
-            if constexpr (q >= K) nv[q] = Ops::update(S[q], va[q], vb[q], ap);
-            else nv[q] = 0u;
+            if constexpr (q >= K) nv[q] = update(q, va[q], vb[q]);
+            else nv[q] = V{};
         });
         static_for<P>([&](auto qc) {
             constexpr int q = decltype(qc)::value;
@@ -287,7 +310,7 @@ struct LinePipe {
                 if constexpr (MIRROR) publish(q, cell(back((MODE == MODE_CTV) ? 1 + ap.r : 1 + 2 * j), q));
                 rotate(q);
             } else if constexpr (q > K) {
-                publish(q, nv[q - 1]);
+                publish(q, nv[q > 0 ? q - 1 : 0]);
                 rotate(q);
             }
         });
@@ -297,10 +320,9 @@ struct LinePipe {
 
     // Dispatcher for callers that cannot structure their loops by phase (the tiled H kernel): phase counters
     // live in the pipe.  Requires n >= fast_begin().
-    int ek = 0, ej = 0;
-    __device__ __forceinline__ uint32_t step_any(int t, uint32_t v_in) {
+    __device__ __forceinline__ V step_any(int t, const V& v_in) {
         if (t >= fast_begin() && t < n) return step_fast(v_in);
-        uint32_t o = 0u;
+        V o{};
         if (t < n) {
             static_for<P + 1>([&](auto kc) {
                 constexpr int k = decltype(kc)::value;
@@ -320,41 +342,23 @@ struct LinePipe {
         return o;
     }
 
-    // any t: also seeds stages that start at this step and publishes mirrored tails.  v_in is the input
-    // sample for time t (ignored once t >= n).  The result is meaningful iff 0 <= t - P*D < n.
-    __device__ __forceinline__ uint32_t step_edge(int t, uint32_t v_in) {
-        uint32_t nv[P];
+    // any t, any n (tiny lines): also seeds stages that start at this step and publishes mirrored tails.  v_in is
+    // the input sample for time t (ignored once t >= n).  The result is meaningful iff 0 <= t - P*D < n.
+    __device__ __forceinline__ V step_edge(int t, const V& v_in) {
+        V nv[P];
         const int r = ap.r;
 #pragma unroll
         for (int q = 0; q < P; ++q) {
             const int x = t - (q + 1) * D;  // position of stage q+1
-            if (x == 0) {
-                // ring q holds positions -r..r of stage q; position p sits (r - p + 1) slots behind slot(t)
-                Ops::init(S[q], ap, [&](int pos) { return cell(back(r - pos + 1), q); });
-                for (int k = 1; k <= r; ++k) {  // virtual position -k: SYM -> k-1, reflect-101 (comptime V) -> k
-                    const int from = (MODE == MODE_CTV) ? k : k - 1;
-                    cell(back(r + k + 1), q) = cell(back(r - from + 1), q);
-                }
-                // the seeding rewrote slot(t) and slot(t+1) of ring q: refresh the look-ahead registers
-                pa[q] = cell(slot, q);
-                pb[q] = cell(slot + 1 == ap.ring ? 0 : slot + 1, q);
-                if constexpr (MODE == MODE_CTV) {
-                    nv[q] = Ops::emit(S[q], ap);
-                } else {
-                    const uint32_t c = cell(back(1), q);
-                    nv[q] = Ops::update(S[q], c, c, ap);  // the reference's x = 0 step adds in[r] - in[r]
-                }
-            } else if (x > 0 && x < n) {
-                nv[q] = Ops::update(S[q], va[q], vb[q], ap);
-            } else {
-                nv[q] = 0u;  // not started yet / already drained: nothing to compute
-            }
+            if (x == 0) nv[q] = seed(q);
+            else if (x > 0 && x < n) nv[q] = update(q, va[q], vb[q]);
+            else nv[q] = V{};  // not started yet / already drained: nothing to compute
         }
 #pragma unroll
         for (int q = 0; q < P; ++q) {
             const int y = t - q * D;  // position stage q publishes now
             if (y >= 0 && y < n + r) {
-                uint32_t v = (q == 0) ? v_in : nv[q - 1];
+                V v = (q == 0) ? v_in : nv[q > 0 ? q - 1 : 0];
                 if (y >= n) {
                     // mirrored tail, re-read from the stage's own ring (never from global memory: the kernels
                     // run in place).  SYM: position 2n-1-y; comptime V (R101q): position y-r-1.
@@ -376,43 +380,46 @@ __device__ __forceinline__ const PlaneJob& find_plane(const BatchJob& b, int cta
     return b.pl[k];
 }
 
-// 4-byte asynchronous global->shared copies (LDGSTS): their completion is tracked by commit groups, not
+// 4/8-byte asynchronous global->shared copies (LDGSTS): their completion is tracked by commit groups, not
 // by the register scoreboards the ring traffic uses, so deep input prefetch never stalls the math.
-__device__ __forceinline__ void cp_async4(uint32_t* smem_dst, const void* gsrc) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+template <int BYTES>
+__device__ __forceinline__ void cp_async(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;\n" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc), "n"(BYTES) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
 // --------------------------------------------------------------------------- V: lines are columns
-template <int NT> struct VStage { static constexpr int AHEAD = 8, SLOTS = 16, WORDS = SLOTS * NT; };
+template <int NT, int W> struct VStage { static constexpr int AHEAD = 8, SLOTS = 16, WORDS = SLOTS * NT * W; };
 
-template <typename T, int P, int MODE, int NT>
+template <typename T, int P, int MODE, int NT, int W>
 __global__ void __launch_bounds__(NT) blur_v_kernel(const BatchJob job, const AxisParams ap) {
     extern __shared__ uint32_t smem[];
     constexpr int NL = Px<T>::NL;
-    using Pipe = LinePipe<T, P, MODE, NT>;
-    using ST = VStage<NT>;
+    using Pipe = LinePipe<T, P, MODE, NT, W>;
+    using V = Vec<W>;
+    using ST = VStage<NT, W>;
     int local;
     const PlaneJob& pj = find_plane(job, blockIdx.x, local);
-    const int g = local * NT + threadIdx.x;  // 32-bit column group
-    if (g * NL >= pj.w) return;               // no block-level sync in this kernel
-    const char* src = job.src + (size_t)blockIdx.y * job.src_fs + pj.src_off + (size_t)g * 4;
-    char* dst = job.dst + (size_t)blockIdx.y * job.dst_fs + pj.dst_off + (size_t)g * 4;
+    const int g = local * NT + threadIdx.x;  // (32*W)-bit column group
+    if (g * NL * W >= pj.w) return;           // no block-level sync in this kernel
+    const char* src = job.src + (size_t)blockIdx.y * job.src_fs + pj.src_off + (size_t)g * 4 * W;
+    char* dst = job.dst + (size_t)blockIdx.y * job.dst_fs + pj.dst_off + (size_t)g * 4 * W;
     const int sp = pj.src_pitch, dp = pj.dst_pitch;
 
-    uint32_t* stage = smem + threadIdx.x;                 // [SLOTS][NT] input rows in flight
+    uint32_t* stage = smem + threadIdx.x * W;               // [SLOTS][NT] input rows in flight
     Pipe pipe;
-    pipe.start(smem + ST::WORDS + threadIdx.x, pj.h, ap);
+    pipe.start(smem + ST::WORDS + threadIdx.x * W, pj.h, ap);
     const int n = pj.h, lag = pipe.lag(), total = n + lag;
     const int t_fast = min(pipe.fast_begin(), n);
 
     // one commit group per input row, AHEAD rows in flight
+    auto staged = [&](int row) -> V& { return *reinterpret_cast<V*>(stage + (row & (ST::SLOTS - 1)) * (NT * W)); };
     auto fetch = [&](int row) {
-        cp_async4(stage + (row & (ST::SLOTS - 1)) * NT, src + (size_t)min(row, n - 1) * sp);
+        cp_async<4 * W>(&staged(row), src + (size_t)min(row, n - 1) * sp);
         cp_async_commit();
     };
-    auto store = [&](int x, uint32_t v) { *reinterpret_cast<uint32_t*>(dst + (size_t)x * dp) = v; };
+    auto store = [&](int x, const V& v) { *reinterpret_cast<V*>(dst + (size_t)x * dp) = v; };
 #pragma unroll
     for (int i = 0; i < ST::AHEAD; ++i) fetch(i);
 
@@ -426,8 +433,8 @@ __global__ void __launch_bounds__(NT) blur_v_kernel(const BatchJob job, const Ax
             for (int j = 0; j < steps; ++j, ++t) {
                 fetch(t + ST::AHEAD);
                 cp_async_wait<ST::AHEAD>();
-                const uint32_t v = stage[(t & (ST::SLOTS - 1)) * NT];
-                uint32_t o;
+                const V v = staged(t);
+                V o;
                 if (j == 0 && k >= 1) o = pipe.template step_start<k, (k >= 1)>(v);
                 else o = pipe.template step_start<k, false>(v);
                 if (k == P) store(0, o);
@@ -437,7 +444,7 @@ __global__ void __launch_bounds__(NT) blur_v_kernel(const BatchJob job, const Ax
         for (; t < t_fast; ++t) {  // tiny lines: generic edge step
             fetch(t + ST::AHEAD);
             cp_async_wait<ST::AHEAD>();
-            const uint32_t o = pipe.step_edge(t, stage[(t & (ST::SLOTS - 1)) * NT]);
+            const V o = pipe.step_edge(t, staged(t));
             const int x = t - lag;
             if (x >= 0 && x < n) store(x, o);
         }
@@ -451,14 +458,14 @@ __global__ void __launch_bounds__(NT) blur_v_kernel(const BatchJob job, const Ax
         for (; t + ST::AHEAD + U <= n; t += U) {
 #pragma unroll
             for (int i = 0; i < U; ++i) {
-                cp_async4(stage + ((t + ST::AHEAD + i) & (ST::SLOTS - 1)) * NT, fsrc);
+                cp_async<4 * W>(&staged(t + ST::AHEAD + i), fsrc);
                 cp_async_commit();
                 fsrc += sp;
             }
             cp_async_wait<ST::AHEAD>();
 #pragma unroll
             for (int i = 0; i < U; ++i) {
-                *reinterpret_cast<uint32_t*>(fdst) = pipe.step_fast(stage[((t + i) & (ST::SLOTS - 1)) * NT]);
+                *reinterpret_cast<V*>(fdst) = pipe.step_fast(staged(t + i));
                 fdst += dp;
             }
         }
@@ -466,7 +473,7 @@ __global__ void __launch_bounds__(NT) blur_v_kernel(const BatchJob job, const Ax
     for (; t < n; ++t) {
         fetch(t + ST::AHEAD);
         cp_async_wait<ST::AHEAD>();
-        store(t - lag, pipe.step_fast(stage[(t & (ST::SLOTS - 1)) * NT]));
+        store(t - lag, pipe.step_fast(staged(t)));
     }
     cp_async_wait<0>();
     if (phased) {
@@ -474,13 +481,13 @@ __global__ void __launch_bounds__(NT) blur_v_kernel(const BatchJob job, const Ax
         static_for<P>([&](auto kc) {
             constexpr int k = decltype(kc)::value;
             for (int j = 0; j < pipe.D; ++j, ++t) {
-                const uint32_t o = (j < ap.r) ? pipe.template step_drain<k, true>(j) : pipe.template step_drain<k, false>(0);
+                const V o = (j < ap.r) ? pipe.template step_drain<k, true>(j) : pipe.template step_drain<k, false>(0);
                 store(t - lag, o);
             }
         });
     } else {
         for (; t < total; ++t) {
-            const uint32_t o = pipe.step_edge(t, 0u);
+            const V o = pipe.step_edge(t, V{});
             const int x = t - lag;
             if (x >= 0 && x < n) store(x, o);
         }
@@ -583,14 +590,14 @@ __global__ void __launch_bounds__(NT) blur_h_kernel(const BatchJob job, const Ax
             const int x0 = t0 - lag;  // >= 1
 #pragma unroll 4
             for (int i = 0; i < TL::CH; ++i)
-                out_tile[((x0 + i) & (TL::OUT - 1)) * TL::PITCH_W + threadIdx.x] = pipe.step_fast(in_tile[i * TL::PITCH_W + threadIdx.x]);
+                out_tile[((x0 + i) & (TL::OUT - 1)) * TL::PITCH_W + threadIdx.x] = pipe.step_fast(Vec<1>{{in_tile[i * TL::PITCH_W + threadIdx.x]}}).v[0];
         } else {
             for (int t = t0; t < t1; ++t) {
-                const uint32_t v = in_tile[(t - t0) * TL::PITCH_W + threadIdx.x];
+                const Vec<1> v{{in_tile[(t - t0) * TL::PITCH_W + threadIdx.x]}};
                 uint32_t o;
-                if (phased) o = pipe.step_any(t, v);
-                else if (t >= t_fast && t < n) o = pipe.step_fast(v);
-                else o = pipe.step_edge(t, v);
+                if (phased) o = pipe.step_any(t, v).v[0];
+                else if (t >= t_fast && t < n) o = pipe.step_fast(v).v[0];
+                else o = pipe.step_edge(t, v).v[0];
                 const int x = t - lag;
                 if (x >= 0 && x < n) out_tile[(x & (TL::OUT - 1)) * TL::PITCH_W + threadIdx.x] = o;
             }
@@ -794,23 +801,27 @@ static constexpr int kMaxSmem = 227 * 1024;
 static constexpr int NT_V = VSZ_NT_V;
 static constexpr int NT_H = VSZ_NT_H;
 
+#ifndef VSZ_V_WORDS
+#define VSZ_V_WORDS 2
+#endif
 template <typename T, int P, int MODE>
 static int launch_v(const FrameLayout& l, const bool mask[3], const char* src, size_t src_fs, char* dst, size_t dst_fs,
                     int count, int r, cudaStream_t st) {
     constexpr int NL = Px<T>::NL;
+    constexpr int W = VSZ_V_WORDS, NT = NT_V / W;  // same shared memory per CTA for W = 1 and W = 2
     const AxisParams ap = axis_params(r);
-    const size_t smem = ((size_t)ap.ring * P * NT_V + VStage<NT_V>::WORDS) * 4;
+    const size_t smem = ((size_t)ap.ring * P * NT * W + VStage<NT, W>::WORDS) * 4;
     if (smem > (size_t)kMaxSmem) { set_error("BoxBlur: vradius %d with %d fused passes exceeds the shared-memory delay ring", r, P); return -2; }
-    auto kern = blur_v_kernel<T, P, MODE, NT_V>;
+    auto kern = blur_v_kernel<T, P, MODE, NT, W>;
     VSZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     BatchJob job = make_batch(l, mask, src, src_fs, nullptr, 0, dst, dst_fs,
-                              [](int w, int) { return ((w + NL - 1) / NL + NT_V - 1) / NT_V; });
+                              [](int w, int) { return ((w + NL * W - 1) / (NL * W) + NT - 1) / NT; });
     if (job.ctas_per_frame == 0) return 0;
     for (int f0 = 0; f0 < count; f0 += 65535) {
         const int nf = std::min(65535, count - f0);
         BatchJob j = job;
         j.src += (size_t)f0 * src_fs; j.dst += (size_t)f0 * dst_fs;
-        kern<<<dim3(job.ctas_per_frame, nf), NT_V, smem, st>>>(j, ap);
+        kern<<<dim3(job.ctas_per_frame, nf), NT, smem, st>>>(j, ap);
         count_launch();
     }
     VSZ_CUDA(cudaGetLastError());
@@ -844,7 +855,7 @@ static int launch_h(const FrameLayout& l, const bool mask[3], const char* src, s
 // largest number of passes one launch can fuse for this radius (shared-memory bound), at most 5
 static int max_fused(int r, bool horizontal) {
     const size_t per_pass = (size_t)(2 * r + 1) * (horizontal ? NT_H : NT_V) * 4;
-    const size_t fixed = horizontal ? (size_t)(HTile<uint16_t, NT_H>::IN_WORDS + HTile<uint16_t, NT_H>::OUT_WORDS) * 4 : (size_t)VStage<NT_V>::WORDS * 4;
+    const size_t fixed = horizontal ? (size_t)(HTile<uint16_t, NT_H>::IN_WORDS + HTile<uint16_t, NT_H>::OUT_WORDS) * 4 : (size_t)VStage<NT_V, 1>::WORDS * 4;
     int p = (int)((kMaxSmem - fixed) / per_pass);
     return p > 5 ? 5 : p;
 }
