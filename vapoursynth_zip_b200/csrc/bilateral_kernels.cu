@@ -86,7 +86,9 @@ __device__ __forceinline__ float range_weight(float fi, float top, const Bilater
 // One CTA (32x8 threads) walks a horizontal strip of `prm.strip` 32x32-pixel tiles; every thread produces
 // 4 pixels per tile (rows ty, ty+8, ty+16, ty+24).  The spatial table and - in W_SMEM mode - the range
 // LUT are loaded once per CTA and reused by every tile of the strip.
-template <typename T, bool JOINT, int WM>
+// SAMPLES/STEP > 0: the tap pattern (radius = 1 + (SAMPLES-1)*STEP) is a compile-time constant, so the tile pitch
+// and every tap offset become immediates and the tap loops unroll; SAMPLES == 0: any radius/step at run time.
+template <typename T, bool JOINT, int WM, int SAMPLES, int STEP>
 __global__ void __launch_bounds__(TW * TH) bilateral_kernel(const BatchJob job, const BilateralParams prm) {
     extern __shared__ float smem_f[];
     int k = job.nplanes - 1;
@@ -97,7 +99,8 @@ __global__ void __launch_bounds__(TW * TH) bilateral_kernel(const BatchJob job, 
     const int strips_x = prm.strips_x[k];
     const int sx = local % strips_x, ty0 = local / strips_x;
     const int y0 = ty0 * TILE;
-    const int r = pp.radius, step = pp.step, r2 = r + 1;
+    constexpr bool FIXED = SAMPLES > 0;
+    const int r = FIXED ? 1 + (SAMPLES - 1) * STEP : pp.radius, step = FIXED ? STEP : pp.step, r2 = r + 1;
     const int tw = TILE + 2 * r, th = TILE + 2 * r, tsize = tw * th;
     const uint32_t inv_tw = ((1u << 20) + (uint32_t)tw - 1u) / (uint32_t)tw;  // exact e / tw for e < 2^12
 
@@ -136,23 +139,30 @@ __global__ void __launch_bounds__(TW * TH) bilateral_kernel(const BatchJob job, 
             const float cref = s_ref[cxy];
             float wsum = __fmul_rn(s_gs[0], range_weight<WM>(0.0f, top, pp, s_lut));
             float sum = __fmul_rn(s_src[cxy], wsum);
-            for (int yy = 1; yy < r2; yy += step) {
+            auto taps = [&](int yy, int xx) {
                 const int up = cxy - yy * tw, dn = cxy + yy * tw;
-                for (int xx = 1; xx < r2; xx += step) {
-                    const float sw = s_gs[yy * r2 + xx];
-                    const float r1 = s_ref[up + xx], r2v = s_ref[dn + xx], r3 = s_ref[up - xx], r4 = s_ref[dn - xx];
-                    const float v1 = JOINT ? s_src[up + xx] : r1, v2 = JOINT ? s_src[dn + xx] : r2v;
-                    const float v3 = JOINT ? s_src[up - xx] : r3, v4 = JOINT ? s_src[dn - xx] : r4;
-                    const float g1 = range_weight<WM>(range_index_f<T>(cref, r1), top, pp, s_lut);
-                    const float g2 = range_weight<WM>(range_index_f<T>(cref, r2v), top, pp, s_lut);
-                    const float g3 = range_weight<WM>(range_index_f<T>(cref, r3), top, pp, s_lut);
-                    const float g4 = range_weight<WM>(range_index_f<T>(cref, r4), top, pp, s_lut);
-                    const float gsum = __fadd_rn(__fadd_rn(__fadd_rn(g1, g2), g3), g4);
-                    wsum = __fadd_rn(wsum, __fmul_rn(sw, gsum));
-                    const float p1 = __fmul_rn(v1, g1), p2 = __fmul_rn(v2, g2), p3 = __fmul_rn(v3, g3), p4 = __fmul_rn(v4, g4);
-                    const float psum = __fadd_rn(__fadd_rn(__fadd_rn(p1, p2), p3), p4);
-                    sum = __fadd_rn(sum, __fmul_rn(sw, psum));
-                }
+                const float sw = s_gs[yy * r2 + xx];
+                const float r1 = s_ref[up + xx], r2v = s_ref[dn + xx], r3 = s_ref[up - xx], r4 = s_ref[dn - xx];
+                const float v1 = JOINT ? s_src[up + xx] : r1, v2 = JOINT ? s_src[dn + xx] : r2v;
+                const float v3 = JOINT ? s_src[up - xx] : r3, v4 = JOINT ? s_src[dn - xx] : r4;
+                const float g1 = range_weight<WM>(range_index_f<T>(cref, r1), top, pp, s_lut);
+                const float g2 = range_weight<WM>(range_index_f<T>(cref, r2v), top, pp, s_lut);
+                const float g3 = range_weight<WM>(range_index_f<T>(cref, r3), top, pp, s_lut);
+                const float g4 = range_weight<WM>(range_index_f<T>(cref, r4), top, pp, s_lut);
+                const float gsum = __fadd_rn(__fadd_rn(__fadd_rn(g1, g2), g3), g4);
+                wsum = __fadd_rn(wsum, __fmul_rn(sw, gsum));
+                const float p1 = __fmul_rn(v1, g1), p2 = __fmul_rn(v2, g2), p3 = __fmul_rn(v3, g3), p4 = __fmul_rn(v4, g4);
+                const float psum = __fadd_rn(__fadd_rn(__fadd_rn(p1, p2), p3), p4);
+                sum = __fadd_rn(sum, __fmul_rn(sw, psum));
+            };
+            if constexpr (FIXED) {
+#pragma unroll
+                for (int a = 0; a < SAMPLES; ++a)
+#pragma unroll
+                    for (int b = 0; b < SAMPLES; ++b) taps(1 + a * STEP, 1 + b * STEP);
+            } else {
+                for (int yy = 1; yy < r2; yy += step)
+                    for (int xx = 1; xx < r2; xx += step) taps(yy, xx);
             }
             const float q = __fdiv_rn(sum, wsum);
             T* out = reinterpret_cast<T*>(dst + (size_t)y * pj.dst_pitch) + x;
@@ -174,21 +184,30 @@ static int weight_mode_for(int lut_len) {
 
 int bilateral_weights_exact(int lut_len) { return weight_mode_for(lut_len) != W_COMPUTE; }
 
-template <typename T, bool JOINT>
-static int launch_mode(int wm, const BatchJob& j, const BilateralParams& prm, int nf, size_t smem, cudaStream_t st) {
-    const dim3 grid(j.ctas_per_frame, nf), block(TW, TH);
-#define VSZ_BL(WMV)                                                                                       \
-    {                                                                                                     \
-        auto kern = bilateral_kernel<T, JOINT, WMV>;                                                      \
-        VSZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
-        kern<<<grid, block, smem, st>>>(j, prm);                                                          \
-    }
-    if (wm == W_SMEM) VSZ_BL(W_SMEM)
-    else if (wm == W_COMPUTE) VSZ_BL(W_COMPUTE)
-    else VSZ_BL(W_GLOBAL)
-#undef VSZ_BL
+template <typename T, bool JOINT, int WM, int SAMPLES, int STEP>
+static int launch_one(const BatchJob& j, const BilateralParams& prm, int nf, size_t smem, cudaStream_t st) {
+    auto kern = bilateral_kernel<T, JOINT, WM, SAMPLES, STEP>;
+    VSZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<dim3(j.ctas_per_frame, nf), dim3(TW, TH), smem, st>>>(j, prm);
     count_launch();
     return 0;
+}
+
+template <typename T, bool JOINT>
+static int launch_mode(int wm, int samples, int step, const BatchJob& j, const BilateralParams& prm, int nf, size_t smem, cudaStream_t st) {
+    if constexpr (!JOINT) {
+        // specialised tap patterns: sigmaS up to 7.5 (bilateral.zig:164-190 yields exactly these (samples, step) pairs)
+#define VSZ_BL(SA, SE)                                                                                           \
+        if (samples == SA && step == SE) {                                                                          \
+            if (wm == W_SMEM) return launch_one<T, false, W_SMEM, SA, SE>(j, prm, nf, smem, st);                     \
+            if (wm == W_COMPUTE) return launch_one<T, false, W_COMPUTE, SA, SE>(j, prm, nf, smem, st);               \
+        }
+        VSZ_BL(1, 1) VSZ_BL(2, 1) VSZ_BL(2, 2) VSZ_BL(3, 2) VSZ_BL(3, 3) VSZ_BL(4, 3)
+#undef VSZ_BL
+    }
+    if (wm == W_SMEM) return launch_one<T, JOINT, W_SMEM, 0, 0>(j, prm, nf, smem, st);
+    if (wm == W_COMPUTE) return launch_one<T, JOINT, W_COMPUTE, 0, 0>(j, prm, nf, smem, st);
+    return launch_one<T, JOINT, W_GLOBAL, 0, 0>(j, prm, nf, smem, st);
 }
 
 template <typename T>
@@ -226,7 +245,8 @@ static int run_bilateral_t(const FrameLayout& l, const bool mask[3], const char*
             BatchJob jj = j;
             jj.src += (size_t)f0 * sfs; jj.dst += (size_t)f0 * dfs;
             if (ref) jj.ref += (size_t)f0 * rfs;
-            const int rc = ref ? launch_mode<T, true>(wm, jj, prm, nf, smem, st) : launch_mode<T, false>(wm, jj, prm, nf, smem, st);
+            const int samples = pp.step > 0 ? (pp.radius - 1) / pp.step + 1 : 0;
+            const int rc = ref ? launch_mode<T, true>(wm, samples, pp.step, jj, prm, nf, smem, st) : launch_mode<T, false>(wm, samples, pp.step, jj, prm, nf, smem, st);
             if (rc) return rc;
         }
     }
