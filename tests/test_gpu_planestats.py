@@ -65,8 +65,11 @@ def test_planeaverage_golden(key):
     props_close({prop + "Avg": got[prop + "Avg"]}, {prop + "Avg": GOLD_AV[key]["avg"]}, rel=1e-9)
 
 
+@pytest.mark.parametrize("exact", ["0", "1"])
 @pytest.mark.parametrize("fmt", ["GRAY8", "GRAY10", "GRAY16", "GRAYH", "GRAYS", "YUV420P16", "RGBS"])
-def test_noise_planeminmax(fmt):
+def test_noise_planeminmax(fmt, exact, monkeypatch):
+    # exact=1 forces the two-pass radix select; 0 lets the sampled single-read path resolve what it can
+    monkeypatch.setenv("VSZIP_MINMAX_EXACT", exact)
     base = "GRAY16" if fmt == "GRAY10" else fmt
     clip = noise_clip(base, 517, 243, seed=9)
     if fmt == "GRAY10":
@@ -132,6 +135,42 @@ def test_exclude_exact():
     assert src.vszip.PlaneAverage(exclude=[1000, 3000]).get_frame(0).props["psmAvg"] == 0.0
     twof = np.vstack([np.full((32, 64), 3.0, np.float32), np.full((32, 64), 1.0, np.float32)])
     assert vz.core.clip_from_frames("GRAYS", [[twof]]).vszip.PlaneAverage(exclude=[3]).get_frame(0).props["psmAvg"] == 1.0
+
+
+def _structured(kind, w, h, rng):
+    y, x = np.mgrid[0:h, 0:w]
+    if kind == "gradient":
+        return ((x * 65535) // (w - 1)).astype(np.uint16)
+    if kind == "dark_noise":      # fade-to-black: everything within a few codes of 4096
+        return (4096 + rng.integers(-2, 3, (h, w))).astype(np.uint16)
+    if kind == "letterbox":       # flat bars hold the min rank, picture holds the max rank
+        img = rng.integers(8000, 60000, (h, w)).astype(np.uint16)
+        img[: h // 6] = 4096
+        img[-(h // 6):] = 4096
+        return img
+    if kind == "sparse":          # 8-bit content shifted to 16 bits: only every 256th code is used
+        return (rng.integers(0, 256, (h, w)) << 8).astype(np.uint16)
+    if kind == "rows":            # the row sample misrepresents the plane: rare rows carry the extremes
+        img = np.full((h, w), 30000, np.uint16)
+        img[1::16] = rng.integers(0, 65536, (len(range(1, h, 16)), w)).astype(np.uint16)
+        return img
+    if kind == "ten_bit_invalid":  # GRAY10 with samples above the peak (skipped by the reference)
+        img = rng.integers(0, 1024, (h, w)).astype(np.uint16)
+        img[::7, ::5] = 40000
+        return img
+    raise KeyError(kind)
+
+
+@pytest.mark.parametrize("kind", ["gradient", "dark_noise", "letterbox", "sparse", "rows", "ten_bit_invalid"])
+def test_structured_planeminmax(kind):
+    """Content on which the sampled brackets are wide, degenerate or wrong: results must stay exact."""
+    rng = np.random.default_rng(77)
+    fmt = "GRAY10" if kind == "ten_bit_invalid" else "GRAY16"
+    for (w, h) in ((640, 480), (1283, 721)):
+        clip = {"format": fmt, "planes": [_structured(kind, w, h, rng)]}
+        for thr in ((0.1, 0.1), (0.02, 0.4), (0.3, 0.0), (0.0005, 0.0005)):
+            args = dict(minthr=thr[0], maxthr=thr[1])
+            props_close(mm(clip, **args), oa.planeminmax(clip, **args))
 
 
 @pytest.mark.parametrize("fmt", ["GRAY16", "GRAYS"])

@@ -16,6 +16,7 @@
 #include <cuda_fp16.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "filter.h"
 
@@ -32,11 +33,19 @@ struct Partial {
     unsigned int pad;
 };
 
+// Coarse-bin brackets guessed from a row sample (threshold fast path) and the "already resolved" flag.
+struct Bracket { unsigned int l_min, u_min, l_max, u_max; unsigned int done; unsigned int pad[3]; };  // [l, u) in bins
+static constexpr int SBINS = 4096;   // bins of the sample histogram
+static constexpr int FINE_W = 768;   // widest bracket the single-read kernel can histogram
+
 struct StatsPlane {
     size_t a_off, b_off;
     int a_pitch, b_pitch;
     int w, h;
     int cta_begin, nctas;
+    int s_cta_begin, s_nctas;  // CTAs of the sampling kernel
+    int b_cta_begin, b_nctas;  // CTAs of the single-read bracket kernel
+    int s_step, s_lpr;         // it reads every s_step-th 128-byte line; s_lpr lines per row
     unsigned int tmin, tmax;  // trunc(total * thr)
 };
 
@@ -52,6 +61,12 @@ struct StatsJob {
     unsigned int* counters2;  // [frame][plane] completed-CTA counters of pass 2
     unsigned int* coarse;     // [frame][plane][256]
     unsigned int* fine;       // [frame][plane][2][256]
+    unsigned int* counters3;  // [frame][plane] completed-CTA counters of the sampling kernel
+    unsigned int* ssample;    // [frame][plane][SBINS] histogram of the line sample
+    unsigned int* bfine;      // [frame][plane][2][FINE_W] exact histograms of the two brackets
+    struct Bracket* brackets; // [frame][plane]
+    int sample_ctas_per_frame, bracket_ctas_per_frame;
+    int sshift;               // sample bin = bin >> sshift
     StatsRaw* out;            // [frame][plane]
     // parameters
     int nex;
@@ -292,6 +307,7 @@ __global__ void __launch_bounds__(NT) stats_kernel(const StatsJob j) {
 // warp-private 256-bin histograms in shared memory; a warp whose 32 lanes all hit the same bin
 // (flat areas, blank clips) issues one atomic of 32 instead of 32 serialised ones.
 __device__ __forceinline__ void hist_add(unsigned int* h, unsigned int key, bool valid) {
+    // (MATCH.ANY would aggregate arbitrary groups but was measured 3x slower than this on B200)
     const unsigned int active = __ballot_sync(0xffffffffu, valid);
     if (active == 0u) return;
     const int leader = __ffs(active) - 1;
@@ -305,11 +321,11 @@ __device__ __forceinline__ void hist_add(unsigned int* h, unsigned int key, bool
 }
 
 template <typename T, bool HAS_B>
-__global__ void __launch_bounds__(NT) hist_coarse_kernel(const StatsJob j) {
+__device__ __forceinline__ void hist_coarse_body(const StatsJob& j, const int frame) {
     __shared__ unsigned int s_hist[NT / 32][256];
     int k, local;
     const StatsPlane& p = find_plane(j, blockIdx.x, k, local);
-    const int frame = blockIdx.y;
+    if (j.brackets[(size_t)frame * j.nplanes + k].done) return;  // resolved by the sampled fast path
     const char* a = j.a + (size_t)frame * j.a_fs + p.a_off;
     const char* b = HAS_B ? j.b + (size_t)frame * j.b_fs + p.b_off : nullptr;
     int y0, y1;
@@ -390,14 +406,14 @@ __device__ int scan_rank(const unsigned int* h, int n, unsigned int base, unsign
 
 // --------------------------------------------------------------------------- threshold path, pass 2
 template <typename T>
-__global__ void __launch_bounds__(NT) hist_fine_kernel(const StatsJob j) {
+__device__ __forceinline__ void hist_fine_body(const StatsJob& j, const int frame) {
     __shared__ unsigned int s_fine[2][256];
     __shared__ int s_bmin, s_bmax;
     __shared__ unsigned int s_cmin, s_cmax;
     __shared__ bool s_last;
     int k, local;
     const StatsPlane& p = find_plane(j, blockIdx.x, k, local);
-    const int frame = blockIdx.y;
+    if (j.brackets[(size_t)frame * j.nplanes + k].done) return;  // resolved by the sampled fast path
     const char* a = j.a + (size_t)frame * j.a_fs + p.a_off;
     const unsigned int* coarse = j.coarse + ((size_t)frame * j.nplanes + k) * 256;
     const int shift = j.shift;
@@ -459,20 +475,409 @@ __global__ void __launch_bounds__(NT) hist_fine_kernel(const StatsJob j) {
     r.bin_min = lo; r.bin_max = hi;
 }
 
+// The exact kernels walk the frames of a batch with a grid-stride loop: when the fast path below is on they are
+// only a fallback, so the launcher gives them a few frame rows instead of one CTA per (chunk, frame) that would
+// exit at once.
+template <typename T, bool HAS_B>
+__global__ void __launch_bounds__(NT) hist_coarse_kernel(const StatsJob j, const int nframes) {
+    for (int frame = blockIdx.y; frame < nframes; frame += gridDim.y) {
+        hist_coarse_body<T, HAS_B>(j, frame);
+        __syncthreads();
+    }
+}
+template <typename T>
+__global__ void __launch_bounds__(NT) hist_fine_kernel(const StatsJob j, const int nframes) {
+    for (int frame = blockIdx.y; frame < nframes; frame += gridDim.y) {
+        hist_fine_body<T>(j, frame);
+        __syncthreads();
+    }
+}
+
+// --------------------------------------------------------------------------- threshold path, sampled fast path
+// The exact two-pass select above costs two full reads and one shared-memory atomic per sample.  The fast path
+// brackets, from a 1/16 sample of the plane's 128-byte lines (4096-bin histogram), the bin range that must hold each
+// requested rank and then makes ONE full pass that (a) counts exactly how many samples lie below / above the
+// brackets with packed 16-bit min/max arithmetic (no atomics, content independent) and (b) builds exact histograms
+// of the (few) samples inside the brackets.  If the true rank lies inside its bracket - which the exact counts
+// prove or disprove - the bin is resolved exactly; otherwise the plane is left to the exact two-pass kernels,
+// which return immediately when `done`.
+template <typename T>
+__global__ void __launch_bounds__(NT) hist_sample_kernel(const StatsJob j) {
+    __shared__ unsigned int s_h[SBINS];
+    __shared__ unsigned int s_scan[NT];
+    __shared__ int s_res[4];
+    __shared__ bool s_last;
+    // sample CTAs have their own plane map (far fewer CTAs than the full-read kernels)
+    int k = j.nplanes - 1;
+    while (k > 0 && (int)blockIdx.x < j.pl[k].s_cta_begin) --k;
+    const StatsPlane& p = j.pl[k];
+    const int local = (int)blockIdx.x - p.s_cta_begin;
+    const int frame = blockIdx.y;
+    const size_t fp = (size_t)frame * j.nplanes + k;
+    const char* a = j.a + (size_t)frame * j.a_fs + p.a_off;
+    for (int i = threadIdx.x; i < SBINS; i += NT) s_h[i] = 0u;
+    __syncthreads();
+
+    constexpr int V = El<T>::PER16, U = 4;
+    const int nvec = p.w / V;
+    const int sshift = j.sshift;
+    const unsigned int hist_size = j.hist_size;
+    // The sample is every s_step-th 128-byte line of the plane in raster order; s_step is coprime with the lines per
+    // row, so consecutive rows are sampled at shifting columns.  8 lanes read one line, a warp 4 lines, U in flight.
+    const long long nlines = (long long)p.h * p.s_lpr;
+    const long long nsl = (nlines + p.s_step - 1) / p.s_step;  // sampled lines
+    const int sub = threadIdx.x & 7;
+    const long long first = (long long)local * (NT / 8) + (threadIdx.x >> 3);
+    const long long stride = (long long)p.s_nctas * (NT / 8);
+    for (long long s0 = first; s0 < nsl; s0 += stride * U) {
+        uint4 av[U];
+        bool ok[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long s = s0 + u * stride;
+            const long long line = s * p.s_step;
+            const int r = (int)(line / p.s_lpr), c = (int)(line - (long long)r * p.s_lpr);
+            const int v = c * 8 + sub;
+            ok[u] = s < nsl && v < nvec;
+            if (ok[u]) av[u] = __ldg(reinterpret_cast<const uint4*>(a + (size_t)r * p.a_pitch) + v);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (!ok[u]) continue;
+            const T* e = reinterpret_cast<const T*>(&av[u]);
+            bool flat = (av[u].x == av[u].y) & (av[u].y == av[u].z) & (av[u].z == av[u].w);
+            if (sizeof(T) <= 2) flat = flat & (__byte_perm(av[u].x, 0u, 0x1032) == av[u].x);
+            if (sizeof(T) == 1) flat = flat & (__byte_perm(av[u].x, 0u, 0x0321) == av[u].x);
+            if (flat) {  // constant vector: one atomic (flat areas would otherwise serialise on one address)
+                const unsigned int bin = bin_of<T>(e[0]);
+                if (bin < hist_size) atomicAdd(&s_h[bin >> sshift], (unsigned)V);
+            } else {
+#pragma unroll
+                for (int i = 0; i < V; ++i) {
+                    const unsigned int bin = bin_of<T>(e[i]);
+                    if (bin < hist_size) atomicAdd(&s_h[bin >> sshift], 1u);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    unsigned int* sh = j.ssample + fp * SBINS;
+    for (int i = threadIdx.x; i < SBINS; i += NT) {
+        const unsigned int c = s_h[i];
+        if (c) atomicAdd(&sh[i], c);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(j.counters3 + fp, 1u) == (unsigned)p.s_nctas - 1u);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    // ---- last sample CTA of the plane: bracket both ranks.  Each thread owns SBINS/NT consecutive bins.
+    constexpr int PER = SBINS / NT;
+    unsigned int mine[PER], local_sum = 0u;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) { mine[i] = __ldcg(sh + threadIdx.x * PER + i); local_sum += mine[i]; }
+    s_scan[threadIdx.x] = local_sum;
+    if (threadIdx.x < 4) s_res[threadIdx.x] = -1;
+    __syncthreads();
+    for (int o = 1; o < NT; o <<= 1) {  // inclusive Hillis-Steele scan
+        const unsigned int add = (int)threadIdx.x >= o ? s_scan[threadIdx.x - o] : 0u;
+        __syncthreads();
+        s_scan[threadIdx.x] += add;
+        __syncthreads();
+    }
+    const unsigned int ns = s_scan[NT - 1];
+    const unsigned int before = s_scan[threadIdx.x] - local_sum;
+    // requested ranks scaled to the sample, +- a margin of 4.5 binomial sigmas + 0.05 % (pictures are not i.i.d.)
+    const double npx = (double)p.w * (double)p.h, scale = (double)ns / npx;
+    double q[4];
+    {
+        const double full = (p.s_step == 1 && nvec * V == p.w) ? 0.0 : 1.0;  // complete sample: no margin
+        const double f_lo = fmin((double)p.tmin / npx, 1.0), f_hi = fmin((double)p.tmax / npx, 1.0);
+        const double dmin = full * (4.5 * sqrt((double)ns * f_lo * (1.0 - f_lo)) + 0.0005 * ns + 2.0);
+        const double dmax = full * (4.5 * sqrt((double)ns * f_hi * (1.0 - f_hi)) + 0.0005 * ns + 2.0);
+        const double tmin_s = (double)p.tmin * scale, top = (double)ns - 1.0 - (double)p.tmax * scale;
+        q[0] = tmin_s - dmin; q[1] = tmin_s + dmin; q[2] = top - dmax; q[3] = top + dmax;
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const double qc = fmin(fmax(q[t], 0.0), (double)ns - 1.0);
+        const unsigned int qi = ns ? (unsigned int)qc : 0u;
+        if (local_sum && qi >= before && qi < before + local_sum) {
+            unsigned int c = before;
+            int hit = PER - 1;
+#pragma unroll
+            for (int i = 0; i < PER; ++i) { c += mine[i]; if (qi < c) { hit = i; break; } }
+            s_res[t] = (int)threadIdx.x * PER + hit;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    const int nsb = (int)((hist_size + (1u << sshift) - 1u) >> sshift);
+    auto to_bins = [&](int lo_sb, int hi_sb, unsigned int& l, unsigned int& u) {
+        if (lo_sb < 0) lo_sb = 0;
+        if (hi_sb < 0) hi_sb = nsb - 1;
+        l = (unsigned)lo_sb << sshift;
+        u = min((unsigned)(hi_sb + 1) << sshift, hist_size);
+        if (u - l > (unsigned)FINE_W) {  // sparse codes: keep the middle, the exactness check decides
+            const unsigned int mid = l + (u - l) / 2u;
+            l = max(l, mid - FINE_W / 2u);
+            u = l + FINE_W;
+        }
+    };
+    Bracket br;
+    to_bins(s_res[0], s_res[1], br.l_min, br.u_min);
+    to_bins(s_res[2], s_res[3], br.l_max, br.u_max);
+    br.done = 0u; br.pad[0] = br.pad[1] = br.pad[2] = 0u;
+    j.brackets[fp] = br;
+}
+
+// Packs the histogram bins of one 16-byte vector two per 32-bit word so that the per-sample work below runs on
+// VIMNMX.U16x2 (two samples per instruction).
+template <typename T> __device__ __forceinline__ void pack_bins(const uint4& v, unsigned int (&w)[El<T>::PER16 / 2]) {
+    if constexpr (sizeof(T) == 2 && !El<T>::flt) {
+        w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+    } else if constexpr (sizeof(T) == 1) {
+        const unsigned int s[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { w[2 * q] = __byte_perm(s[q], 0u, 0x4140); w[2 * q + 1] = __byte_perm(s[q], 0u, 0x4342); }
+    } else {
+        const T* e = reinterpret_cast<const T*>(&v);
+#pragma unroll
+        for (int q = 0; q < El<T>::PER16 / 2; ++q) w[q] = bin_of<T>(e[2 * q]) | (bin_of<T>(e[2 * q + 1]) << 16);
+    }
+}
+
+// "count samples whose bin is >= t" as packed arithmetic: min(max(x, A), B) - C is 1 in each 16-bit half whose
+// bin is >= t and 0 otherwise (A = t-1, B = t, C = t-1; t = 0 and t = 65536 degenerate to constants).
+struct PackedThr { unsigned int A, B, C; };
+__device__ __forceinline__ PackedThr packed_thr(unsigned int t) {
+    unsigned int a, b, c;
+    if (t == 0u) { a = b = 1u; c = 0u; }
+    else if (t >= 65536u) { a = b = 0u; c = 0u; }
+    else { a = t - 1u; b = t; c = t - 1u; }
+    return PackedThr{a * 0x10001u, b * 0x10001u, c * 0x10001u};
+}
+
+// TRACK = false: every bin is valid (full-depth integer or float clip) and both ranks are > 0, so the exact
+// min/max tracking drops out of the per-sample work.  With TRACK the packed min/max give the answers for zero
+// ranks and detect samples above the format's peak (such planes are left to the exact two-pass kernels).
+template <typename T, bool HAS_B, bool TRACK>
+__global__ void __launch_bounds__(NT) minmax_bracket_kernel(const StatsJob j) {
+    constexpr int V = El<T>::PER16, NW = V / 2, G = HAS_B ? 2 : 4;
+    __shared__ unsigned int s_fine[2][FINE_W];
+    __shared__ uint4 s_q[NT / 32][G * 32];  // per warp: the vectors of one step that hold a sample inside a bracket
+    // own plane map: in large batches this kernel uses fewer, longer-running CTAs than the other reductions
+    int k = j.nplanes - 1;
+    while (k > 0 && (int)blockIdx.x < j.pl[k].b_cta_begin) --k;
+    const StatsPlane& p = j.pl[k];
+    const int local = (int)blockIdx.x - p.b_cta_begin;
+    const int frame = blockIdx.y;
+    const size_t fp = (size_t)frame * j.nplanes + k;
+    const char* a = j.a + (size_t)frame * j.a_fs + p.a_off;
+    const char* b = HAS_B ? j.b + (size_t)frame * j.b_fs + p.b_off : nullptr;
+    const Bracket br = j.brackets[fp];
+    const int rows_per = (p.h + p.b_nctas - 1) / p.b_nctas;
+    const int y0 = min(local * rows_per, p.h), y1 = min(y0 + rows_per, p.h);
+    for (int i = threadIdx.x; i < 2 * FINE_W; i += NT) (&s_fine[0][0])[i] = 0u;
+    __syncthreads();
+    const unsigned int hist_size = j.hist_size;
+    const unsigned int l_min = br.l_min, u_min = br.u_min, l_max = br.l_max, u_max = br.u_max;  // [l, u) in bins
+    const unsigned int w_min = u_min - l_min, w_max = u_max - l_max;
+    const PackedThr t0 = packed_thr(l_min), t1 = packed_thr(u_min), t2 = packed_thr(l_max), t3 = packed_thr(u_max);
+    const unsigned int k01 = t1.C - t0.C, k23 = t3.C - t2.C;
+
+    Partial acc = empty_partial();
+    unsigned int ge_lmin = 0, ge_umax = 0, idiff32 = 0;    // exact counts of samples with bin >= l_min / >= u_max
+    unsigned int pk_ge_lmin = 0, pk_ge_umax = 0;           // packed 2 x 16-bit partial counts
+    unsigned int pk_min = 0xffffffffu, pk_max = 0u;
+
+    auto fine_add = [&](unsigned int bin, unsigned int n) {
+        if (bin - l_min < w_min) atomicAdd(&s_fine[0][bin - l_min], n);
+        if (bin - l_max < w_max) atomicAdd(&s_fine[1][bin - l_max], n);
+    };
+    auto visit_vec = [&](const uint4& av, const uint4& bv) -> bool {  // true: some sample lies inside a bracket
+        unsigned int w[NW];
+        pack_bins<T>(av, w);
+        unsigned int any = 0u;
+#pragma unroll
+        for (int q = 0; q < NW; ++q) {
+            const unsigned int m0 = __vminu2(__vmaxu2(w[q], t0.A), t0.B);
+            const unsigned int m1 = __vminu2(__vmaxu2(w[q], t1.A), t1.B);
+            const unsigned int m2 = __vminu2(__vmaxu2(w[q], t2.A), t2.B);
+            const unsigned int m3 = __vminu2(__vmaxu2(w[q], t3.A), t3.B);
+            pk_ge_lmin += m0 - t0.C;
+            pk_ge_umax += m3 - t3.C;
+            any |= (m0 - m1 + k01) | (m2 - m3 + k23);  // per half: 1 if inside the min / max bracket
+            if constexpr (TRACK) { pk_min = __vminu2(pk_min, w[q]); pk_max = __vmaxu2(pk_max, w[q]); }
+        }
+        if constexpr (HAS_B) {
+            const T* ae = reinterpret_cast<const T*>(&av);
+            const T* be = reinterpret_cast<const T*>(&bv);
+#pragma unroll
+            for (int i = 0; i < V; ++i) acc.fdiff += abs_diff<T>(ae[i], be[i], idiff32);
+        }
+        return any != 0u;
+    };
+    auto visit_one = [&](T at, T bt) {  // scalar row tails
+        const unsigned int bin = bin_of<T>(at);
+        ge_lmin += bin >= l_min ? 1u : 0u;
+        ge_umax += bin >= u_max ? 1u : 0u;
+        fine_add(bin, 1u);
+        if constexpr (TRACK) { pk_min = __vminu2(pk_min, bin * 0x10001u); pk_max = __vmaxu2(pk_max, bin * 0x10001u); }
+        if constexpr (HAS_B) acc.fdiff += abs_diff<T>(at, bt, idiff32);
+    };
+
+    const int nvec = p.w / V;
+    const int iters = (nvec + NT - 1) / NT;
+    const int lane = threadIdx.x & 31;
+    const unsigned int lt_mask = (1u << lane) - 1u;
+    uint4* myq = s_q[threadIdx.x >> 5];
+    for (int y = y0; y < y1; y += G) {
+        for (int it = 0; it < iters; ++it) {
+            const int v = it * NT + (int)threadIdx.x;
+            uint4 av[G], bv[G];
+            bool hit[G];
+#pragma unroll
+            for (int g = 0; g < G; ++g) hit[g] = false;
+            if (v < nvec) {
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    const int yy = min(y + g, y1 - 1);
+                    av[g] = __ldg(reinterpret_cast<const uint4*>(a + (size_t)yy * p.a_pitch) + v);
+                    if constexpr (HAS_B) bv[g] = __ldg(reinterpret_cast<const uint4*>(b + (size_t)yy * p.b_pitch) + v);
+                    else bv[g] = av[g];
+                }
+#pragma unroll
+                for (int g = 0; g < G; ++g)
+                    if (y + g < y1) hit[g] = visit_vec(av[g], bv[g]);
+            }
+            // queue the vectors with hits (slots from a ballot, no atomics), then the warp drains its own queue one
+            // sample per lane; nothing here needs a CTA barrier
+            unsigned int nq = 0u;
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                const unsigned int m = __ballot_sync(0xffffffffu, hit[g]);
+                if (hit[g]) myq[nq + __popc(m & lt_mask)] = av[g];
+                nq += __popc(m);
+            }
+            __syncwarp();
+            nq *= (unsigned)V;
+            for (unsigned int i0 = 0; i0 < nq; i0 += 32) {
+                const unsigned int i = i0 + lane;
+                const bool ok = i < nq;
+                const unsigned int bin = ok ? bin_of<T>(reinterpret_cast<const T*>(myq)[i]) : 0xffffffffu;
+                const unsigned int d0 = bin - l_min, d1 = bin - l_max;
+                const bool v0 = ok && d0 < w_min, v1 = ok && d1 < w_max;
+                if (!__any_sync(0xffffffffu, v0 || v1)) continue;
+                if (__all_sync(0xffffffffu, bin == __shfl_sync(0xffffffffu, bin, 0))) {
+                    // flat picture area: one atomic instead of 32 serialised on the same address
+                    if (lane == 0) { if (v0) atomicAdd(&s_fine[0][d0], 32u); if (v1) atomicAdd(&s_fine[1][d1], 32u); }
+                } else {
+                    if (v0) atomicAdd(&s_fine[0][d0], 1u);
+                    if (v1) atomicAdd(&s_fine[1][d1], 1u);
+                }
+            }
+            __syncwarp();
+        }
+        const int x = nvec * V + threadIdx.x;
+        if (x < p.w) {
+            for (int g = 0; g < G && y + g < y1; ++g) {
+                const T at = reinterpret_cast<const T*>(a + (size_t)(y + g) * p.a_pitch)[x];
+                const T bt = HAS_B ? reinterpret_cast<const T*>(b + (size_t)(y + g) * p.b_pitch)[x] : at;
+                visit_one(at, bt);
+            }
+        }
+        // a thread adds at most G * iters * NW <= 4 * 32 * 8 to each 16-bit half per group of rows
+        ge_lmin += (pk_ge_lmin & 0xffffu) + (pk_ge_lmin >> 16);
+        ge_umax += (pk_ge_umax & 0xffffu) + (pk_ge_umax >> 16);
+        pk_ge_lmin = pk_ge_umax = 0u;
+        acc.idiff += idiff32; idiff32 = 0;
+    }
+    acc.isum = (unsigned long long)ge_lmin + ((unsigned long long)ge_umax << 32);
+    acc.imin = min(pk_min & 0xffffu, pk_min >> 16);
+    acc.imax = max(pk_max & 0xffffu, pk_max >> 16);
+    __syncthreads();
+    unsigned int* gf = j.bfine + fp * 1536;
+    for (int i = threadIdx.x; i < 1536; i += NT) {
+        const unsigned int c = (&s_fine[0][0])[i];
+        if (c) atomicAdd(&gf[i], c);
+    }
+    Partial total;
+    if (!block_finish(j, frame, k, local, p.b_nctas, j.counters + fp, acc, total)) return;
+    // ---- last CTA: resolve both ranks exactly if they lie inside their brackets (warp 0: min, warp 1: max)
+    __shared__ unsigned int s_cnt[2], s_ans[2];
+    __shared__ int s_okk[2];
+    if (threadIdx.x == 0) {
+        StatsRaw& r = j.out[fp];
+        r.idiff = total.idiff; r.fdiff = total.fdiff;
+        const unsigned long long npx0 = (unsigned long long)p.w * p.h;
+        s_cnt[0] = (unsigned int)(npx0 - (total.isum & 0xffffffffull));  // samples below l_min
+        s_cnt[1] = (unsigned int)(total.isum >> 32);                     // samples at or above u_max
+        s_okk[0] = s_okk[1] = 0;
+        s_ans[0] = total.imin; s_ans[1] = total.imax;
+    }
+    for (int i = threadIdx.x; i < 2 * FINE_W; i += NT) (&s_fine[0][0])[i] = __ldcg(gf + i);
+    __syncthreads();
+    if (TRACK && s_ans[1] >= hist_size) return;  // samples above the peak: exact path
+    const unsigned long long npx = (unsigned long long)p.w * p.h;
+    const int side = threadIdx.x >> 5;
+    if (side < 2) {
+        const unsigned int thr = side == 0 ? p.tmin : p.tmax;
+        const unsigned int width = side == 0 ? w_min : w_max;
+        const unsigned int outside = s_cnt[side];
+        // bins in scan order: ascending for the min rank, descending for the max rank
+        constexpr int PER = FINE_W / 32;
+        unsigned int mine[PER], sum = 0u;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            const unsigned int o = (unsigned)(lane * PER + i);
+            mine[i] = o < width ? s_fine[side][side == 0 ? o : width - 1u - o] : 0u;
+            sum += mine[i];
+        }
+        unsigned int incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        const unsigned int before = outside + incl - sum;
+        if ((unsigned long long)thr >= npx) { if (lane == 0) { s_okk[side] = 1; s_ans[side] = side == 0 ? hist_size - 1u : 0u; } }  // planeminmax.zig:44-48
+        else if (thr == 0u) { if (lane == 0) s_okk[side] = TRACK ? 1 : 0; }  // first / last non-empty bin (already in s_ans)
+        else if (outside <= thr && before <= thr && before + sum > thr) {
+            unsigned int c = before;
+#pragma unroll
+            for (int i = 0; i < PER; ++i) {
+                c += mine[i];
+                if (c > thr) {
+                    const unsigned int o = (unsigned)(lane * PER + i);
+                    s_ans[side] = side == 0 ? l_min + o : l_max + (width - 1u - o);
+                    s_okk[side] = 1;
+                    break;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && s_okk[0] && s_okk[1]) {
+        StatsRaw& r = j.out[fp];
+        r.bin_min = s_ans[0]; r.bin_max = s_ans[1];
+        j.brackets[fp].done = 1u;
+    }
+}
+
 // =========================================================================== host launchers
 // scratch layout (all zeroed before each call):
 //   counters  [2][count][np] u32 | coarse [count][np][256] u32 | fine [count][np][512] u32 | partials
 static size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 size_t stats_scratch_bytes(int count, int np) {
     const size_t n = (size_t)count * np;
-    return align256(2 * n * 4) + align256(n * 256 * 4) + align256(n * 512 * 4) + align256(n * MAX_CTAS_PER_PLANE * sizeof(Partial));
+    return align256(3 * n * 4) + align256(n * 256 * 4) + align256(n * SBINS * 4) + align256(n * 512 * 4) + align256(n * 1536 * 4) + align256(n * sizeof(Bracket)) +
+           align256(n * MAX_CTAS_PER_PLANE * sizeof(Partial));
 }
 
 static StatsJob make_job(const FrameLayout& l, const bool mask[3], const char* a, size_t a_fs, const char* b, size_t b_fs, int count,
                          void* scratch, StatsRaw* out, size_t* zero_bytes) {
     StatsJob j{};
     j.a = a; j.b = b; j.a_fs = a_fs; j.b_fs = b_fs;
-    int cta = 0, k = 0;
+    int cta = 0, scta = 0, bcta = 0, k = 0;
     for (int p = 0; p < l.nplanes; ++p) {
         if (!mask[p]) continue;
         StatsPlane& s = j.pl[k++];
@@ -486,13 +891,31 @@ static StatsJob make_job(const FrameLayout& l, const bool mask[3], const char* a
         n = std::min(n, s.h);
         s.cta_begin = cta; s.nctas = n;
         cta += n;
+        // line sample of the threshold fast path: planes under 1 M samples are sampled completely
+        s.s_lpr = (s.w * l.bps + 127) / 128;
+        s.s_step = 1;
+        if (px >= (1ll << 20)) {
+            s.s_step = 16;
+            if (s.s_lpr % 2 == 0) s.s_step = s.s_lpr % 17 ? 17 : 19;  // coprime with the lines per row
+        }
+        const long long nsl = ((long long)s.h * s.s_lpr + s.s_step - 1) / s.s_step;
+        s.s_nctas = (int)std::min<long long>(16, std::max<long long>(1, nsl / (NT / 8 * 8)));
+        s.s_cta_begin = scta;
+        scta += s.s_nctas;
+        // bracket kernel: 4x longer CTAs once the batch alone fills the GPU several times over
+        s.b_nctas = (long long)count * n >= 4096 ? std::max(1, n / 4) : n;
+        s.b_cta_begin = bcta;
+        bcta += s.b_nctas;
     }
-    j.nplanes = k; j.ctas_per_frame = cta;
+    j.nplanes = k; j.ctas_per_frame = cta; j.sample_ctas_per_frame = scta; j.bracket_ctas_per_frame = bcta;
     const size_t n = (size_t)count * k;
     char* sp = (char*)scratch;
-    j.counters = (unsigned int*)sp; j.counters2 = j.counters + n; sp += align256(2 * n * 4);
+    j.counters = (unsigned int*)sp; j.counters2 = j.counters + n; j.counters3 = j.counters2 + n; sp += align256(3 * n * 4);
     j.coarse = (unsigned int*)sp; sp += align256(n * 256 * 4);
+    j.ssample = (unsigned int*)sp; sp += align256(n * SBINS * 4);
     j.fine = (unsigned int*)sp; sp += align256(n * 512 * 4);
+    j.bfine = (unsigned int*)sp; sp += align256(n * 1536 * 4);
+    j.brackets = (Bracket*)sp; sp += align256(n * sizeof(Bracket));
     *zero_bytes = (size_t)(sp - (char*)scratch);
     j.partials = (Partial*)sp;
     j.out = out;
@@ -523,10 +946,27 @@ static int launch_minmax_t(StatsJob j, int count, bool no_thr, bool has_b, size_
             c.counters += (size_t)f0 * np; c.counters2 += (size_t)f0 * np;
             c.coarse += (size_t)f0 * np * 256; c.fine += (size_t)f0 * np * 512;
             c.out += (size_t)f0 * np;
+            c.counters3 += (size_t)f0 * np; c.ssample += (size_t)f0 * np * SBINS; c.bfine += (size_t)f0 * np * 1536;
+            c.brackets += (size_t)f0 * np;
             const dim3 grid(j.ctas_per_frame, nf);
-            if (has_b) hist_coarse_kernel<T, true><<<grid, NT, 0, st>>>(c);
-            else hist_coarse_kernel<T, false><<<grid, NT, 0, st>>>(c);
-            hist_fine_kernel<T><<<grid, NT, 0, st>>>(c);
+            // VSZIP_MINMAX_EXACT=1 skips the sampled fast path (used by the tests to exercise the exact kernels)
+            const char* ev = getenv("VSZIP_MINMAX_EXACT");
+            const bool fast = !(ev && ev[0] == '1') && (long long)j.pl[0].w * j.pl[0].h < (1ll << 31);
+            if (fast) {
+                hist_sample_kernel<T><<<dim3(j.sample_ctas_per_frame, nf), NT, 0, st>>>(c);  // 1/16 of the lines
+                // one full read (also Diff); the lean variant needs every bin valid and both ranks > 0 on every plane
+                bool lean = (j.hist_size == 65536u) || (sizeof(T) == 1 && j.hist_size == 256u);
+                for (int k = 0; k < np; ++k) lean = lean && j.pl[k].tmin > 0u && j.pl[k].tmax > 0u;
+                const dim3 bgrid(j.bracket_ctas_per_frame, nf);
+                if (has_b) { if (lean) minmax_bracket_kernel<T, true, false><<<bgrid, NT, 0, st>>>(c); else minmax_bracket_kernel<T, true, true><<<bgrid, NT, 0, st>>>(c); }
+                else { if (lean) minmax_bracket_kernel<T, false, false><<<bgrid, NT, 0, st>>>(c); else minmax_bracket_kernel<T, false, true><<<bgrid, NT, 0, st>>>(c); }
+                count_launch(2);
+            }
+            // exact two-pass select: only for planes the fast path could not resolve (else immediate exit)
+            const dim3 xgrid(j.ctas_per_frame, fast ? std::min(nf, 8) : nf);
+            if (has_b && !fast) hist_coarse_kernel<T, true><<<xgrid, NT, 0, st>>>(c, nf);
+            else hist_coarse_kernel<T, false><<<xgrid, NT, 0, st>>>(c, nf);
+            hist_fine_kernel<T><<<xgrid, NT, 0, st>>>(c, nf);
             count_launch(2);
         }
     }
@@ -545,6 +985,7 @@ int run_planeminmax(const FrameLayout& l, const bool mask[3], const char* a, siz
     int bits = 0;
     while ((1u << bits) < hist_size) ++bits;
     j.shift = bits > 8 ? bits - 8 : 0;
+    j.sshift = bits > 12 ? bits - 12 : 0;
     for (int k = 0; k < j.nplanes; ++k) {
         const double total = (double)((uint32_t)j.pl[k].w * (uint32_t)j.pl[k].h);
         j.pl[k].tmin = (unsigned int)(total * (double)minthr);  // trunc (src/filters/planeminmax.zig:40-41)
