@@ -59,6 +59,10 @@ def lib():
         _lib.vso_boxblur_plane.argtypes = [C.c_int, C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_ssize_t] + [C.c_int] * 6
         _lib.vso_bilateral_plane.argtypes = [C.c_int, C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_ssize_t,
                                              C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int]
+        _lib.vso_bilateral_pbfic_plane.argtypes = [C.c_int, C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_ssize_t,
+                                                   C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int]
+        _lib.vso_recursive_gaussian_params.argtypes = [C.c_double, C.c_void_p]
+        _lib.vso_recursive_gaussian_params.restype = None
         _lib.vso_bilateral_luts.argtypes = [C.c_double, C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         _lib.vso_bilateral_luts.restype = None
         _lib.vso_planeminmax_plane.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_ssize_t, C.c_int, C.c_int,
@@ -136,6 +140,27 @@ def bilateral_plane(src: np.ndarray, sigmaS, sigmaR, radius, step, hist_len, ref
                                    w, h, float(sigmaS), float(sigmaR), int(radius), int(step), int(hist_len))
     assert rc == 0
     return dst
+
+
+def bilateral_pbfic_plane(src: np.ndarray, sigmaS, sigmaR, pbfic_num, hist_len, ref: np.ndarray | None = None) -> np.ndarray:
+    """Algorithm-1 (PBFIC) bilateral on one plane with already-derived per-plane parameters."""
+    _chk2d(src)
+    if ref is None:
+        ref = src
+    _chk2d(ref)
+    assert ref.shape == src.shape and ref.dtype == src.dtype
+    dst = np.empty_like(src, order="C")
+    h, w = src.shape
+    rc = lib().vso_bilateral_pbfic_plane(sample_type_of(src), _p(src), src.strides[0], _p(ref), ref.strides[0], _p(dst), dst.strides[0],
+                                         w, h, float(sigmaS), float(sigmaR), int(pbfic_num), int(hist_len))
+    assert rc == 0
+    return dst
+
+
+def recursive_gaussian_params(sigma) -> np.ndarray:
+    out = np.zeros(4, np.float32)
+    lib().vso_recursive_gaussian_params(float(sigma), _p(out))
+    return out
 
 
 def planeminmax_plane(src: np.ndarray, bits: int, minthr=0.0, maxthr=0.0, ref: np.ndarray | None = None) -> dict:

@@ -319,6 +319,130 @@ void bilateral_plane_t(const void* src, ptrdiff_t sst, const void* ref, ptrdiff_
 }
 
 // ---------------------------------------------------------------------------
+// Bilateral, algorithm 1 (PBFIC, "Real-Time O(1) Bilateral Filtering")
+// ---------------------------------------------------------------------------
+
+// src/filters/bilateral.zig:336-348 (f64 -> f32)
+void recursive_gaussian_params(double sigma, float* b, float* b1, float* b2, float* b3) {
+    const double q = sigma < 2.5 ? (3.97156 - 4.14554 * std::sqrt(1 - 0.26891 * sigma)) : 0.98711 * sigma - 0.96330;
+    const double den = 1.57825 + 2.44413 * q + 1.4281 * q * q + 0.422205 * q * q * q;
+    const double n1 = 2.44413 * q + 2.85619 * q * q + 1.26661 * q * q * q;
+    const double n2 = -(1.4281 * q * q + 1.26661 * q * q * q);
+    const double n3 = 0.422205 * q * q * q;
+    *b = (float)(1 - (n1 + n2 + n3) / den);
+    *b1 = (float)(n1 / den);
+    *b2 = (float)(n2 / den);
+    *b3 = (float)(n3 / den);
+}
+
+// p0 = ((b*x + b1*p1) + b2*p2) + b3*p3, separate multiplies and adds (strict float mode)
+inline float iir_tap(float b, float x, float b1, float p1, float b2, float p2, float b3, float p3) {
+    float acc = b * x;
+    acc = acc + b1 * p1;
+    acc = acc + b2 * p2;
+    acc = acc + b3 * p3;
+    return acc;
+}
+
+// In-place horizontal pass, src/filters/bilateral.zig:396-431: forward with the history initialised to the first
+// sample, backward with the history initialised to the (forward-filtered) last sample, which itself is kept.
+void recursive_gaussian_h(float* img, int w, int h, float b, float b1, float b2, float b3) {
+    for (int j = 0; j < h; ++j) {
+        float* row = img + (size_t)j * w;
+        float p1 = row[0], p2 = p1, p3 = p1;
+        for (int i = 1; i < w; ++i) {
+            const float p0 = iir_tap(b, row[i], b1, p1, b2, p2, b3, p3);
+            p3 = p2; p2 = p1; p1 = p0;
+            row[i] = p0;
+        }
+        if (w == 1) continue;
+        p1 = row[w - 1]; p2 = p1; p3 = p1;
+        for (int i = w - 2; i >= 0; --i) {
+            const float p0 = iir_tap(b, row[i], b1, p1, b2, p2, b3, p3);
+            p3 = p2; p2 = p1; p1 = p0;
+            row[i] = p0;
+        }
+    }
+}
+
+// In-place vertical pass, src/filters/bilateral.zig:350-394: the history rows are clamped row indices, so row 0
+// (forward) and row h-1 (backward) are filtered against themselves (the right-hand side is read before the store).
+void recursive_gaussian_v(float* img, int w, int h, float b, float b1, float b2, float b3) {
+    for (int j = 0; j < h; ++j) {
+        float* x0 = img + (size_t)j * w;
+        const float* x1 = j < 1 ? x0 : x0 - w;
+        const float* x2 = j < 2 ? x1 : x1 - w;
+        const float* x3 = j < 3 ? x2 : x2 - w;
+        for (int i = 0; i < w; ++i) x0[i] = iir_tap(b, x0[i], b1, x1[i], b2, x2[i], b3, x3[i]);
+    }
+    for (int j = h - 1; j >= 0; --j) {
+        float* x0 = img + (size_t)j * w;
+        const float* x1 = j >= h - 1 ? x0 : x0 + w;
+        const float* x2 = j >= h - 2 ? x1 : x1 + w;
+        const float* x3 = j >= h - 3 ? x2 : x2 + w;
+        for (int i = 0; i < w; ++i) x0[i] = iir_tap(b, x0[i], b1, x1[i], b2, x2[i], b3, x3[i]);
+    }
+}
+
+// src/filters/bilateral.zig:91-171
+template <class T>
+void pbfic_plane_t(const void* src, ptrdiff_t sst, const void* ref, ptrdiff_t rst, void* dst, ptrdiff_t dstt, int w, int h,
+                   const float* gr, double sigma_s, int num, float peak) {
+    std::vector<T> pk((size_t)num);
+    if (is_flt<T>::value) {
+        const T denom = (T)(float)(num - 1);
+        for (int k = 0; k < num; ++k) pk[k] = (T)((T)(float)k / denom);  // the division is done in T
+    } else {
+        const float numf = (float)num;
+        for (int k = 0; k < num; ++k) {
+            float v = peak * (float)k;
+            v = v / (numf - 1.0f);
+            v = v + 0.5f;
+            const float hi = (float)std::numeric_limits<T>::max();  // lossyCast: saturating truncation
+            pk[k] = std::isnan(v) ? (T)0 : v >= hi ? std::numeric_limits<T>::max() : v <= 0.0f ? (T)0 : (T)v;
+        }
+    }
+    float b, b1, b2, b3;
+    recursive_gaussian_params(sigma_s, &b, &b1, &b2, &b3);
+    const size_t n = (size_t)w * h;
+    std::vector<float> levels((size_t)num * n), wk(n), jk(n);
+    for (int k = 0; k < num; ++k) {
+        for (int y = 0; y < h; ++y) {
+            const T* sp = row_ptr<T>(src, sst, y);
+            const T* rp = row_ptr<T>(ref, rst, y);
+            for (int x = 0; x < w; ++x) {
+                const float wv = gr[range_index<T>(pk[k], rp[x])];
+                wk[(size_t)y * w + x] = wv;
+                jk[(size_t)y * w + x] = wv * (float)sp[x];
+            }
+        }
+        recursive_gaussian_h(wk.data(), w, h, b, b1, b2, b3);
+        recursive_gaussian_v(wk.data(), w, h, b, b1, b2, b3);
+        recursive_gaussian_h(jk.data(), w, h, b, b1, b2, b3);
+        recursive_gaussian_v(jk.data(), w, h, b, b1, b2, b3);
+        float* lv = levels.data() + (size_t)k * n;
+        for (size_t i = 0; i < n; ++i) lv[i] = (wk[i] == 0.0f) ? 0.0f : jk[i] / wk[i];
+    }
+    for (int y = 0; y < h; ++y) {
+        const T* rp = row_ptr<T>(ref, rst, y);
+        T* dp = row_ptr<T>(dst, dstt, y);
+        for (int x = 0; x < w; ++x) {
+            int k = 0;
+            while (k < num - 2) {
+                if (rp[x] < pk[k + 1] && rp[x] >= pk[k]) break;
+                ++k;
+            }
+            const float rf = (float)rp[x], p0f = (float)pk[k], p1f = (float)pk[k + 1];
+            const size_t i = (size_t)y * w + x;
+            const float lo = levels[(size_t)k * n + i], hi = levels[(size_t)(k + 1) * n + i];
+            const float t0 = (p1f - rf) * lo, t1 = (rf - p0f) * hi;
+            const float vf = (t0 + t1) / (p1f - p0f);
+            dp[x] = bilateral_finalize<T>(vf, 1.0f, peak);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // PlaneMinMax / PlaneAverage
 // ---------------------------------------------------------------------------
 
@@ -573,6 +697,26 @@ int vso_bilateral_plane(int st, const void* src, ptrdiff_t sstride, const void* 
     }
     return -1;
 }
+
+// Algorithm-1 (PBFIC) bilateral on one plane.  `ref` may equal `src` (non-joint).
+int vso_bilateral_pbfic_plane(int st, const void* src, ptrdiff_t sstride, const void* ref, ptrdiff_t rstride,
+                              void* dst, ptrdiff_t dstride, int w, int h, double sigmaS, double sigmaR,
+                              int pbfic_num, int hist_len) {
+    if (pbfic_num < 2) return -2;
+    std::vector<float> gr;
+    const float peak = (float)(hist_len - 1);
+    range_lut(gr, hist_len, (double)peak, sigmaR);
+    switch (st) {
+        case ST_U8: pbfic_plane_t<uint8_t>(src, sstride, ref, rstride, dst, dstride, w, h, gr.data(), sigmaS, pbfic_num, peak); return 0;
+        case ST_U16: pbfic_plane_t<uint16_t>(src, sstride, ref, rstride, dst, dstride, w, h, gr.data(), sigmaS, pbfic_num, peak); return 0;
+        case ST_F16: pbfic_plane_t<f16>(src, sstride, ref, rstride, dst, dstride, w, h, gr.data(), sigmaS, pbfic_num, peak); return 0;
+        case ST_F32: pbfic_plane_t<float>(src, sstride, ref, rstride, dst, dstride, w, h, gr.data(), sigmaS, pbfic_num, peak); return 0;
+    }
+    return -1;
+}
+
+// src/filters/bilateral.zig:336-348, exposed for the host-logic tests
+void vso_recursive_gaussian_params(double sigma, float* out4) { recursive_gaussian_params(sigma, out4, out4 + 1, out4 + 2, out4 + 3); }
 
 struct vso_minmax_out { long long imin, imax; double fmin, fmax, diff; };
 

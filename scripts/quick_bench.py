@@ -22,6 +22,9 @@ def t(f):
 cfgs = {"H5": dict(hradius=13, hpasses=5, vradius=0, vpasses=0), "V5": dict(hradius=0, hpasses=0, vradius=13, vpasses=5),
         "HV5": dict(hradius=13, hpasses=5, vradius=13, vpasses=5), "CT13": dict(hradius=13, vradius=13),
         "H1": dict(hradius=13, hpasses=1, vradius=0, vpasses=0), "V1": dict(hradius=0, hpasses=0, vradius=13, vpasses=1)}
+for p in (2, 3, 4):
+    cfgs["H%d" % p] = dict(hradius=13, hpasses=p, vradius=0, vpasses=0)
+    cfgs["V%d" % p] = dict(hradius=0, hpasses=0, vradius=13, vpasses=p)
 out = {}
 for k, a in cfgs.items():
     ms = t(vz.BoxBlurFilter(src.info(), **a))

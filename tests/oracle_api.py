@@ -45,8 +45,10 @@ def bilateral(clip, ref=None, sigmaS=None, sigmaR=None, planes=None, algorithm=N
         if not prm.process[i]:
             out.append(p.copy())
             continue
-        assert prm.algorithm[i] == 2, "oracle restates algorithm 2 only"
         r = None if ref is None else ref["planes"][i]
+        if prm.algorithm[i] == 1:
+            out.append(oracle.bilateral_pbfic_plane(p, prm.sigmaS[i], prm.sigmaR[i], prm.pbfic_num[i], prm.hist_len, r))
+            continue
         out.append(oracle.bilateral_plane(p, prm.sigmaS[i], prm.sigmaR[i], prm.radius[i], prm.step[i], prm.hist_len, r))
     return {"format": clip["format"], "planes": out}
 

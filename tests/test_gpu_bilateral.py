@@ -1,4 +1,4 @@
-"""Bilateral (algorithm 2) parity on the GPU against the CPU oracle.
+"""Bilateral (algorithm 2 and algorithm 1 / PBFIC) parity on the GPU against the CPU oracle.
 
 Bars (BASELINE.json north_star): integer outputs within 1 LSB with the exact-match fraction reported,
 float outputs within 1e-5 relative.  Where the range weights come from the reference's own LUT
@@ -48,7 +48,7 @@ def compare(got, want, info, what):
     return report
 
 
-@pytest.mark.parametrize("key", sorted(k for k in GOLD if "|ref" not in k and "algorithm=1" not in k))
+@pytest.mark.parametrize("key", sorted(k for k in GOLD if "|ref" not in k))
 def test_golden_cases(key):
     fmt, geo, args, _ = oa.parse_case_id(key)
     clip = fx.make_clip(fmt, geo)
@@ -127,3 +127,50 @@ def test_device_batch_matches_get_frame():
         planes = src.download(i)
         node = vz.core.clip_from_frames(fmt, [planes]).vszip.Bilateral(sigmaS=2, sigmaR=2)
         assert_same_planes(dst.download(i), node.get_frame(0).planes, f"frame {i}")
+
+
+# --------------------------------------------------------------------------- algorithm 1 (PBFIC): bit-exact
+@pytest.mark.parametrize("fmt", ["GRAY8", "GRAY10", "GRAY16", "GRAYH", "GRAYS", "YUV420P16", "YUV444PS"])
+@pytest.mark.parametrize("args", [dict(sigmaS=3, sigmaR=0.1, PBFICnum=4), dict(sigmaS=8, sigmaR=0.1), dict(sigmaS=1.5, sigmaR=0.02, PBFICnum=7),
+                                  dict(sigmaS=[4, 2], sigmaR=[0.2, 0.05], PBFICnum=[3, 9])], ids=str)
+def test_pbfic_noise(fmt, args):
+    base = "GRAY16" if fmt == "GRAY10" else fmt
+    clip = noise_clip(base, 203, 131, seed=15)
+    if fmt == "GRAY10":
+        clip = {"format": "GRAY10", "planes": [clip["planes"][0] >> 6]}
+    got, info = run(clip, algorithm=1, **args)
+    assert all(a == 1 for a, p in zip(info.algorithm, info.process) if p)
+    assert_same_planes(got["planes"], oa.bilateral(clip, algorithm=1, **args)["planes"], f"PBFIC {fmt} {args}")
+
+
+def test_pbfic_auto_selected_and_mixed_planes():
+    """sigmaS=8, sigmaR=0.1 auto-selects algorithm 1 on luma (bilateral.zig:196); chroma of a 4:2:0 clip gets
+    sigmaS/2 and stays on algorithm 2 (computed weights there: <= 1 LSB)."""
+    clip = noise_clip("YUV420P16", 322, 178, seed=21)
+    got, info = run(clip, sigmaS=8, sigmaR=0.1)
+    want = oa.bilateral(clip, sigmaS=8, sigmaR=0.1)
+    assert list(info.algorithm)[0] == 1
+    compare(got, want, info, "auto PBFIC")
+
+
+def test_pbfic_joint_and_tiny_planes():
+    clip = noise_clip("GRAY16", 97, 45, seed=3)
+    ref = noise_clip("GRAY16", 97, 45, seed=4)
+    got, _ = run(clip, ref=ref, sigmaS=3, sigmaR=0.1, algorithm=1)
+    assert_same_planes(got["planes"], oa.bilateral(clip, ref=ref, sigmaS=3, sigmaR=0.1, algorithm=1)["planes"], "PBFIC joint")
+    for (w, h) in ((1, 1), (1, 9), (9, 1), (2, 3), (33, 2), (64, 33)):
+        c = noise_clip("GRAYS", w, h, seed=w * 100 + h)
+        got, _ = run(c, sigmaS=2, sigmaR=0.3, algorithm=1, PBFICnum=2)
+        assert_same_planes(got["planes"], oa.bilateral(c, sigmaS=2, sigmaR=0.3, algorithm=1, PBFICnum=2)["planes"], f"PBFIC {w}x{h}")
+
+
+def test_pbfic_device_batch_and_full_size():
+    fmt, w, h, n = "YUV420P16", 1920, 1080, 3
+    a, d = vz.DeviceClip(fmt, w, h, n), vz.DeviceClip(fmt, w, h, n)
+    a.fill_noise(seed=11)
+    f = vz.BilateralFilter(a.info(), sigmaS=3, sigmaR=0.1, algorithm=1, planes=[0, 1])
+    f.run_device(a, d)
+    src = {"format": fmt, "planes": a.download(2)}
+    want = oa.bilateral(src, sigmaS=3, sigmaR=0.1, algorithm=1, planes=[0, 1])
+    got = d.download(2)
+    assert_same_planes(got[:2], want["planes"][:2], "PBFIC 1080p frame 2")

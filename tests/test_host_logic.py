@@ -71,8 +71,10 @@ def test_bilateral_small_chroma_errors():
            lambda: core.BlankClip("YUV420P8", 64, 64).vszip.Bilateral(sigmaS=[2, 20], algorithm=2))
 
 
-def test_bilateral_algorithm1_is_rejected_loudly():
-    raises("algorithm 1 \\(PBFIC\\).*no CPU fallback", lambda: core.BlankClip("GRAY16", 64, 64).vszip.Bilateral(sigmaS=3, sigmaR=0.1, algorithm=1))
+def test_bilateral_algorithm1_is_accepted():
+    """PBFIC has a CUDA path; a plane on algorithm 1 is exempt from the radius size check (bilateral.zig:201-214)."""
+    info = core.BlankClip("GRAY16", 8, 8).vszip.Bilateral(sigmaS=20, sigmaR=0.1, algorithm=1).filter.info()
+    assert info.algorithm[0] == 1 and info.PBFICnum[0] == 4
 
 
 def test_bilateral_ref_mismatch():

@@ -5,8 +5,8 @@ from the real Zig plugin under VapourSynth).  Each case rebuilds the reference's
 (oracle/fixtures.py), runs the oracle and compares with the recorded snapshot - tighter than the
 reference's own rel=1e-6 (tests/golden.py:187-191): averages to 1e-12 relative, min/max exact.
 
-Keys that need VapourSynth's std.BoxBlur (a different plugin) for their second clip, and the
-algorithm=1 (PBFIC) keys, are not reproducible here and are listed as skipped.
+Keys that need VapourSynth's std.BoxBlur (a different plugin) for their second clip are not
+reproducible here and are listed as skipped.
 """
 import json
 from pathlib import Path
@@ -61,8 +61,6 @@ def test_bilateral_golden(key):
     fmt, geo, args, variant = oa.parse_case_id(key)
     if variant == "ref":
         pytest.skip("joint clip is built with VapourSynth's std.BoxBlur (not part of vszip)")
-    if args.get("algorithm") == 1:
-        pytest.skip("algorithm 1 (PBFIC) is outside the restated hot path (SURVEY 8f rank 2)")
     out = oa.bilateral(fx.make_clip(fmt, geo), **args)
     _assert_stats(oa.golden_stats(out), _load("bilateral")[key])
 

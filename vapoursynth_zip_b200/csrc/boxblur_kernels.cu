@@ -182,7 +182,12 @@ struct LinePipe {
     static constexpr int NL = Px<T>::NL;
     static constexpr int SLOT_WORDS = P * NT * W;
 
+    // u16 runtime path: the low 16-bit line of va[] is also carried unpacked (it falls out of the previous stage's
+    // S >> 16) and the subtrahend's low line is folded in arithmetically, which moves three unpack operations per
+    // word and stage from the ALU pipe (the bound of these kernels on B200) to IMADs on the FMA pipe.
+    static constexpr bool SPLIT = std::is_same<T, uint16_t>::value && MODE == MODE_RT;
     Acc S[P][W][NL];
+    uint32_t alo[P][W];  // SPLIT only: va[q].v[w] & 0xffff
     V va[P], vb[P];   // operands of stage q+1 for the next step
     V pa[P], pb[P];   // ring cells of slot(t) and slot(t+1), fetched two / one step(s) ahead of their exchange
     uint32_t* ring;   // &ring_base[tid * W]
@@ -201,6 +206,7 @@ struct LinePipe {
 #pragma unroll
             for (int w = 0; w < W; ++w) {
                 va[q].v[w] = vb[q].v[w] = pa[q].v[w] = pb[q].v[w] = 0u;
+                alo[q][w] = 0u;
 #pragma unroll
                 for (int l = 0; l < NL; ++l) S[q][w][l] = Acc(0);
             }
@@ -217,11 +223,38 @@ struct LinePipe {
         cur2 += SLOT_WORDS;
         if (cur2 == ring + ap.ring * SLOT_WORDS) cur2 = ring;
     }
-    __device__ __forceinline__ V update(int q, const V& a, const V& b) {
+    static __device__ __forceinline__ uint32_t mad_lo(uint32_t a, uint32_t b, uint32_t c) {
+        uint32_t d;
+        asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+        return d;
+    }
+    // one stage update; lo[w] = low 16-bit line of the result (SPLIT only)
+    __device__ __forceinline__ V update(int q, const V& a, const V& b, uint32_t (&lo)[W]) {
         V o;
+        if constexpr (SPLIT) {
+            const uint32_t inv2 = ap.inv2, ninv2 = 0u - ap.inv2, inv2s = ap.inv2 << 16;
 #pragma unroll
-        for (int w = 0; w < W; ++w) o.v[w] = Ops::update(S[q][w], a.v[w], b.v[w], ap);
+            for (int w = 0; w < W; ++w) {
+                const uint32_t aw = a.v[w], bw = b.v[w];
+                const uint32_t bhi = bw >> 16;
+                // S_lo += inv2*a_lo - inv2*b_lo with b_lo = bw - (bhi << 16), all modulo 2^32
+                uint32_t s0 = mad_lo(alo[q][w], inv2, S[q][w][0]);
+                s0 = mad_lo(bw, ninv2, s0);
+                s0 = mad_lo(bhi, inv2s, s0);
+                const uint32_t s1 = mad_lo((aw >> 16) - bhi, inv2, S[q][w][1]);
+                S[q][w][0] = s0; S[q][w][1] = s1;
+                lo[w] = s0 >> 16;
+                o.v[w] = (s1 & 0xffff0000u) | lo[w];
+            }
+        } else {
+#pragma unroll
+            for (int w = 0; w < W; ++w) { o.v[w] = Ops::update(S[q][w], a.v[w], b.v[w], ap); lo[w] = 0u; }
+        }
         return o;
+    }
+    __device__ __forceinline__ V update(int q, const V& a, const V& b) {
+        uint32_t lo[W];
+        return update(q, a, b, lo);
     }
 
     // publish v as stage q's value of this step: exchange with the ring cell of slot(t) (already in pa[q],
@@ -229,6 +262,19 @@ struct LinePipe {
     __device__ __forceinline__ void publish(int q, const V& v) {
         vb[q] = pa[q];
         va[q] = v;
+        if constexpr (SPLIT) {
+#pragma unroll
+            for (int w = 0; w < W; ++w) alo[q][w] = v.v[w] & 0xffffu;
+        }
+        at(cur, q) = v;
+    }
+    __device__ __forceinline__ void publish(int q, const V& v, const uint32_t (&lo)[W]) {  // lo = known low lines of v
+        vb[q] = pa[q];
+        va[q] = v;
+        if constexpr (SPLIT) {
+#pragma unroll
+            for (int w = 0; w < W; ++w) alo[q][w] = lo[w];
+        }
         at(cur, q) = v;
     }
     __device__ __forceinline__ void rotate(int q) {
@@ -239,11 +285,13 @@ struct LinePipe {
     // steady state, t in [fast_begin, n).  Returns stage P's output for position t - P*D.
     __device__ __forceinline__ V step_fast(const V& v_in) {
         V nv[P];
+        uint32_t nlo[P][W];
 #pragma unroll
-        for (int q = 0; q < P; ++q) nv[q] = update(q, va[q], vb[q]);
+        for (int q = 0; q < P; ++q) nv[q] = update(q, va[q], vb[q], nlo[q]);
 #pragma unroll
         for (int q = 0; q < P; ++q) {
-            publish(q, (q == 0) ? v_in : nv[q > 0 ? q - 1 : 0]);
+            if (q == 0) publish(0, v_in);
+            else publish(q, nv[q > 0 ? q - 1 : 0], nlo[q > 0 ? q - 1 : 0]);
             rotate(q);
         }
         advance();

@@ -68,6 +68,10 @@ int bilateral_weights_exact(int lut_len);
 int run_bilateral(const FrameLayout& l, const bool mask[3], const char* src, size_t src_fs, const char* ref, size_t ref_fs,
                   char* dst, size_t dst_fs, int count, const BilateralLaunch& bp, cudaStream_t st);
 
+// pbfic_kernels.cu: Bilateral algorithm 1 on one plane of `count` frames (ref == nullptr: non-joint)
+int run_pbfic(const FrameLayout& l, int plane, const char* src, size_t src_fs, const char* ref, size_t ref_fs, char* dst, size_t dst_fs,
+              int count, const float* gr_dev, int hist_len, double sigmaS, int num, float peak, cudaStream_t st);
+
 // planestats_kernels.cu
 struct StatsRaw {  // one per (frame, processed plane), written by the kernels
     unsigned long long isum;   // integer sum of non-excluded samples / integer sum of |a-b|

@@ -270,13 +270,6 @@ vszip_filter* vszip_bilateral_create(const vszip_video_info* vi, const vszip_vid
     if (ref_vi && !compare_nodes(*vi, *ref_vi, name)) return fail();
     for (int i = 0; i < 3; ++i) f->process[i] = process[i] && i < vi->num_planes;
     f->has_ref = ref_vi != nullptr;
-    for (int i = 0; i < vi->num_planes; ++i) {
-        if (f->process[i] && f->bl[i].algorithm == 1) {
-            set_error("Bilateral: algorithm 1 (PBFIC) is selected for plane %d but only algorithm 2 has a CUDA path; "
-                      "there is no CPU fallback. Pass algorithm=2.", i);
-            return fail();
-        }
-    }
     // LUTs (src/filters/bilateral.zig:306-334), f64 math rounded to f32, uploaded to every device
     f->gs_host.resize(3); f->gr_host.resize(3);
     for (int i = 0; i < vi->num_planes; ++i) {
@@ -300,7 +293,7 @@ vszip_filter* vszip_bilateral_create(const vszip_video_info* vi, const vszip_vid
         const float tail = gr[std::min<uint32_t>(top, (uint32_t)f->hist_len - 1)];
         for (; j < (uint32_t)f->hist_len; ++j) gr[j] = tail;
         b.lut_len = (int)std::min<uint32_t>(top + 1, (uint32_t)f->hist_len);
-        b.exact = bilateral_weights_exact(b.lut_len);
+        b.exact = (b.algorithm == 1) ? 1 : bilateral_weights_exact(b.lut_len);  // PBFIC always gathers the full LUT
     }
     return f;
 }
@@ -350,6 +343,25 @@ static BilateralLaunch bilateral_launch(const vszip_filter* f, int dev_index) {
     return bp;
 }
 
+// Algorithm 2 planes go through the tiled kernel in one launch; algorithm 1 (PBFIC) planes one plane at a time.
+static int bilateral_run(const vszip_filter* f, int dev_index, const char* src, size_t sfs, const char* ref, size_t rfs, char* dst,
+                         size_t dfs, int count, cudaStream_t st) {
+    bool mask2[3] = {false, false, false}, any2 = false;
+    for (int i = 0; i < 3; ++i) { mask2[i] = f->process[i] && f->bl[i].algorithm == 2; any2 = any2 || mask2[i]; }
+    if (any2) {
+        const BilateralLaunch bp = bilateral_launch(f, dev_index);
+        const int rc = run_bilateral(f->layout, mask2, src, sfs, ref, rfs, dst, dfs, count, bp, st);
+        if (rc) return rc;
+    }
+    for (int i = 0; i < 3; ++i) {
+        if (!f->process[i] || f->bl[i].algorithm != 1) continue;
+        const int rc = run_pbfic(f->layout, i, src, sfs, ref, rfs, dst, dfs, count, f->gr_dev[dev_index][i], f->hist_len, f->bl[i].sigmaS,
+                                 (int)f->bl[i].pbfic, f->peak, st);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
 static int device_index_of(DeviceCtx* d) {
     for (int i = 0; i < num_devices(); ++i) if (device_ctx(i) == d) return i;
     return 0;
@@ -368,8 +380,7 @@ int vszip_bilateral_get_frame(const vszip_filter* f, int32_t n, const vszip_fram
     if (stage_in(s, 0, f->layout, src, f->process)) return -1;
     if (ref && stage_in(s, 1, f->layout, ref, f->process)) return -1;
     if (bilateral_upload(f, device_index_of(d))) return -1;
-    const BilateralLaunch bp = bilateral_launch(f, device_index_of(d));
-    int rc = run_bilateral(f->layout, f->process, s->dev[0], 0, ref ? s->dev[1] : nullptr, 0, s->dev[2], 0, 1, bp, s->stream);
+    int rc = bilateral_run(f, device_index_of(d), s->dev[0], 0, ref ? s->dev[1] : nullptr, 0, s->dev[2], 0, 1, s->stream);
     if (rc) return rc;
     bool direct[3];
     if (stage_out_begin(s, f->layout, dst, f->process, direct)) return -1;
@@ -392,9 +403,8 @@ int vszip_bilateral_device(const vszip_filter* f, const vszip_dev_clip* src, con
     cudaStream_t st = stream ? (cudaStream_t)stream : d->batch_stream;
     const size_t fs = src->layout.frame_stride;
     if (bilateral_upload(f, src->device_index)) return -1;
-    const BilateralLaunch bp = bilateral_launch(f, src->device_index);
-    return run_bilateral(f->layout, f->process, src->base + (size_t)first * fs, fs, ref ? ref->base + (size_t)first * fs : nullptr, fs,
-                         dst->base + (size_t)first * fs, fs, count, bp, st);
+    return bilateral_run(f, src->device_index, src->base + (size_t)first * fs, fs, ref ? ref->base + (size_t)first * fs : nullptr, fs,
+                         dst->base + (size_t)first * fs, fs, count, st);
 }
 
 // =========================================================================== PlaneMinMax
