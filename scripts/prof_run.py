@@ -1,5 +1,5 @@
 """Small driver for ncu captures: runs one filter over a device-resident noise batch a few times.
-usage: python scripts/prof_run.py boxblur|boxblur_ct|bilateral|minmax|average [frames] [reps]"""
+usage: python scripts/prof_run.py boxblur|boxblur_ct|bilateral|pbfic|minmax|average [frames] [reps]"""
 import sys
 from pathlib import Path
 
@@ -31,6 +31,9 @@ elif what == "boxblur_ct":
     run = lambda: f.run_device(src, dst)
 elif what == "bilateral":
     f = vz.BilateralFilter(src.info(), sigmaS=2, sigmaR=2)
+    run = lambda: f.run_device(src, dst)
+elif what == "pbfic":
+    f = vz.BilateralFilter(src.info(), sigmaS=8, sigmaR=0.1, planes=[0])
     run = lambda: f.run_device(src, dst)
 elif what == "minmax":
     f = vz.PlaneMinMaxFilter(src.info(), minthr=0.1, maxthr=0.1)

@@ -9,10 +9,10 @@
 // Design: levels are processed one after the other so only four f32 images per plane live in HBM (W, J and a
 // ping-pong pair of level images), whatever `num` is; a batch is cut into chunks of frames so that scratch stays
 // bounded.  Per level and chunk two launches:
-//   pbfic_h_kernel  one warp owns 32 rows and walks them in 32-column tiles: the tile of src/ref is loaded
+//   pbfic_h_kernel  one warp owns 16 rows and walks them in 32-column tiles: the tile of src/ref is loaded
 //                   coalesced, turned into W/J on the fly (range LUT gathered from L2), transposed through shared
-//                   memory (pitch 33: conflict-free both ways) so that lane = row for the recursion, and written
-//                   back coalesced; then the same walk right-to-left over the forward result.
+//                   memory (odd pitch: conflict-free both ways) so that lane = (image, row) for the recursion, and
+//                   written back coalesced; then the same walk right-to-left over the forward result.
 //   pbfic_v_kernel  one thread owns one column (coalesced by construction), forward then backward; the backward
 //                   sweep emits the level image and, for samples bracketed by (level-1, level), the output.
 // Bound: HBM/L2 traffic of the f32 intermediates (~60 B per sample and level) and the dependent 7-flop tap chains.
@@ -74,87 +74,120 @@ __device__ __forceinline__ float tap(const PbficJob& j, float x, float p1, float
 }
 
 // --------------------------------------------------------------------------- rows (build + forward + backward)
+// One warp owns HR = 16 rows: lanes 0-15 run the W recursions of those rows, lanes 16-31 the J recursions, so a warp
+// carries 32 independent chains while the grid has twice the warps of a 32-row layout (the kernel is latency-bound).
+// The global loads of the next tile are issued before the current tile's recursion and parked in registers.
 template <typename T>
 __global__ void __launch_bounds__(32) pbfic_h_kernel(const PbficJob j) {
-    constexpr int TP = 33;
-    __shared__ float tw[32 * TP], tj[32 * TP];
-    const int lane = threadIdx.x;
-    const int row0 = blockIdx.x * 32, frame = blockIdx.y;
-    const int nrows = min(32, j.h - row0);
+    constexpr int HR = 16, TP = HR + 1;
+    __shared__ float tile[2 * 32 * TP + 16];
+    float* tw = tile;
+    float* tj = tile + 32 * TP + 16;  // +16 floats: the two half-warps then read disjoint banks
+    const int lane = threadIdx.x, half = lane >> 4, r = lane & 15;
+    float* mine = half ? tj : tw;
+    const int row0 = blockIdx.x * HR, frame = blockIdx.y;
+    const int nrows = min(HR, j.h - row0);
     const char* src = j.src + (size_t)frame * j.src_fs + (size_t)row0 * j.src_pitch;
     const char* ref = j.ref + (size_t)frame * j.ref_fs + (size_t)row0 * j.ref_pitch;
     float* W = j.W + (size_t)frame * j.img_fs + (size_t)row0 * j.fpitch;
     float* J = j.J + (size_t)frame * j.img_fs + (size_t)row0 * j.fpitch;
     const int nch = (j.w + 31) / 32;
-    float w1 = 0.f, w2 = 0.f, w3 = 0.f, j1 = 0.f, j2 = 0.f, j3 = 0.f;
+    float p1 = 0.f, p2 = 0.f, p3 = 0.f;
+    float pa[HR], pb[HR];  // prefetched tile: (src, ref) going forward, (W, J) going backward
+
+    auto fetch_fwd = [&](int c) {
+        const int x = c * 32 + lane;
+        if (c < nch && x < j.w) {
+#pragma unroll
+            for (int rr = 0; rr < HR; ++rr) {
+                if (rr < nrows) {
+                    pa[rr] = to_f32<T>(reinterpret_cast<const T*>(src + (size_t)rr * j.src_pitch)[x]);
+                    pb[rr] = to_f32<T>(reinterpret_cast<const T*>(ref + (size_t)rr * j.ref_pitch)[x]);
+                }
+            }
+        }
+    };
+    auto fetch_bwd = [&](int c) {
+        const int x = c * 32 + lane;
+        if (c >= 0 && x < j.w) {
+#pragma unroll
+            for (int rr = 0; rr < HR; ++rr) {
+                if (rr < nrows) { pa[rr] = W[(size_t)rr * j.fpitch + x]; pb[rr] = J[(size_t)rr * j.fpitch + x]; }
+            }
+        }
+    };
+    auto store_tile = [&](int x0, int ncols) {
+        if (lane < ncols) {
+#pragma unroll
+            for (int rr = 0; rr < HR; ++rr) {
+                if (rr < nrows) {
+                    W[(size_t)rr * j.fpitch + x0 + lane] = tw[lane * TP + rr];
+                    J[(size_t)rr * j.fpitch + x0 + lane] = tj[lane * TP + rr];
+                }
+            }
+        }
+    };
 
     // ---- forward, W/J built on the fly (src/filters/bilateral.zig:131-140, 396-414)
+    fetch_fwd(0);
     for (int c = 0; c < nch; ++c) {
         const int x0 = c * 32, ncols = min(32, j.w - x0);
         if (lane < ncols) {
-#pragma unroll 8
-            for (int rr = 0; rr < nrows; ++rr) {
-                const float s = to_f32<T>(reinterpret_cast<const T*>(src + (size_t)rr * j.src_pitch)[x0 + lane]);
-                const float r = to_f32<T>(reinterpret_cast<const T*>(ref + (size_t)rr * j.ref_pitch)[x0 + lane]);
-                const float wv = __ldg(j.gr + min(range_index<T>(j.pk_f, r), j.gr_top));
-                tw[lane * TP + rr] = wv;
-                tj[lane * TP + rr] = __fmul_rn(wv, s);
+#pragma unroll
+            for (int rr = 0; rr < HR; ++rr) {
+                if (rr < nrows) {
+                    const float wv = __ldg(j.gr + min(range_index<T>(j.pk_f, pb[rr]), j.gr_top));
+                    tw[lane * TP + rr] = wv;
+                    tj[lane * TP + rr] = __fmul_rn(wv, pa[rr]);
+                }
             }
         }
+        fetch_fwd(c + 1);
         __syncwarp();
-        if (lane < nrows) {
+        if (r < nrows) {
+#pragma unroll 4
             for (int i = 0; i < ncols; ++i) {
-                const float xw = tw[i * TP + lane], xj = tj[i * TP + lane];
+                const float x = mine[i * TP + r];
                 if (x0 + i == 0) {  // the first sample passes through and seeds the history
-                    w1 = w2 = w3 = xw; j1 = j2 = j3 = xj;
+                    p1 = p2 = p3 = x;
                 } else {
-                    const float pw = tap(j, xw, w1, w2, w3), pj = tap(j, xj, j1, j2, j3);
-                    w3 = w2; w2 = w1; w1 = pw; j3 = j2; j2 = j1; j1 = pj;
-                    tw[i * TP + lane] = pw; tj[i * TP + lane] = pj;
+                    const float p0 = tap(j, x, p1, p2, p3);
+                    p3 = p2; p2 = p1; p1 = p0;
+                    mine[i * TP + r] = p0;
                 }
             }
         }
         __syncwarp();
-        if (lane < ncols) {
-#pragma unroll 8
-            for (int rr = 0; rr < nrows; ++rr) {
-                W[(size_t)rr * j.fpitch + x0 + lane] = tw[lane * TP + rr];
-                J[(size_t)rr * j.fpitch + x0 + lane] = tj[lane * TP + rr];
-            }
-        }
+        store_tile(x0, ncols);
         __syncwarp();
     }
     // ---- backward over the forward result (:416-430); every lane re-reads only what it stored itself
+    fetch_bwd(nch - 1);
     for (int c = nch - 1; c >= 0; --c) {
         const int x0 = c * 32, ncols = min(32, j.w - x0);
         if (lane < ncols) {
-#pragma unroll 8
-            for (int rr = 0; rr < nrows; ++rr) {
-                tw[lane * TP + rr] = W[(size_t)rr * j.fpitch + x0 + lane];
-                tj[lane * TP + rr] = J[(size_t)rr * j.fpitch + x0 + lane];
+#pragma unroll
+            for (int rr = 0; rr < HR; ++rr) {
+                if (rr < nrows) { tw[lane * TP + rr] = pa[rr]; tj[lane * TP + rr] = pb[rr]; }
             }
         }
+        fetch_bwd(c - 1);
         __syncwarp();
-        if (lane < nrows) {
+        if (r < nrows) {
+#pragma unroll 4
             for (int i = ncols - 1; i >= 0; --i) {
-                const float xw = tw[i * TP + lane], xj = tj[i * TP + lane];
+                const float x = mine[i * TP + r];
                 if (x0 + i == j.w - 1) {  // the last sample keeps its forward value and seeds the history
-                    w1 = w2 = w3 = xw; j1 = j2 = j3 = xj;
+                    p1 = p2 = p3 = x;
                 } else {
-                    const float pw = tap(j, xw, w1, w2, w3), pj = tap(j, xj, j1, j2, j3);
-                    w3 = w2; w2 = w1; w1 = pw; j3 = j2; j2 = j1; j1 = pj;
-                    tw[i * TP + lane] = pw; tj[i * TP + lane] = pj;
+                    const float p0 = tap(j, x, p1, p2, p3);
+                    p3 = p2; p2 = p1; p1 = p0;
+                    mine[i * TP + r] = p0;
                 }
             }
         }
         __syncwarp();
-        if (lane < ncols) {
-#pragma unroll 8
-            for (int rr = 0; rr < nrows; ++rr) {
-                W[(size_t)rr * j.fpitch + x0 + lane] = tw[lane * TP + rr];
-                J[(size_t)rr * j.fpitch + x0 + lane] = tj[lane * TP + rr];
-            }
-        }
+        store_tile(x0, ncols);
         __syncwarp();
     }
 }
@@ -209,45 +242,49 @@ __global__ void __launch_bounds__(128) pbfic_v_kernel(const PbficJob j) {
     }
 
     // ---- backward (:375-393) fused with the level image (:146-151) and the interpolation (:154-169)
-    const bool last_level = (j.level == j.num - 1);
-    auto emit = [&](int yy, float wv, float jv) {
+    const bool last_level = (j.level == j.num - 1), interp = (j.level >= 1);
+    // rf / lo are fetched by the caller together with the row's W/J so that no load sits inside the dependent chain
+    auto emit = [&](int yy, float wv, float jv, float rf, float lo) {
         const float L = (wv == 0.0f) ? 0.0f : __fdiv_rn(jv, wv);
         if (!last_level) Lc[(size_t)yy * fp] = L;
-        if (j.level >= 1) {
-            const float rf = to_f32<T>(*reinterpret_cast<const T*>(ref + (size_t)yy * j.ref_pitch));
+        if (interp) {
             // bracket index k = level-1: the first k < num-2 with pk[k] <= ref < pk[k+1], else num-2
             bool mine = (rf >= j.lo_f) && (rf < j.pk_f);
             if (last_level) mine = !((rf >= j.first_f) && (rf < j.last2_f));
             if (mine) {
-                const float lo = Lp[(size_t)yy * fp];
                 const float t0 = __fmul_rn(__fsub_rn(j.pk_f, rf), lo), t1 = __fmul_rn(__fsub_rn(rf, j.lo_f), L);
                 const float vf = __fdiv_rn(__fadd_rn(t0, t1), __fsub_rn(j.pk_f, j.lo_f));
                 *reinterpret_cast<T*>(dst + (size_t)yy * j.dst_pitch) = finalize<T>(vf, j.peak);
             }
         }
     };
+    auto ld_ref = [&](int yy) { return interp ? to_f32<T>(*reinterpret_cast<const T*>(ref + (size_t)yy * j.ref_pitch)) : 0.0f; };
+    auto ld_lo = [&](int yy) { return interp ? Lp[(size_t)yy * fp] : 0.0f; };
     {
         const float xw = w1, xj = j1;  // forward value of row h-1 (still in registers), filtered against itself
         const float pw = tap(j, xw, xw, xw, xw), pj = tap(j, xj, xj, xj, xj);
         w1 = w2 = w3 = pw; j1 = j2 = j3 = pj;
-        emit(h - 1, pw, pj);
+        emit(h - 1, pw, pj, ld_ref(h - 1), ld_lo(h - 1));
     }
     y = h - 2;
     for (; y - (U - 1) >= 0; y -= U) {
-        float xw[U], xj[U];
+        float xw[U], xj[U], rf[U], lo[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) { xw[u] = W[(size_t)(y - u) * fp]; xj[u] = J[(size_t)(y - u) * fp]; }
+        for (int u = 0; u < U; ++u) {
+            xw[u] = W[(size_t)(y - u) * fp]; xj[u] = J[(size_t)(y - u) * fp];
+            rf[u] = ld_ref(y - u); lo[u] = ld_lo(y - u);
+        }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const float pw = tap(j, xw[u], w1, w2, w3), pj = tap(j, xj[u], j1, j2, j3);
             w3 = w2; w2 = w1; w1 = pw; j3 = j2; j2 = j1; j1 = pj;
-            emit(y - u, pw, pj);
+            emit(y - u, pw, pj, rf[u], lo[u]);
         }
     }
     for (; y >= 0; --y) {
         const float pw = tap(j, W[(size_t)y * fp], w1, w2, w3), pj = tap(j, J[(size_t)y * fp], j1, j2, j3);
         w3 = w2; w2 = w1; w1 = pw; j3 = j2; j2 = j1; j1 = pj;
-        emit(y, pw, pj);
+        emit(y, pw, pj, ld_ref(y), ld_lo(y));
     }
 }
 
@@ -308,7 +345,7 @@ static int launch_pbfic_t(PbficJob j, int count, const std::vector<float>& pk, c
             j.pk_f = pk[k];
             j.lo_f = k ? pk[k - 1] : 0.0f;
             j.Lcur = L[k & 1]; j.Lprev = L[(k & 1) ^ 1];
-            pbfic_h_kernel<T><<<dim3((j.h + 31) / 32, nf), 32, 0, st>>>(j);
+            pbfic_h_kernel<T><<<dim3((j.h + 15) / 16, nf), 32, 0, st>>>(j);
             pbfic_v_kernel<T><<<dim3((j.w + 127) / 128, nf), 128, 0, st>>>(j);
             count_launch(2);
         }
