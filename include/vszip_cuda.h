@@ -198,6 +198,24 @@ int vszip_planeaverage_device(const vszip_filter* f, const vszip_dev_clip* clipa
                               int32_t first, int32_t count, vszip_average_props* out, void* stream);
 int vszip_cuda_stream_sync(int32_t device, void* stream);
 
+/* ------------------------------------------------------------------ fused chains of vszip filters
+ * A linear chain A -> B -> C of single-input vszip filters evaluated for one frame with ONE upload and ONE download:
+ * intermediates stay in HBM.  Meant for the Zig glue of a filter whose input node is itself a vszip CUDA filter
+ * (a create-time registry node -> vszip_filter makes that visible): its getFrame requests the
+ * chain's SOURCE frame instead of its immediate input and calls this.  Results are identical to calling the
+ * per-filter get_frame functions one after the other.
+ *  - filters: 1..16 handles in evaluation order, all created for the same video format and without ref/clipb;
+ *    the chain borrows them (they must outlive it).
+ *  - props_out[i]: for a PlaneMinMax / PlaneAverage element a pointer to its vszip_minmax_props /
+ *    vszip_average_props (required), for pixel filters ignored (may be NULL).
+ *  - dst: receives the planes reported by vszip_chain_planes (the union of the planes the pixel filters process);
+ *    the remaining planes equal the source's.  May be NULL when the chain holds no pixel filter. */
+typedef struct vszip_chain vszip_chain;
+vszip_chain* vszip_chain_create(const vszip_filter* const* filters, int32_t count);
+void vszip_chain_free(vszip_chain* c);
+int vszip_chain_planes(const vszip_chain* c, int32_t written[3]);
+int vszip_chain_get_frame(const vszip_chain* c, int32_t n, const vszip_frame* src, vszip_frame* dst, void* const* props_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -5,7 +5,7 @@ import pytest
 
 import oracle_api as oa
 import vapoursynth_zip_b200 as vz
-from helpers import assert_same_planes
+from helpers import assert_same_planes, noise_clip, to_node
 
 pytestmark = pytest.mark.gpu
 
@@ -36,3 +36,53 @@ def test_chain_device_resident(fmt, w, h):
         # the reduction is exact on whatever frame it is given: check it on the GPU's own bilateral output
         want_mm = oa.planeminmax({"format": fmt, "planes": got_bil}, minthr=0.1, maxthr=0.1, planes=[0])
         assert props[i] == want_mm, (props[i], want_mm)
+
+
+# --------------------------------------------------------------------------- fused get_frame chains (vszip_chain_*)
+def _chain_case(fmt, w, h, build):
+    clip = noise_clip(fmt, w, h, seed=71)
+    node = build(to_node(clip))
+    vz.core.fuse_chains = True
+    try:
+        fused = node.get_frame(0)
+        assert getattr(node, "_chain", None) is not None, "the chain was not fused"
+    finally:
+        vz.core.fuse_chains = False
+    try:
+        plain = build(to_node(clip)).get_frame(0)   # one upload/download per filter
+    finally:
+        vz.core.fuse_chains = True
+    assert_same_planes(fused.planes, plain.planes, f"fused chain {fmt}")
+    assert fused.props == plain.props, (fused.props, plain.props)
+    return fused
+
+
+def test_fused_chain_config5_shape():
+    """BASELINE config 5's chain through the frame API: BoxBlur -> Bilateral -> PlaneMinMax, one PCIe round trip."""
+    f = _chain_case("YUV444PS", 320, 180, lambda c: c.vszip.BoxBlur(hradius=13, vradius=13).vszip.Bilateral(sigmaS=2, sigmaR=2)
+                    .vszip.PlaneMinMax(minthr=0.1, maxthr=0.1, planes=[0]))
+    assert "psmMin" in f.props and "psmMax" in f.props
+
+
+def test_fused_chain_partial_planes_and_stats_in_the_middle():
+    def build(c):
+        c = c.vszip.BoxBlur(planes=[0], hradius=3, hpasses=2, vradius=0, vpasses=0)
+        c = c.vszip.PlaneAverage(exclude=[0, 7], planes=[0, 1, 2], prop="a")
+        c = c.vszip.Bilateral(sigmaS=1.5, sigmaR=0.02, planes=[1, 2])
+        c = c.vszip.PlaneMinMax(minthr=0.05, maxthr=0.2, planes=[0, 2], prop="b")
+        return c.vszip.BoxBlur(planes=[2], hradius=0, hpasses=0, vradius=5, vpasses=3)
+    f = _chain_case("YUV420P16", 322, 182, build)
+    assert isinstance(f.props["aAvg"], list) and len(f.props["bMin"]) == 2
+
+
+def test_fused_chain_stats_only_and_pbfic():
+    _chain_case("GRAY16", 200, 120, lambda c: c.vszip.PlaneMinMax(minthr=0.1).vszip.PlaneAverage(exclude=[5]))
+    _chain_case("GRAY16", 200, 120, lambda c: c.vszip.Bilateral(sigmaS=3, sigmaR=0.1, algorithm=1).vszip.BoxBlur(hradius=2, vradius=2))
+
+
+def test_chain_rejects_second_clips():
+    a = to_node(noise_clip("GRAY8", 64, 48, seed=1))
+    b = to_node(noise_clip("GRAY8", 64, 48, seed=2))
+    n = a.vszip.BoxBlur().vszip.PlaneMinMax(clipb=b)
+    out = n.get_frame(0)                      # evaluated unfused: the second clip keeps it out of a chain
+    assert getattr(n, "_chain", None) is None and "psmDiff" in out.props

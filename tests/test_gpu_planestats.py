@@ -126,6 +126,21 @@ def test_blank_clips_and_prop_rename():
     assert multi == [6777 / 65535, 32768 / 65535, 0.0]
 
 
+def test_long_exclude_lists():
+    """Lists beyond the 16 entries carried in the kernel arguments (the reference takes any length)."""
+    rng = np.random.default_rng(5)
+    for fmt in ("GRAY8", "GRAY16", "GRAYS"):
+        clip = noise_clip(fmt, 317, 143, seed=41)
+        other = noise_clip(fmt, 317, 143, seed=42)
+        if fmt == "GRAYS":  # float clips compare against f32(int): make some samples hit
+            clip["planes"][0][::3, ::2] = 1.0
+            clip["planes"][0][1::5, 1::4] = 0.0
+        for n in (17, 40, 200):
+            ex = [int(v) for v in rng.integers(0, 256 if fmt != "GRAY16" else 65536, n)] + [0, 1]
+            props_close(av(clip, exclude=ex), oa.planeaverage(clip, ex))
+            props_close(av(clip, other, exclude=ex), oa.planeaverage(clip, ex, clipb=other))
+
+
 def test_exclude_exact():
     """tests/test_planeaverage.py:118-128 of the reference."""
     two = np.vstack([np.full((32, 64), 1000, np.uint16), np.full((32, 64), 3000, np.uint16)])

@@ -108,6 +108,10 @@ ABI = {
     "vszip_dev_clip_fill_noise": (C.c_int, [_P, C.c_uint64, C.c_int32, C.c_int32]),
     "vszip_dev_clip_frame_bytes": (C.c_size_t, [_P]),
     "vszip_dev_clip_plane_ptr": (_P, [_P, C.c_int32, C.c_int32, C.POINTER(C.c_ssize_t)]),
+    "vszip_chain_create": (_P, [C.POINTER(_P), C.c_int32]),
+    "vszip_chain_free": (None, [_P]),
+    "vszip_chain_planes": (C.c_int, [_P, C.POINTER(C.c_int32 * 3)]),
+    "vszip_chain_get_frame": (C.c_int, [_P, C.c_int32, C.POINTER(_Frame), C.POINTER(_Frame), C.POINTER(_P)]),
 }
 
 _lib = None
@@ -228,6 +232,9 @@ class VideoNode:
     def get_frame(self, n: int) -> VideoFrame:
         if not 0 <= n < self.num_frames:
             raise Error(f"frame {n} out of range")
+        chain = _fusable_chain(self) if core.fuse_chains else None
+        if chain is not None:
+            return _fused_get(chain, n)
         return self._getter(n)
 
     @property
@@ -410,7 +417,7 @@ class _Namespace:
             out = _MinMaxProps()
             _check(load_library().vszip_planeminmax_get_frame(flt.handle, n, C.byref(a), C.byref(b) if b is not None else None, C.byref(out)))
             return PlaneMinMaxFilter.to_props(out, prefix)
-        return _props_node(clipa, clipb, flt, run, [prefix + k for k in ("Diff", "Max", "Min")])
+        return _props_node(clipa, clipb, flt, run, [prefix + k for k in ("Diff", "Max", "Min")], lambda o: PlaneMinMaxFilter.to_props(o, prefix))
 
     def PlaneAverage(self, clipa=None, exclude=None, clipb=None, planes=None, prop=None) -> VideoNode:
         clipa = self._c(clipa)
@@ -421,7 +428,7 @@ class _Namespace:
             out = _AverageProps()
             _check(load_library().vszip_planeaverage_get_frame(flt.handle, n, C.byref(a), C.byref(b) if b is not None else None, C.byref(out)))
             return PlaneAverageFilter.to_props(out, prefix)
-        return _props_node(clipa, clipb, flt, run, [prefix + k for k in ("Diff", "Avg")])
+        return _props_node(clipa, clipb, flt, run, [prefix + k for k in ("Diff", "Avg")], lambda o: PlaneAverageFilter.to_props(o, prefix))
 
 
 def _second_frame(second: VideoNode | None, n: int):
@@ -448,10 +455,11 @@ def _pixel_node(clip: VideoNode, ref: VideoNode | None, flt: _Filter, call) -> V
 
     node = VideoNode(fmt, clip.width, clip.height, clip.num_frames, get)
     node.filter = flt
+    node._chain_info = ("pixel", clip, ref, None)
     return node
 
 
-def _props_node(clipa: VideoNode, clipb: VideoNode | None, flt: _Filter, run, drop_keys) -> VideoNode:
+def _props_node(clipa: VideoNode, clipb: VideoNode | None, flt: _Filter, run, drop_keys, run_fused=None) -> VideoNode:
     def get(n):
         core._ensure_init()
         src = clipa.get_frame(n)
@@ -467,7 +475,68 @@ def _props_node(clipa: VideoNode, clipb: VideoNode | None, flt: _Filter, run, dr
 
     node = VideoNode(clipa.format, clipa.width, clipa.height, clipa.num_frames, get)
     node.filter = flt
+    node._chain_info = ("props", clipa, clipb, (run_fused, drop_keys))
     return node
+
+
+# ---- fused evaluation of linear chains of vszip nodes (vszip_chain_*): one upload, one download
+class _Chain:
+    def __init__(self, nodes):
+        self.nodes = nodes  # evaluation order
+        handles = (_P * len(nodes))(*[nd.filter.handle for nd in nodes])
+        self.handle = load_library().vszip_chain_create(handles, len(nodes))
+        if not self.handle:
+            raise Error(_last_error())
+        w = (C.c_int32 * 3)()
+        _check(load_library().vszip_chain_planes(self.handle, C.byref(w)))
+        self.written = [bool(v) for v in w]
+
+    def __del__(self):
+        try:
+            if self.handle and _lib is not None:
+                _lib.vszip_chain_free(self.handle)
+        except Exception:
+            pass
+        self.handle = None
+
+
+def _fusable_chain(node: "VideoNode"):
+    """The chain ending in `node` if it and at least one predecessor are single-input vszip nodes."""
+    cached = getattr(node, "_chain", False)
+    if cached is not False:
+        return cached
+    nodes, cur = [], node
+    while getattr(cur, "_chain_info", None) is not None and cur._chain_info[2] is None and len(nodes) < 16:
+        nodes.append(cur)
+        cur = cur._chain_info[1]
+    node._chain = (_Chain(nodes[::-1]), cur) if len(nodes) >= 2 else None
+    return node._chain
+
+
+def _fused_get(chain_and_source, n: int) -> "VideoFrame":
+    chain, source = chain_and_source
+    core._ensure_init()
+    src = source.get_frame(n)
+    out_planes = [np.empty_like(p, order="C") if chain.written[i] else p for i, p in enumerate(src.planes)]
+    s = _cframe([_rows(p) for p in src.planes])
+    d = _cframe([p if chain.written[i] else None for i, p in enumerate(out_planes)])
+    outs, ptrs = [], (_P * len(chain.nodes))()
+    for i, nd in enumerate(chain.nodes):
+        kind = nd._chain_info[0]
+        o = None
+        if kind == "props":
+            o = _MinMaxProps() if isinstance(nd.filter, PlaneMinMaxFilter) else _AverageProps()
+            ptrs[i] = C.cast(C.pointer(o), _P)
+        outs.append(o)
+    _check(load_library().vszip_chain_get_frame(chain.handle, n, C.byref(s), C.byref(d), ptrs))
+    props = dict(src.props)
+    for nd, o in zip(chain.nodes, outs):
+        if o is not None:
+            to_props, drop_keys = nd._chain_info[3]
+            for k in drop_keys:
+                props.pop(k, None)
+            props.update(to_props(o))
+    return VideoFrame(source.format, source.width, source.height, out_planes, props)
 
 
 # --------------------------------------------------------------------------- device-resident clips
@@ -521,6 +590,8 @@ class DeviceClip:
 class _Core:
     def __init__(self):
         self._ready = False
+        # evaluate linear chains of single-input vszip nodes with one upload and one download (vszip_chain_*)
+        self.fuse_chains = os.environ.get("VSZIP_FUSE_CHAINS", "1") != "0"
 
     def init(self, devices=None) -> int:
         """vszip_cuda_init: `devices` = list of CUDA ordinals (default: all visible, or $VSZIP_CUDA_DEVICES)."""

@@ -47,6 +47,8 @@ struct vszip_filter {
     // PlaneAverage (src/vapoursynth/planeaverage.zig:14-22)
     std::vector<int32_t> exclude_i;
     std::vector<float> exclude_f;
+    std::vector<int32_t*> exclude_i_dev;  // [device] copies of lists longer than 16 entries (lazy, guarded by lut_mu)
+    std::vector<float*> exclude_f_dev;
     float avg_peak;
 };
 
@@ -86,6 +88,7 @@ size_t stats_scratch_bytes(int count, int nplanes);
 int run_planeminmax(const FrameLayout& l, const bool mask[3], const char* a, size_t a_fs, const char* b, size_t b_fs, int count,
                     bool no_thr, float minthr, float maxthr, uint32_t hist_size, void* scratch, StatsRaw* out_dev, cudaStream_t st);
 int run_planeaverage(const FrameLayout& l, const bool mask[3], const char* a, size_t a_fs, const char* b, size_t b_fs, int count,
-                     const int32_t* excl_i, const float* excl_f, int nex, void* scratch, StatsRaw* out_dev, cudaStream_t st);
+                     const int32_t* excl_i, const float* excl_f, int nex, const int32_t* excl_i_dev, const float* excl_f_dev, void* scratch,
+                     StatsRaw* out_dev, cudaStream_t st);
 
 }  // namespace vsz

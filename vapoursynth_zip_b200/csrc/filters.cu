@@ -117,6 +117,12 @@ void vszip_filter_free(vszip_filter* f) {
         for (float* p : f->gr_dev[d]) if (p) cudaFree(p);
         for (float* p : f->gs_dev[d]) if (p) cudaFree(p);
     }
+    for (size_t d = 0; d < f->exclude_i_dev.size(); ++d) {
+        DeviceCtx* ctx = device_ctx((int)d);
+        if (ctx) cudaSetDevice(ctx->ordinal);
+        if (f->exclude_i_dev[d]) cudaFree(f->exclude_i_dev[d]);
+        if (f->exclude_f_dev[d]) cudaFree(f->exclude_f_dev[d]);
+    }
     delete f;
 }
 
@@ -552,8 +558,26 @@ vszip_filter* vszip_planeaverage_create(const vszip_video_info* vi, const vszip_
         f->exclude_f.push_back((float)a->exclude[i]);           // planeaverage.zig:122-125
         f->exclude_i.push_back(sat_i32(a->exclude[i]));         // math.lossyCast(i32, ..)
     }
-    if (a->num_exclude > 16) { set_error("PlaneAverage: more than 16 exclude values are not supported by the CUDA path"); delete f; return nullptr; }
     return f;
+}
+
+// Exclude lists longer than the 16 entries that travel in the kernel arguments are uploaded to a device the first
+// time the instance runs there.
+static int average_upload(const vszip_filter* cf, int dev_index, const int32_t** xi, const float** xf) {
+    *xi = nullptr; *xf = nullptr;
+    if (cf->exclude_i.size() <= 16) return 0;
+    vszip_filter* f = const_cast<vszip_filter*>(cf);
+    std::lock_guard<std::mutex> lk(f->lut_mu);
+    if (f->exclude_i_dev.size() < (size_t)num_devices()) { f->exclude_i_dev.resize(num_devices(), nullptr); f->exclude_f_dev.resize(num_devices(), nullptr); }
+    if (!f->exclude_i_dev[dev_index]) {
+        const size_t n = f->exclude_i.size();
+        VSZ_CUDA(cudaMalloc((void**)&f->exclude_i_dev[dev_index], n * sizeof(int32_t)));
+        VSZ_CUDA(cudaMalloc((void**)&f->exclude_f_dev[dev_index], n * sizeof(float)));
+        VSZ_CUDA(cudaMemcpy(f->exclude_i_dev[dev_index], f->exclude_i.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice));
+        VSZ_CUDA(cudaMemcpy(f->exclude_f_dev[dev_index], f->exclude_f.data(), n * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    *xi = f->exclude_i_dev[dev_index]; *xf = f->exclude_f_dev[dev_index];
+    return 0;
 }
 
 static void average_finalize(const vszip_filter* f, const StatsRaw* raw, vszip_average_props* out) {
@@ -592,8 +616,10 @@ int vszip_planeaverage_get_frame(const vszip_filter* f, int32_t n, const vszip_f
     if (stage_in(s, 0, f->layout, a, f->process)) return -1;
     if (b && stage_in(s, 1, f->layout, b, f->process)) return -1;
     StatsRaw* raw_dev = (StatsRaw*)s->dev_small;
+    const int32_t* xi; const float* xf;
+    if (average_upload(f, device_index_of(d), &xi, &xf)) return -1;
     int rc = run_planeaverage(f->layout, f->process, s->dev[0], 0, b ? s->dev[1] : nullptr, 0, 1, f->exclude_i.data(), f->exclude_f.data(),
-                              (int)f->exclude_i.size(), s->dev[2], raw_dev, s->stream);
+                              (int)f->exclude_i.size(), xi, xf, s->dev[2], raw_dev, s->stream);
     if (rc) return rc;
     VSZ_CUDA(cudaMemcpyAsync(s->pin_small, raw_dev, sizeof(StatsRaw) * np, cudaMemcpyDeviceToHost, s->stream));
     VSZ_CUDA(cudaStreamSynchronize(s->stream));
@@ -618,8 +644,10 @@ int vszip_planeaverage_device(const vszip_filter* f, const vszip_dev_clip* a, co
     const size_t sb = stats_scratch_bytes(count, np), rb = sizeof(StatsRaw) * (size_t)count * np;
     VSZ_CUDA(cudaMallocAsync((void**)&scratch, sb + rb, st));
     StatsRaw* raw_dev = (StatsRaw*)(scratch + sb);
+    const int32_t* xi; const float* xf;
+    if (average_upload(f, a->device_index, &xi, &xf)) return -1;
     int rc = run_planeaverage(f->layout, f->process, a->base + (size_t)first * fs, fs, b ? b->base + (size_t)first * fs : nullptr, fs, count,
-                              f->exclude_i.data(), f->exclude_f.data(), (int)f->exclude_i.size(), scratch, raw_dev, st);
+                              f->exclude_i.data(), f->exclude_f.data(), (int)f->exclude_i.size(), xi, xf, scratch, raw_dev, st);
     std::vector<StatsRaw> raw((size_t)count * np);
     if (!rc && out) {
         VSZ_CUDA(cudaMemcpyAsync(raw.data(), raw_dev, rb, cudaMemcpyDeviceToHost, st));
@@ -628,6 +656,132 @@ int vszip_planeaverage_device(const vszip_filter* f, const vszip_dev_clip* a, co
     }
     VSZ_CUDA(cudaFreeAsync(scratch, st));
     return rc;
+}
+
+// =========================================================================== fused chains
+struct vszip_chain {
+    std::vector<const vszip_filter*> fl;
+    vsz::FrameLayout layout;
+    bool written[3];
+    int npixel;
+};
+
+vszip_chain* vszip_chain_create(const vszip_filter* const* filters, int32_t count) {
+    if (!filters || count < 1 || count > 16) { set_error("chain: between 1 and 16 filters are required"); return nullptr; }
+    const vszip_filter* f0 = filters[0];
+    for (int i = 0; i < count; ++i) {
+        const vszip_filter* f = filters[i];
+        if (!f) { set_error("chain: filter %d is NULL", i); return nullptr; }
+        if (f->has_ref) { set_error("chain: filter %d takes a second clip (ref/clipb); only single-input filters can be fused", i); return nullptr; }
+        const vszip_video_info &a = f0->vi, &b = f->vi;
+        if (a.width != b.width || a.height != b.height || a.color_family != b.color_family || a.sample_type != b.sample_type ||
+            a.bits_per_sample != b.bits_per_sample || a.sub_sampling_w != b.sub_sampling_w || a.sub_sampling_h != b.sub_sampling_h ||
+            a.num_planes != b.num_planes) {
+            set_error("chain: filter %d was created for a different video format than filter 0", i);
+            return nullptr;
+        }
+    }
+    vszip_chain* c = new vszip_chain();
+    c->fl.assign(filters, filters + count);
+    c->layout = f0->layout;
+    c->npixel = 0;
+    for (int p = 0; p < 3; ++p) c->written[p] = false;
+    for (const vszip_filter* f : c->fl) {
+        if (f->kind == F_BOXBLUR || f->kind == F_BILATERAL) {
+            ++c->npixel;
+            for (int p = 0; p < 3; ++p) c->written[p] = c->written[p] || f->process[p];
+        }
+    }
+    return c;
+}
+
+void vszip_chain_free(vszip_chain* c) { delete c; }
+
+int vszip_chain_planes(const vszip_chain* c, int32_t written[3]) {
+    if (!c) { set_error("chain: bad handle"); return -1; }
+    for (int p = 0; p < 3; ++p) written[p] = c->written[p] ? 1 : 0;
+    return 0;
+}
+
+int vszip_chain_get_frame(const vszip_chain* c, int32_t n, const vszip_frame* src, vszip_frame* dst, void* const* props_out) {
+    if (!c) { set_error("chain: bad handle"); return -1; }
+    if (c->npixel > 0 && !dst) { set_error("chain: dst is required when the chain holds a pixel filter"); return -1; }
+    DeviceCtx* d = route(n, "chain");
+    if (!d) return -1;
+    SlotGuard g(d);
+    Slot* s = g.s;
+    VSZ_CUDA(cudaSetDevice(d->ordinal));
+    const FrameLayout& l = c->layout;
+    const size_t bytes = l.frame_stride;
+    if (slot_reserve(d, s, 0, bytes) || slot_reserve(d, s, 2, bytes) || (c->npixel > 1 && slot_reserve(d, s, 1, bytes))) return -1;
+    bool all[3] = {l.nplanes > 0, l.nplanes > 1, l.nplanes > 2};
+    if (stage_in(s, 0, l, src, all)) return -1;  // later filters may read planes that earlier ones do not process
+    const int dev_index = device_index_of(d);
+    int cur = 0, pixel_seen = 0, stats_seen = 0;
+    char* stats_scratch = nullptr;
+    for (size_t i = 0; i < c->fl.size(); ++i) {
+        const vszip_filter* f = c->fl[i];
+        if (f->kind == F_BOXBLUR || f->kind == F_BILATERAL) {
+            // the last pixel filter must land in dev[2] (the D2H source), the ones before alternate 1 / 2
+            const int nxt = ((c->npixel - 1 - pixel_seen) % 2 == 0) ? 2 : 1;
+            ++pixel_seen;
+            for (int p = 0; p < l.nplanes; ++p) {  // planes this filter passes through
+                if (f->process[p]) continue;
+                VSZ_CUDA(cudaMemcpyAsync(s->dev[nxt] + l.pl[p].offset, s->dev[cur] + l.pl[p].offset, (size_t)l.pl[p].pitch * l.pl[p].h,
+                                         cudaMemcpyDeviceToDevice, s->stream));
+            }
+            int rc;
+            if (f->kind == F_BOXBLUR) {
+                rc = run_boxblur(l, f->process, s->dev[cur], 0, s->dev[nxt], 0, 1, (int)f->hradius, f->hpasses, (int)f->vradius, f->vpasses, s->stream);
+            } else {
+                if (bilateral_upload(f, dev_index)) return -1;
+                rc = bilateral_run(f, dev_index, s->dev[cur], 0, nullptr, 0, s->dev[nxt], 0, 1, s->stream);
+            }
+            if (rc) return rc;
+            cur = nxt;
+        } else {
+            if (!props_out || !props_out[i]) { set_error("chain: props_out[%d] is required for a PlaneMinMax/PlaneAverage element", (int)i); return -1; }
+            const int np = processed_planes(f);
+            if (np == 0) { ++stats_seen; continue; }
+            const size_t sb = stats_scratch_bytes(1, np);
+            VSZ_CUDA(cudaMallocAsync((void**)&stats_scratch, sb, s->stream));
+            StatsRaw* raw_dev = (StatsRaw*)s->dev_small + (size_t)stats_seen * 3;
+            int rc;
+            if (f->kind == F_PLANEMINMAX) {
+                rc = run_planeminmax(l, f->process, s->dev[cur], 0, nullptr, 0, 1, f->no_thr, f->minthr, f->maxthr, f->hist_size, stats_scratch,
+                                     raw_dev, s->stream);
+            } else {
+                const int32_t* xi; const float* xf;
+                if (average_upload(f, dev_index, &xi, &xf)) return -1;
+                rc = run_planeaverage(l, f->process, s->dev[cur], 0, nullptr, 0, 1, f->exclude_i.data(), f->exclude_f.data(),
+                                      (int)f->exclude_i.size(), xi, xf, stats_scratch, raw_dev, s->stream);
+            }
+            if (rc) return rc;
+            VSZ_CUDA(cudaMemcpyAsync((StatsRaw*)s->pin_small + (size_t)stats_seen * 3, raw_dev, sizeof(StatsRaw) * np, cudaMemcpyDeviceToHost, s->stream));
+            VSZ_CUDA(cudaFreeAsync(stats_scratch, s->stream));
+            ++stats_seen;
+        }
+    }
+    bool direct[3] = {false, false, false};
+    if (c->npixel > 0 && stage_out_begin(s, l, dst, c->written, direct)) return -1;
+    VSZ_CUDA(cudaStreamSynchronize(s->stream));
+    if (c->npixel > 0) stage_out_finish(s, l, dst, c->written, direct);
+    stats_seen = 0;
+    for (size_t i = 0; i < c->fl.size(); ++i) {
+        const vszip_filter* f = c->fl[i];
+        if (f->kind != F_PLANEMINMAX && f->kind != F_PLANEAVERAGE) continue;
+        const StatsRaw* raw = (const StatsRaw*)s->pin_small + (size_t)stats_seen * 3;
+        if (processed_planes(f) == 0) {
+            if (f->kind == F_PLANEMINMAX) ((vszip_minmax_props*)props_out[i])->count = 0;
+            else ((vszip_average_props*)props_out[i])->count = 0;
+        } else if (f->kind == F_PLANEMINMAX) {
+            minmax_finalize(f, raw, (vszip_minmax_props*)props_out[i]);
+        } else {
+            average_finalize(f, raw, (vszip_average_props*)props_out[i]);
+        }
+        ++stats_seen;
+    }
+    return 0;
 }
 
 }  // extern "C"

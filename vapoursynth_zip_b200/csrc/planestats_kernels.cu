@@ -239,12 +239,14 @@ __global__ void __launch_bounds__(NT) stats_kernel(const StatsJob j) {
             if constexpr (El<T>::flt) {
                 const float f = as_float<T>(av);
                 if (nex > 0) found = (f == xf[0]) | (f == xf[1]) | (f == xf[2]) | (f == xf[3]);
-                for (int i = 4; i < nex; ++i) found |= (f == j.excl_f[i]);
+                for (int i = 4; i < min(nex, 16); ++i) found |= (f == j.excl_f[i]);
+                for (int i = 16; i < nex; ++i) found |= (f == __ldg(j.excl_f_more + i));  // long lists: device copy
                 if (found) acc.excluded += 1; else acc.fsum += (double)f;
             } else {
                 const int32_t iv = (int32_t)av;
                 if (nex > 0) found = (iv == xi[0]) | (iv == xi[1]) | (iv == xi[2]) | (iv == xi[3]);
-                for (int i = 4; i < nex; ++i) found |= (iv == j.excl_i[i]);
+                for (int i = 4; i < min(nex, 16); ++i) found |= (iv == j.excl_i[i]);
+                for (int i = 16; i < nex; ++i) found |= (iv == __ldg(j.excl_i_more + i));
                 if (found) acc.excluded += 1; else isum32 += (unsigned)av;
             }
         } else {
@@ -1015,14 +1017,16 @@ static int launch_avg_t(const StatsJob& j, int count, bool has_b, cudaStream_t s
 }
 
 int run_planeaverage(const FrameLayout& l, const bool mask[3], const char* a, size_t a_fs, const char* b, size_t b_fs, int count,
-                     const int32_t* excl_i, const float* excl_f, int nex, void* scratch, StatsRaw* out_dev, cudaStream_t st) {
+                     const int32_t* excl_i, const float* excl_f, int nex, const int32_t* excl_i_dev, const float* excl_f_dev, void* scratch,
+                     StatsRaw* out_dev, cudaStream_t st) {
     size_t zero = 0;
     StatsJob j = make_job(l, mask, a, a_fs, b, b_fs, count, scratch, out_dev, &zero);
     if (j.ctas_per_frame == 0) return 0;
-    if (nex > 16) { set_error("PlaneAverage: more than 16 exclude values are not supported by the CUDA path"); return -2; }
+    if (nex > 16 && (!excl_i_dev || !excl_f_dev)) { set_error("PlaneAverage: internal error, long exclude list not uploaded"); return -2; }
     VSZ_CUDA(cudaMemsetAsync(scratch, 0, zero, st));
     j.nex = nex;
-    for (int i = 0; i < nex; ++i) { j.excl_i[i] = excl_i[i]; j.excl_f[i] = excl_f[i]; }
+    for (int i = 0; i < std::min(nex, 16); ++i) { j.excl_i[i] = excl_i[i]; j.excl_f[i] = excl_f[i]; }
+    j.excl_i_more = excl_i_dev; j.excl_f_more = excl_f_dev;  // the whole list (entries >= 16 are read from here)
     const bool has_b = b != nullptr;
     switch (l.kind) {
         case K_U8: return launch_avg_t<uint8_t>(j, count, has_b, st);
