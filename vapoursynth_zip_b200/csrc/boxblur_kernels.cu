@@ -195,7 +195,6 @@ struct LinePipe {
     uint32_t* cur2;   // ring + slot(t+2) * SLOT_WORDS
     int slot;         // t mod (2r+1)
     int n, D;         // line length, stage delay r+1
-    int ek = 0, ej = 0;  // phase counters of step_any
     AxisParams ap;
 
     __device__ __forceinline__ void start(uint32_t* ring_, int n_, const AxisParams& ap_) {
@@ -366,28 +365,44 @@ struct LinePipe {
         return nv[P - 1];
     }
 
-    // Dispatcher for callers that cannot structure their loops by phase (the tiled H kernel): phase counters
-    // live in the pipe.  Requires n >= fast_begin().
-    __device__ __forceinline__ V step_any(int t, const V& v_in) {
-        if (t >= fast_begin() && t < n) return step_fast(v_in);
-        V o{};
-        if (t < n) {
-            static_for<P + 1>([&](auto kc) {
-                constexpr int k = decltype(kc)::value;
-                if (ek == k) {
-                    if (ej == 0 && k >= 1) o = step_start<k, (k >= 1)>(v_in);
-                    else o = step_start<k, false>(v_in);
+    // Runs steps [t, t_end) for callers that cannot structure their loops by phase (the tiled H kernel walks the line
+    // in 32-step chunks): the phase dispatch is hoisted out of the per-step loops, so every inner loop contains one
+    // compile-time step variant.  in(t) -> V is the input sample of step t, out(t, V) receives stage P's result.
+    // Requires n >= fast_begin().
+    template <class IN, class OUT>
+    __device__ __forceinline__ void run_steps(int t, const int t_end, IN in, OUT out) {
+        while (t < t_end) {
+            if (t < n) {
+                if (t >= fast_begin()) {
+                    const int e = min(t_end, n);
+                    for (; t < e; ++t) out(t, step_fast(in(t)));
+                    continue;
                 }
-            });
-        } else {
-            if (t == n) { ek = 0; ej = 0; }
-            static_for<P>([&](auto kc) {
-                constexpr int k = decltype(kc)::value;
-                if (ek == k) o = (ej < ap.r) ? step_drain<k, true>(ej) : step_drain<k, false>(0);
-            });
+                const int k = t / D, j = t - k * D;  // start-up phase k (0..P), step j inside it
+                static_for<P + 1>([&](auto kc) {
+                    constexpr int K = decltype(kc)::value;
+                    if (k == K) {
+                        if constexpr (K >= 1) {
+                            if (j == 0) { out(t, step_start<K, true>(in(t))); ++t; }
+                        }
+                        const int e = min((K == P) ? K * D + 1 : (K + 1) * D, t_end);
+                        for (; t < e; ++t) out(t, step_start<K, false>(in(t)));
+                    }
+                });
+            } else {
+                const int k = (t - n) / D;  // drain phase k (0..P-1)
+                static_for<P>([&](auto kc) {
+                    constexpr int K = decltype(kc)::value;
+                    if (k == K) {
+                        const int base = n + K * D, e = min(base + D, t_end);
+                        const int em = min(base + ap.r, e);  // mirrored-tail steps of this phase come first
+                        for (; t < em; ++t) out(t, step_drain<K, true>(t - base));
+                        for (; t < e; ++t) out(t, step_drain<K, false>(0));
+                    }
+                });
+                if (k >= P) t = t_end;  // nothing left to compute
+            }
         }
-        if (++ej == D) { ej = 0; ++ek; }
-        return o;
     }
 
     // any t, any n (tiny lines): also seeds stages that start at this step and publishes mirrored tails.  v_in is
@@ -596,21 +611,34 @@ __global__ void __launch_bounds__(NT) blur_h_kernel(const BatchJob job, const Ax
     constexpr int NLD = ROWS / (RPI * NWARP);    // loads per thread per tile
     const int lw = lane % WPR, lr = lane / WPR;
     uint32_t pre[NLD];
-    // row rr_i = (i*NWARP + warp)*RPI + lr, word lw: running 64-bit pointers, one add per load
+    // 16-bit samples, one warp: load i fetches row 4*(i/2) + 2*lr + (i%2), so a thread holds both rows of a packed
+    // row pair at the same two positions and the 2x2 transpose happens in registers (2 PRMT + 2 32-bit STS per pair
+    // of loads instead of 4 16-bit STS; the same in reverse when flushing).
+    // Measured on B200: a gain for 1-2 fused passes (staging dominates), a loss from 3 passes up (register pressure).
+    constexpr bool PAIR = (P <= 2 && sizeof(T) == 2 && NWARP == 1);
+    auto row_of = [&](int i) { return PAIR ? 4 * (i >> 1) + 2 * lr + (i & 1) : (i * NWARP + warp) * RPI + lr; };
+    // generic mapping: row rr_i = (i*NWARP + warp)*RPI + lr, word lw: running 64-bit pointers, one add per load
     const bool full = (nrows == ROWS);
-    const char* lsrc = src + (size_t)(warp * RPI + lr) * sp + (size_t)lw * 4;
-    char* ldst = dst + (size_t)(warp * RPI + lr) * dp + (size_t)lw * 4;
+    const char* lsrc = src + (size_t)row_of(0) * sp + (size_t)lw * 4;
+    char* ldst = dst + (size_t)row_of(0) * dp + (size_t)lw * 4;
     const size_t lstep_s = (size_t)(NWARP * RPI) * sp, lstep_d = (size_t)(NWARP * RPI) * dp;
     auto issue_loads = [&](int t0) {
         const char* p = lsrc + (size_t)t0 * sizeof(T);
         if (t0 + lw * EPW >= n) return;  // this lane's word lies beyond the line: keeps stale data, never consumed
-        if (full) {
+        if constexpr (PAIR) {
+#pragma unroll
+            for (int i = 0; i < NLD; i += 2) {
+                if (full || row_of(i) < nrows) pre[i] = *reinterpret_cast<const uint32_t*>(p);
+                if (full || row_of(i + 1) < nrows) pre[i + 1] = *reinterpret_cast<const uint32_t*>(p + sp);
+                p += 4 * (size_t)sp;
+            }
+        } else if (full) {
 #pragma unroll
             for (int i = 0; i < NLD; ++i) { pre[i] = *reinterpret_cast<const uint32_t*>(p); p += lstep_s; }
         } else {
 #pragma unroll
             for (int i = 0; i < NLD; ++i) {
-                if ((i * NWARP + warp) * RPI + lr < nrows) pre[i] = *reinterpret_cast<const uint32_t*>(p);
+                if (row_of(i) < nrows) pre[i] = *reinterpret_cast<const uint32_t*>(p);
                 p += lstep_s;
             }
         }
@@ -622,12 +650,21 @@ __global__ void __launch_bounds__(NT) blur_h_kernel(const BatchJob job, const Ax
     for (int c = 0; c < nchunks; ++c) {
         const int t0 = c * TL::CH;
         // ---- scatter the prefetched tile (positions [t0, t0+32) of every row) and prefetch the next one
+        if constexpr (PAIR) {
 #pragma unroll
-        for (int i = 0; i < NLD; ++i) {
-            const int rr = (i * NWARP + warp) * RPI + lr;
-            const T* e = reinterpret_cast<const T*>(&pre[i]);
+            for (int i = 0; i < NLD; i += 2) {
+                const int tw = (i >> 1) * 2 + lr;  // the thread that owns rows (row_of(i), row_of(i) + 1)
+                in_tile[(lw * 2) * TL::PITCH_W + tw] = __byte_perm(pre[i], pre[i + 1], 0x5410);
+                in_tile[(lw * 2 + 1) * TL::PITCH_W + tw] = __byte_perm(pre[i], pre[i + 1], 0x7632);
+            }
+        } else {
 #pragma unroll
-            for (int k = 0; k < EPW; ++k) in_t[((lw * EPW + k) * TL::PITCH_W) * NL + rr] = e[k];
+            for (int i = 0; i < NLD; ++i) {
+                const int rr = row_of(i);
+                const T* e = reinterpret_cast<const T*>(&pre[i]);
+#pragma unroll
+                for (int k = 0; k < EPW; ++k) in_t[((lw * EPW + k) * TL::PITCH_W) * NL + rr] = e[k];
+            }
         }
         if (t0 + TL::CH < n) issue_loads(t0 + TL::CH);
         __syncthreads();
@@ -640,14 +677,18 @@ __global__ void __launch_bounds__(NT) blur_h_kernel(const BatchJob job, const Ax
             for (int i = 0; i < TL::CH; ++i)
                 out_tile[((x0 + i) & (TL::OUT - 1)) * TL::PITCH_W + threadIdx.x] = pipe.step_fast(Vec<1>{{in_tile[i * TL::PITCH_W + threadIdx.x]}}).v[0];
         } else {
-            for (int t = t0; t < t1; ++t) {
-                const Vec<1> v{{in_tile[(t - t0) * TL::PITCH_W + threadIdx.x]}};
-                uint32_t o;
-                if (phased) o = pipe.step_any(t, v).v[0];
-                else if (t >= t_fast && t < n) o = pipe.step_fast(v).v[0];
-                else o = pipe.step_edge(t, v).v[0];
+            auto in = [&](int t) { return Vec<1>{{in_tile[(t - t0) * TL::PITCH_W + threadIdx.x]}}; };
+            auto out = [&](int t, const Vec<1>& o) {
                 const int x = t - lag;
-                if (x >= 0 && x < n) out_tile[(x & (TL::OUT - 1)) * TL::PITCH_W + threadIdx.x] = o;
+                if (x >= 0 && x < n) out_tile[(x & (TL::OUT - 1)) * TL::PITCH_W + threadIdx.x] = o.v[0];
+            };
+            if (phased) {
+                pipe.run_steps(t0, t1, in, out);
+            } else {
+                for (int t = t0; t < t1; ++t) {
+                    if (t >= t_fast && t < n) out(t, pipe.step_fast(in(t)));
+                    else out(t, pipe.step_edge(t, in(t)));
+                }
             }
         }
         __syncthreads();
@@ -661,29 +702,47 @@ __global__ void __launch_bounds__(NT) blur_h_kernel(const BatchJob job, const Ax
             if (full && xb + 32 <= upto) {
                 // common case (full CTA, complete block): branch-free, all shared-memory reads issued before the stores
                 uint32_t wv[NLD];
+                if constexpr (PAIR) {
 #pragma unroll
-                for (int i = 0; i < NLD; ++i) {
-                    const int rr = (i * NWARP + warp) * RPI + lr;
-                    T e[EPW];
+                    for (int i = 0; i < NLD; i += 2) {
+                        const int tw = (i >> 1) * 2 + lr;
+                        const uint32_t o0 = out_tile[(x & (TL::OUT - 1)) * TL::PITCH_W + tw];
+                        const uint32_t o1 = out_tile[((x + 1) & (TL::OUT - 1)) * TL::PITCH_W + tw];
+                        wv[i] = __byte_perm(o0, o1, 0x5410);
+                        wv[i + 1] = __byte_perm(o0, o1, 0x7632);
+                    }
 #pragma unroll
-                    for (int k = 0; k < EPW; ++k) e[k] = out_t[(((x + k) & (TL::OUT - 1)) * TL::PITCH_W) * NL + rr];
-                    wv[i] = *reinterpret_cast<const uint32_t*>(e);
+                    for (int i = 0; i < NLD; i += 2) {
+                        *reinterpret_cast<uint32_t*>(q) = wv[i];
+                        *reinterpret_cast<uint32_t*>(q + dp) = wv[i + 1];
+                        q += 4 * (size_t)dp;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < NLD; ++i) {
+                        const int rr = row_of(i);
+                        T e[EPW];
+#pragma unroll
+                        for (int k = 0; k < EPW; ++k) e[k] = out_t[(((x + k) & (TL::OUT - 1)) * TL::PITCH_W) * NL + rr];
+                        wv[i] = *reinterpret_cast<const uint32_t*>(e);
+                    }
+#pragma unroll
+                    for (int i = 0; i < NLD; ++i) { *reinterpret_cast<uint32_t*>(q) = wv[i]; q += lstep_d; }
                 }
-#pragma unroll
-                for (int i = 0; i < NLD; ++i) { *reinterpret_cast<uint32_t*>(q) = wv[i]; q += lstep_d; }
             } else if (x < upto) {
                 const bool whole = (x + EPW <= upto);
 #pragma unroll 4
                 for (int i = 0; i < NLD; ++i) {
-                    const int rr = (i * NWARP + warp) * RPI + lr;
+                    const int rr = row_of(i);
+                    char* qi = PAIR ? dst + (size_t)rr * dp + (size_t)lw * 4 + (size_t)xb * sizeof(T) : q;
                     if (rr < nrows) {
                         T e[EPW];
 #pragma unroll
                         for (int k = 0; k < EPW; ++k) e[k] = out_t[(((x + k) & (TL::OUT - 1)) * TL::PITCH_W) * NL + rr];
                         if (whole) {
-                            *reinterpret_cast<uint32_t*>(q) = *reinterpret_cast<const uint32_t*>(e);
+                            *reinterpret_cast<uint32_t*>(qi) = *reinterpret_cast<const uint32_t*>(e);
                         } else {
-                            for (int k = 0; k < EPW && x + k < upto; ++k) reinterpret_cast<T*>(q)[k] = e[k];
+                            for (int k = 0; k < EPW && x + k < upto; ++k) reinterpret_cast<T*>(qi)[k] = e[k];
                         }
                     }
                     q += lstep_d;
