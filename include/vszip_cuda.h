@@ -161,6 +161,21 @@ vszip_filter* vszip_planeaverage_create(const vszip_video_info* vi, const vszip_
 int vszip_planeaverage_get_frame(const vszip_filter* f, int32_t n, const vszip_frame* clipa,
                                  const vszip_frame* clipb, vszip_average_props* out);
 
+/* ------------------------------------------------------------------ Limiter (the pointwise neighbour of BoxBlur)
+ * replaces limiterCreate / Limiter.getFrame / LimiterRT.getFrame (src/vapoursynth/limiter.zig:24-233) and the range
+ * tables of src/filters/limiter.zig:66-91.  Argument string kept:
+ * "clip:vnode;min:float[]:opt;max:float[]:opt;tv_range:int:opt;mask:int:opt;planes:int[]:opt;" (src/vszip.zig:162).
+ * num_min / num_max / num_planes < 0 mean "key absent"; 32-bit integer clips are not supported by the CUDA path. */
+typedef struct vszip_limiter_args {
+    const double* min; int32_t num_min;
+    const double* max; int32_t num_max;
+    const int64_t* planes; int32_t num_planes;
+    int32_t has_tv_range; int32_t tv_range;
+    int32_t has_mask; int32_t mask;
+} vszip_limiter_args;
+vszip_filter* vszip_limiter_create(const vszip_video_info* vi, const vszip_limiter_args* args);
+int vszip_limiter_get_frame(const vszip_filter* f, int32_t n, const vszip_frame* src, vszip_frame* dst);
+
 /* ------------------------------------------------------------------ common filter calls */
 void vszip_filter_free(vszip_filter* f);                         /* replaces xxxFree */
 int vszip_filter_planes(const vszip_filter* f, int32_t process[3]); /* d.planes after create */
@@ -196,6 +211,8 @@ int vszip_planeminmax_device(const vszip_filter* f, const vszip_dev_clip* clipa,
                              int32_t first, int32_t count, vszip_minmax_props* out, void* stream);
 int vszip_planeaverage_device(const vszip_filter* f, const vszip_dev_clip* clipa, const vszip_dev_clip* clipb,
                               int32_t first, int32_t count, vszip_average_props* out, void* stream);
+int vszip_limiter_device(const vszip_filter* f, const vszip_dev_clip* src, vszip_dev_clip* dst,
+                         int32_t first, int32_t count, void* stream);
 int vszip_cuda_stream_sync(int32_t device, void* stream);
 
 /* ------------------------------------------------------------------ fused chains of vszip filters

@@ -63,6 +63,7 @@ def lib():
                                                    C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int]
         _lib.vso_recursive_gaussian_params.argtypes = [C.c_double, C.c_void_p]
         _lib.vso_recursive_gaussian_params.restype = None
+        _lib.vso_limiter_plane.argtypes = [C.c_int, C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_ssize_t, C.c_int, C.c_int, C.c_double, C.c_double]
         _lib.vso_bilateral_luts.argtypes = [C.c_double, C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         _lib.vso_bilateral_luts.restype = None
         _lib.vso_planeminmax_plane.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_ssize_t, C.c_int, C.c_int,
@@ -161,6 +162,16 @@ def recursive_gaussian_params(sigma) -> np.ndarray:
     out = np.zeros(4, np.float32)
     lib().vso_recursive_gaussian_params(float(sigma), _p(out))
     return out
+
+
+def limiter_plane(src: np.ndarray, lo: float, hi: float) -> np.ndarray:
+    """dst = min(max(lo, src), hi) with the bounds rounded to the sample type."""
+    _chk2d(src)
+    dst = np.empty_like(src, order="C")
+    h, w = src.shape
+    rc = lib().vso_limiter_plane(sample_type_of(src), _p(src), src.strides[0], _p(dst), dst.strides[0], w, h, float(lo), float(hi))
+    assert rc == 0
+    return dst
 
 
 def planeminmax_plane(src: np.ndarray, bits: int, minthr=0.0, maxthr=0.0, ref: np.ndarray | None = None) -> dict:

@@ -443,6 +443,22 @@ void pbfic_plane_t(const void* src, ptrdiff_t sst, const void* ref, ptrdiff_t rs
 }
 
 // ---------------------------------------------------------------------------
+// Limiter (src/vapoursynth/limiter.zig:24-93): dst = min(max(lo, src), hi), bounds in the sample type
+// ---------------------------------------------------------------------------
+template <class T>
+void limiter_plane_t(const void* src, ptrdiff_t sst, void* dst, ptrdiff_t dstt, int w, int h, double lo, double hi) {
+    const T l = is_flt<T>::value ? (T)(float)lo : (T)(uint32_t)lo, u = is_flt<T>::value ? (T)(float)hi : (T)(uint32_t)hi;
+    for (int y = 0; y < h; ++y) {
+        const T* sp = row_ptr<T>(src, sst, y);
+        T* dp = row_ptr<T>(dst, dstt, y);
+        for (int x = 0; x < w; ++x) {
+            if (is_flt<T>::value) dp[x] = (T)std::fmin(std::fmax((float)l, (float)sp[x]), (float)u);  // @max/@min: NaN yields the other operand
+            else dp[x] = std::min(std::max(l, sp[x]), u);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // PlaneMinMax / PlaneAverage
 // ---------------------------------------------------------------------------
 
@@ -717,6 +733,16 @@ int vso_bilateral_pbfic_plane(int st, const void* src, ptrdiff_t sstride, const 
 
 // src/filters/bilateral.zig:336-348, exposed for the host-logic tests
 void vso_recursive_gaussian_params(double sigma, float* out4) { recursive_gaussian_params(sigma, out4, out4 + 1, out4 + 2, out4 + 3); }
+
+int vso_limiter_plane(int st, const void* src, ptrdiff_t sstride, void* dst, ptrdiff_t dstride, int w, int h, double lo, double hi) {
+    switch (st) {
+        case ST_U8: limiter_plane_t<uint8_t>(src, sstride, dst, dstride, w, h, lo, hi); return 0;
+        case ST_U16: limiter_plane_t<uint16_t>(src, sstride, dst, dstride, w, h, lo, hi); return 0;
+        case ST_F16: limiter_plane_t<f16>(src, sstride, dst, dstride, w, h, lo, hi); return 0;
+        case ST_F32: limiter_plane_t<float>(src, sstride, dst, dstride, w, h, lo, hi); return 0;
+    }
+    return -1;
+}
 
 struct vso_minmax_out { long long imin, imax; double fmin, fmax, diff; };
 

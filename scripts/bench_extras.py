@@ -80,6 +80,7 @@ pixel_cfg("C3 Bilateral(sigmaS=2,sigmaR=2) all planes", "YUV420P16", 1920, 1080,
 pixel_cfg("C3' Bilateral default sigmaR=0.02 (exact smem LUT)", "YUV420P16", 1920, 1080, N, lambda s: vz.BilateralFilter(s.info(), sigmaS=2, sigmaR=0.02, planes=[0, 1, 2]))
 pixel_cfg("C3'' Bilateral(sigmaS=8, sigmaR=0.1): PBFIC luma (num=4) + alg 2 chroma", "YUV420P16", 1920, 1080, min(N, 32), lambda s: vz.BilateralFilter(s.info(), sigmaS=8, sigmaR=0.1, planes=[0, 1, 2]))
 pixel_cfg("C3'' Bilateral(sigmaS=3, sigmaR=0.02, algorithm=1): PBFIC num=12/13", "YUV420P16", 1920, 1080, min(N, 32), lambda s: vz.BilateralFilter(s.info(), sigmaS=3, sigmaR=0.02, algorithm=1, planes=[0, 1, 2]))
+pixel_cfg("C6 Limiter(tv_range=True) (pointwise neighbour, 8f rank 3)", "YUV420P16", 1920, 1080, N, lambda s: vz.LimiterFilter(s.info(), tv_range=True))
 M = max(8, N // 2)
 stats_cfg("C4 PlaneMinMax(minthr=.1,maxthr=.1) GRAY16 4K", "GRAY16", 3840, 2160, M, lambda s: vz.PlaneMinMaxFilter(s.info(), minthr=0.1, maxthr=0.1))
 stats_cfg("C4 PlaneMinMax(minthr=.1,maxthr=.1) GRAYS 4K", "GRAYS", 3840, 2160, M, lambda s: vz.PlaneMinMaxFilter(s.info(), minthr=0.1, maxthr=0.1))

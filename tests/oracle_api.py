@@ -53,6 +53,31 @@ def bilateral(clip, ref=None, sigmaS=None, sigmaR=None, planes=None, algorithm=N
     return {"format": clip["format"], "planes": out}
 
 
+def limiter(clip, min=None, max=None, tv_range=False, mask=False, planes=None):
+    """src/vapoursynth/limiter.zig:100-233 (valid arguments only) + the range tables of src/filters/limiter.zig:66-91."""
+    fam, st, bits, ssw, ssh = _fmt(clip)
+    pm = _plane_mask(clip, planes)
+    n = len(clip["planes"])
+    if min is not None:
+        assert max is not None and len(min) == len(max) == n
+        if st == "i":
+            lo, hi = [float(np.trunc(v)) for v in min], [float(np.trunc(v)) for v in max]
+        else:
+            lo, hi = [float(np.float32(v)) for v in min], [float(np.float32(v)) for v in max]
+    else:
+        yuv = fam == "YUV" and not mask
+        if st == "f":
+            lo = [0.0] + [-0.5 if yuv else 0.0] * 2
+            hi = [1.0] + [0.5 if yuv else 1.0] * 2
+        elif tv_range:
+            lo = [float(16 << (bits - 8))] * 3
+            hi = [float(235 << (bits - 8))] + [float((240 if yuv else 235) << (bits - 8))] * 2
+        else:
+            lo, hi = [0.0] * 3, [float((1 << bits) - 1)] * 3
+    out = [oracle.limiter_plane(p, lo[i], hi[i]) if m else p.copy() for i, (p, m) in enumerate(zip(clip["planes"], pm))]
+    return {"format": clip["format"], "planes": out}
+
+
 def _props(values_per_plane, keys, prop):
     """Append semantics of the reference: scalar for one processed plane, list for several."""
     res = {}

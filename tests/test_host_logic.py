@@ -173,3 +173,27 @@ def test_planeaverage_exclude_required_and_int32():
     raises("32-bit integer", lambda: core.BlankClip("GRAY32", 64, 32).vszip.PlaneAverage(exclude=[-1]))
     raises("plane index out of range", lambda: core.BlankClip("YUV420P16", 64, 32).vszip.PlaneAverage(exclude=[-1], planes=[3]))
     raises("plane specified twice", lambda: core.BlankClip("YUV420P16", 64, 32).vszip.PlaneAverage(exclude=[-1], planes=[0, 0]))
+
+
+# --------------------------------------------------------------------------- Limiter (src/vapoursynth/limiter.zig:100-218)
+@pytest.mark.parametrize(("args", "msg"), [
+    (dict(min=[1, 2]), "min array must have the same number of elements as planes"),
+    (dict(min=[-1, 0, 0], max=[1, 1, 1]), "min value must be greater than or equal to 0"),
+    (dict(min=[70000, 0, 0], max=[1, 1, 1]), "min value must be less than or equal to peak value"),
+    (dict(min=[0, 0, 0], max=[1, 1]), "max array must have the same number of elements as planes"),
+    (dict(min=[0, 0, 0], max=[1, 70000, 1]), "max value must be less than or equal to peak value"),
+    (dict(min=[0, 0, 0], max=[1, -3, 1]), "max value must be greater than or equal to 0"),
+    (dict(min=[0, 0, 0]), "min array is set but max array is not"),
+    (dict(max=[9, 9, 9]), "max array is set but min array is not"),
+    (dict(min=[5, 0, 0], max=[4, 9, 9]), "min value must be less than or equal to max value"),
+    (dict(planes=[3]), "plane index out of range"),
+    (dict(planes=[1, 1]), "plane specified twice"),
+])
+def test_limiter_argument_errors(args, msg):
+    raises("Limiter: " + msg, lambda: core.BlankClip("YUV444P16", 64, 32).vszip.Limiter(**args))
+
+
+def test_limiter_format_errors_come_last():
+    raises("Limiter: not supported Int format", lambda: core.BlankClip("GRAY11", 64, 32).vszip.Limiter())
+    # a bad min array is reported before the format (limiter.zig:121 vs :220)
+    raises("min array must have", lambda: core.BlankClip("GRAY11", 64, 32).vszip.Limiter(min=[1, 2]))

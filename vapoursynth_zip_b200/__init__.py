@@ -72,6 +72,12 @@ class _AverageArgs(C.Structure):
     _fields_ = [("exclude", C.POINTER(C.c_int64)), ("num_exclude", C.c_int32), ("planes", C.POINTER(C.c_int64)), ("num_planes", C.c_int32)]
 
 
+class _LimiterArgs(C.Structure):
+    _fields_ = [("min", C.POINTER(C.c_double)), ("num_min", C.c_int32), ("max", C.POINTER(C.c_double)), ("num_max", C.c_int32),
+                ("planes", C.POINTER(C.c_int64)), ("num_planes", C.c_int32), ("has_tv_range", C.c_int32), ("tv_range", C.c_int32),
+                ("has_mask", C.c_int32), ("mask", C.c_int32)]
+
+
 class _AverageProps(C.Structure):
     _fields_ = [("count", C.c_int32), ("plane", C.c_int32 * 3), ("has_diff", C.c_int32), ("avg", C.c_double * 3), ("diff", C.c_double * 3)]
 
@@ -108,6 +114,9 @@ ABI = {
     "vszip_dev_clip_fill_noise": (C.c_int, [_P, C.c_uint64, C.c_int32, C.c_int32]),
     "vszip_dev_clip_frame_bytes": (C.c_size_t, [_P]),
     "vszip_dev_clip_plane_ptr": (_P, [_P, C.c_int32, C.c_int32, C.POINTER(C.c_ssize_t)]),
+    "vszip_limiter_create": (_P, [C.POINTER(_VideoInfo), C.POINTER(_LimiterArgs)]),
+    "vszip_limiter_get_frame": (C.c_int, [_P, C.c_int32, C.POINTER(_Frame), C.POINTER(_Frame)]),
+    "vszip_limiter_device": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, _P]),
     "vszip_chain_create": (_P, [C.POINTER(_P), C.c_int32]),
     "vszip_chain_free": (None, [_P]),
     "vszip_chain_planes": (C.c_int, [_P, C.POINTER(C.c_int32 * 3)]),
@@ -166,7 +175,8 @@ def _mk(name, fam, st, bits, ssw=0, ssh=0):
 
 
 FORMATS = {f.name: f for f in [
-    _mk("GRAY8", GRAY, INTEGER, 8), _mk("GRAY10", GRAY, INTEGER, 10), _mk("GRAY12", GRAY, INTEGER, 12), _mk("GRAY16", GRAY, INTEGER, 16),
+    _mk("GRAY8", GRAY, INTEGER, 8), _mk("GRAY9", GRAY, INTEGER, 9), _mk("GRAY10", GRAY, INTEGER, 10), _mk("GRAY11", GRAY, INTEGER, 11),
+    _mk("GRAY12", GRAY, INTEGER, 12), _mk("GRAY14", GRAY, INTEGER, 14), _mk("GRAY16", GRAY, INTEGER, 16),
     _mk("GRAY32", GRAY, INTEGER, 32), _mk("GRAYH", GRAY, FLOAT, 16), _mk("GRAYS", GRAY, FLOAT, 32),
     _mk("YUV420P8", YUV, INTEGER, 8, 1, 1), _mk("YUV420P10", YUV, INTEGER, 10, 1, 1), _mk("YUV420P16", YUV, INTEGER, 16, 1, 1),
     _mk("YUV420PH", YUV, FLOAT, 16, 1, 1), _mk("YUV420PS", YUV, FLOAT, 32, 1, 1),
@@ -385,8 +395,21 @@ class PlaneAverageFilter(_Filter):
         return [self.to_props(out[i], prop) for i in range(count)]
 
 
+class LimiterFilter(_Filter):
+    def __init__(self, vi: _VideoInfo, min=None, max=None, tv_range=None, mask=None, planes=None):
+        pl, npl = _planes_arg(planes)
+        mn, nmn = (None, -1) if min is None else _f64(_as_list(min))
+        mx, nmx = (None, -1) if max is None else _f64(_as_list(max))
+        a = _LimiterArgs(mn, nmn, mx, nmx, pl, npl, tv_range is not None, int(bool(tv_range)), mask is not None, int(bool(mask)))
+        super().__init__(load_library().vszip_limiter_create(C.byref(vi), C.byref(a)))
+
+    def run_device(self, src: "DeviceClip", dst: "DeviceClip", first=0, count=None, stream=None):
+        count = src.num_frames - first if count is None else count
+        _check(load_library().vszip_limiter_device(self.handle, src.handle, dst.handle, first, count, stream))
+
+
 class _Namespace:
-    """`clip.vszip` / `core.vszip`: the four plugin functions with the reference's argument names."""
+    """`clip.vszip` / `core.vszip`: the plugin functions with the reference's argument names."""
 
     def __init__(self, clip: VideoNode | None = None):
         self._clip = clip
@@ -401,6 +424,11 @@ class _Namespace:
         clip = self._c(clip)
         flt = BoxBlurFilter(clip._info(), planes, hradius, hpasses, vradius, vpasses)
         return _pixel_node(clip, None, flt, lambda n, s, r, d: load_library().vszip_boxblur_get_frame(flt.handle, n, C.byref(s), C.byref(d)))
+
+    def Limiter(self, clip=None, min=None, max=None, tv_range=None, mask=None, planes=None) -> VideoNode:
+        clip = self._c(clip)
+        flt = LimiterFilter(clip._info(), min, max, tv_range, mask, planes)
+        return _pixel_node(clip, None, flt, lambda n, s, r, d: load_library().vszip_limiter_get_frame(flt.handle, n, C.byref(s), C.byref(d)))
 
     def Bilateral(self, clip=None, ref=None, sigmaS=None, sigmaR=None, planes=None, algorithm=None, PBFICnum=None) -> VideoNode:
         clip = self._c(clip)

@@ -6,7 +6,7 @@
 
 namespace vsz {
 
-enum FilterKind { F_BOXBLUR = 1, F_BILATERAL = 2, F_PLANEMINMAX = 3, F_PLANEAVERAGE = 4 };
+enum FilterKind { F_BOXBLUR = 1, F_BILATERAL = 2, F_PLANEMINMAX = 3, F_PLANEAVERAGE = 4, F_LIMITER = 5 };
 
 struct BilateralPlane {
     double sigmaS = 0, sigmaR = 0;
@@ -47,6 +47,9 @@ struct vszip_filter {
     // PlaneAverage (src/vapoursynth/planeaverage.zig:14-22)
     std::vector<int32_t> exclude_i;
     std::vector<float> exclude_f;
+
+    // Limiter (src/vapoursynth/limiter.zig:16-23): per-plane bounds in the sample type, held as exact doubles
+    double lim_lo[3], lim_hi[3];
     std::vector<int32_t*> exclude_i_dev;  // [device] copies of lists longer than 16 entries (lazy, guarded by lut_mu)
     std::vector<float*> exclude_f_dev;
     float avg_peak;
@@ -73,6 +76,10 @@ int run_bilateral(const FrameLayout& l, const bool mask[3], const char* src, siz
 // pbfic_kernels.cu: Bilateral algorithm 1 on one plane of `count` frames (ref == nullptr: non-joint)
 int run_pbfic(const FrameLayout& l, int plane, const char* src, size_t src_fs, const char* ref, size_t ref_fs, char* dst, size_t dst_fs,
               int count, const float* gr_dev, int hist_len, double sigmaS, int num, float peak, cudaStream_t st);
+
+// pointwise_kernels.cu
+int run_limiter(const FrameLayout& l, const bool mask[3], const char* src, size_t src_fs, char* dst, size_t dst_fs, int count,
+                const double lo[3], const double hi[3], cudaStream_t st);
 
 // planestats_kernels.cu
 struct StatsRaw {  // one per (frame, processed plane), written by the kernels

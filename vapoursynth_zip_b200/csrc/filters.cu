@@ -658,6 +658,119 @@ int vszip_planeaverage_device(const vszip_filter* f, const vszip_dev_clip* a, co
     return rc;
 }
 
+// =========================================================================== Limiter
+// Range tables of src/filters/limiter.zig:66-91: [lo|hi][plane] for full / tv-range YUV / tv-range RGB at 8 bits;
+// deeper integer formats are the 8-bit values shifted left by (bits - 8), full range is (1 << bits) - 1.
+static void limiter_table(const vszip_video_info& vi, bool tv_range, bool yuv, double lo[3], double hi[3]) {
+    if (vi.sample_type == VSZIP_ST_FLOAT) {  // floats ignore tv_range (limiter.zig:53-54 of the filter file)
+        for (int p = 0; p < 3; ++p) { lo[p] = (yuv && p > 0) ? -0.5 : 0.0; hi[p] = (yuv && p > 0) ? 0.5 : 1.0; }
+        return;
+    }
+    const int sh = vi.bits_per_sample - 8;
+    for (int p = 0; p < 3; ++p) {
+        if (!tv_range) { lo[p] = 0.0; hi[p] = (double)((1u << vi.bits_per_sample) - 1u); }
+        else { lo[p] = (double)(16u << sh); hi[p] = (double)(((yuv && p > 0) ? 240u : 235u) << sh); }
+    }
+}
+
+vszip_filter* vszip_limiter_create(const vszip_video_info* vi, const vszip_limiter_args* a) {
+    static const char* name = "Limiter";
+    if (!basic_vi_ok(vi, name)) return nullptr;
+    const int np = vi->num_planes;
+    const bool is_int = vi->sample_type == VSZIP_ST_INTEGER;
+    const double peak = is_int ? (double)(float)((1ll << vi->bits_per_sample) - 1) : 1.0;  // getPeakValue(.., false, .FULL) is f32
+    bool process[3] = {true, true, true};
+    if (!parse_planes(a->planes, a->num_planes, np, name, process)) return nullptr;
+    double lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+    const bool has_min = a->num_min >= 0, has_max = a->num_max >= 0;
+    if (has_min) {  // limiter.zig:121-150
+        if (a->num_min != np) { set_error("Limiter: min array must have the same number of elements as planes."); return nullptr; }
+        for (int i = 0; i < np; ++i) {
+            if (is_int) {
+                const double t = std::trunc(a->min[i]);
+                if (t < 0) { set_error("Limiter: min value must be greater than or equal to 0."); return nullptr; }
+                if (a->min[i] > peak) { set_error("Limiter: min value must be less than or equal to peak value."); return nullptr; }
+                lo[i] = t;
+            } else {
+                lo[i] = (double)(float)a->min[i];
+            }
+        }
+    }
+    if (has_max) {  // limiter.zig:152-181 (peak is tested before the sign here)
+        if (a->num_max != np) { set_error("Limiter: max array must have the same number of elements as planes."); return nullptr; }
+        for (int i = 0; i < np; ++i) {
+            if (is_int) {
+                const double t = std::trunc(a->max[i]);
+                if (a->max[i] > peak) { set_error("Limiter: max value must be less than or equal to peak value."); return nullptr; }
+                if (t < 0) { set_error("Limiter: max value must be greater than or equal to 0."); return nullptr; }
+                hi[i] = t;
+            } else {
+                hi[i] = (double)(float)a->max[i];
+            }
+        }
+    }
+    if (has_min && !has_max) { set_error("Limiter: min array is set but max array is not."); return nullptr; }
+    if (!has_min && has_max) { set_error("Limiter: max array is set but min array is not."); return nullptr; }
+    if (has_min) {
+        for (int p = 0; p < np; ++p)
+            if (lo[p] > hi[p]) { set_error("Limiter: min value must be less than or equal to max value."); return nullptr; }
+    }
+    // BPSType.select (src/helper.zig:25-56)
+    if (is_int) {
+        const int b = vi->bits_per_sample;
+        if (b == 32) { set_error("Limiter: 32-bit integer clips are not supported by the CUDA path."); return nullptr; }
+        if (!(b == 8 || b == 9 || b == 10 || b == 12 || b == 14 || b == 16)) { set_error("Limiter: not supported Int format."); return nullptr; }
+    } else if (!(vi->bits_per_sample == 16 || vi->bits_per_sample == 32)) {
+        set_error("Limiter: not supported Float format.");
+        return nullptr;
+    }
+    SampleKind kind;
+    if (!select_kind(*vi, name, false, &kind)) return nullptr;
+    const bool tv_range = a->has_tv_range && a->tv_range != 0, maskf = a->has_mask && a->mask != 0;
+    const bool yuv = vi->color_family == VSZIP_CF_YUV && !maskf;
+    if (!has_min) limiter_table(*vi, tv_range, yuv, lo, hi);
+    vszip_filter* f = new vszip_filter();
+    f->kind = F_LIMITER;
+    f->vi = *vi;
+    f->sample = kind;
+    f->layout = make_layout(*vi, kind);
+    for (int i = 0; i < 3; ++i) { f->process[i] = process[i] && i < np; f->lim_lo[i] = lo[i]; f->lim_hi[i] = hi[i]; }
+    f->has_ref = false;
+    return f;
+}
+
+int vszip_limiter_get_frame(const vszip_filter* f, int32_t n, const vszip_frame* src, vszip_frame* dst) {
+    if (!f || f->kind != F_LIMITER) { set_error("Limiter: bad filter handle"); return -1; }
+    DeviceCtx* d = route(n, "Limiter");
+    if (!d) return -1;
+    SlotGuard g(d);
+    Slot* s = g.s;
+    VSZ_CUDA(cudaSetDevice(d->ordinal));
+    const size_t bytes = f->layout.frame_stride;
+    if (slot_reserve(d, s, 0, bytes) || slot_reserve(d, s, 2, bytes)) return -1;
+    if (stage_in(s, 0, f->layout, src, f->process)) return -1;
+    int rc = run_limiter(f->layout, f->process, s->dev[0], 0, s->dev[2], 0, 1, f->lim_lo, f->lim_hi, s->stream);
+    if (rc) return rc;
+    bool direct[3];
+    if (stage_out_begin(s, f->layout, dst, f->process, direct)) return -1;
+    VSZ_CUDA(cudaStreamSynchronize(s->stream));
+    stage_out_finish(s, f->layout, dst, f->process, direct);
+    return 0;
+}
+
+int vszip_limiter_device(const vszip_filter* f, const vszip_dev_clip* src, vszip_dev_clip* dst, int32_t first, int32_t count, void* stream) {
+    static const char* name = "Limiter";
+    if (!f || f->kind != F_LIMITER) { set_error("Limiter: bad filter handle"); return -1; }
+    if (!same_clip_shape(src, f, name) || !same_clip_shape(dst, f, name) || !range_ok(src, first, count, name) || !range_ok(dst, first, count, name)) return -1;
+    if (src->device_index != dst->device_index) { set_error("Limiter: clips live on different devices"); return -1; }
+    DeviceCtx* d = device_ctx(src->device_index);
+    if (!d) { set_error("Limiter: library not initialised"); return -1; }
+    VSZ_CUDA(cudaSetDevice(d->ordinal));
+    cudaStream_t st = stream ? (cudaStream_t)stream : d->batch_stream;
+    const size_t fs = src->layout.frame_stride;
+    return run_limiter(f->layout, f->process, src->base + (size_t)first * fs, fs, dst->base + (size_t)first * fs, fs, count, f->lim_lo, f->lim_hi, st);
+}
+
 // =========================================================================== fused chains
 struct vszip_chain {
     std::vector<const vszip_filter*> fl;
@@ -687,7 +800,7 @@ vszip_chain* vszip_chain_create(const vszip_filter* const* filters, int32_t coun
     c->npixel = 0;
     for (int p = 0; p < 3; ++p) c->written[p] = false;
     for (const vszip_filter* f : c->fl) {
-        if (f->kind == F_BOXBLUR || f->kind == F_BILATERAL) {
+        if (f->kind == F_BOXBLUR || f->kind == F_BILATERAL || f->kind == F_LIMITER) {
             ++c->npixel;
             for (int p = 0; p < 3; ++p) c->written[p] = c->written[p] || f->process[p];
         }
@@ -721,7 +834,7 @@ int vszip_chain_get_frame(const vszip_chain* c, int32_t n, const vszip_frame* sr
     char* stats_scratch = nullptr;
     for (size_t i = 0; i < c->fl.size(); ++i) {
         const vszip_filter* f = c->fl[i];
-        if (f->kind == F_BOXBLUR || f->kind == F_BILATERAL) {
+        if (f->kind == F_BOXBLUR || f->kind == F_BILATERAL || f->kind == F_LIMITER) {
             // the last pixel filter must land in dev[2] (the D2H source), the ones before alternate 1 / 2
             const int nxt = ((c->npixel - 1 - pixel_seen) % 2 == 0) ? 2 : 1;
             ++pixel_seen;
@@ -733,6 +846,8 @@ int vszip_chain_get_frame(const vszip_chain* c, int32_t n, const vszip_frame* sr
             int rc;
             if (f->kind == F_BOXBLUR) {
                 rc = run_boxblur(l, f->process, s->dev[cur], 0, s->dev[nxt], 0, 1, (int)f->hradius, f->hpasses, (int)f->vradius, f->vpasses, s->stream);
+            } else if (f->kind == F_LIMITER) {
+                rc = run_limiter(l, f->process, s->dev[cur], 0, s->dev[nxt], 0, 1, f->lim_lo, f->lim_hi, s->stream);
             } else {
                 if (bilateral_upload(f, dev_index)) return -1;
                 rc = bilateral_run(f, dev_index, s->dev[cur], 0, nullptr, 0, s->dev[nxt], 0, 1, s->stream);
