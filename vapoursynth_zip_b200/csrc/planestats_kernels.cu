@@ -214,7 +214,9 @@ __device__ bool block_finish(const StatsJob& j, int frame, int k, int local, int
 }
 
 // --------------------------------------------------------------------------- PlaneAverage / no-threshold PlaneMinMax
-template <typename T, bool HAS_B, bool AVERAGE>
+// LONGEX: the exclude list has more than 4 entries (entries 4..15 in the job, the rest in device memory); the usual
+// short lists compile to four register compares per sample and nothing else.
+template <typename T, bool HAS_B, bool AVERAGE, bool LONGEX = false>
 __global__ void __launch_bounds__(NT) stats_kernel(const StatsJob j) {
     int k, local;
     const StatsPlane& p = find_plane(j, blockIdx.x, k, local);
@@ -239,14 +241,18 @@ __global__ void __launch_bounds__(NT) stats_kernel(const StatsJob j) {
             if constexpr (El<T>::flt) {
                 const float f = as_float<T>(av);
                 if (nex > 0) found = (f == xf[0]) | (f == xf[1]) | (f == xf[2]) | (f == xf[3]);
-                for (int i = 4; i < min(nex, 16); ++i) found |= (f == j.excl_f[i]);
-                for (int i = 16; i < nex; ++i) found |= (f == __ldg(j.excl_f_more + i));  // long lists: device copy
+                if constexpr (LONGEX) {
+                    for (int i = 4; i < min(nex, 16); ++i) found |= (f == j.excl_f[i]);
+                    for (int i = 16; i < nex; ++i) found |= (f == __ldg(j.excl_f_more + i));  // long lists: device copy
+                }
                 if (found) acc.excluded += 1; else acc.fsum += (double)f;
             } else {
                 const int32_t iv = (int32_t)av;
                 if (nex > 0) found = (iv == xi[0]) | (iv == xi[1]) | (iv == xi[2]) | (iv == xi[3]);
-                for (int i = 4; i < min(nex, 16); ++i) found |= (iv == j.excl_i[i]);
-                for (int i = 16; i < nex; ++i) found |= (iv == __ldg(j.excl_i_more + i));
+                if constexpr (LONGEX) {
+                    for (int i = 4; i < min(nex, 16); ++i) found |= (iv == j.excl_i[i]);
+                    for (int i = 16; i < nex; ++i) found |= (iv == __ldg(j.excl_i_more + i));
+                }
                 if (found) acc.excluded += 1; else isum32 += (unsigned)av;
             }
         } else {
@@ -1009,8 +1015,13 @@ template <typename T>
 static int launch_avg_t(const StatsJob& j, int count, bool has_b, cudaStream_t st) {
     if (count > 32768) { set_error("PlaneAverage: batches above 32768 frames are not supported"); return -2; }
     const dim3 grid(j.ctas_per_frame, count);
-    if (has_b) stats_kernel<T, true, true><<<grid, NT, 0, st>>>(j);
-    else stats_kernel<T, false, true><<<grid, NT, 0, st>>>(j);
+    if (j.nex > 4) {
+        if (has_b) stats_kernel<T, true, true, true><<<grid, NT, 0, st>>>(j);
+        else stats_kernel<T, false, true, true><<<grid, NT, 0, st>>>(j);
+    } else {
+        if (has_b) stats_kernel<T, true, true><<<grid, NT, 0, st>>>(j);
+        else stats_kernel<T, false, true><<<grid, NT, 0, st>>>(j);
+    }
     count_launch();
     VSZ_CUDA(cudaGetLastError());
     return 0;
