@@ -453,7 +453,9 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
 // --------------------------------------------------------------------------- V: lines are columns
-template <int NT, int W> struct VStage { static constexpr int AHEAD = 8, SLOTS = 16, WORDS = SLOTS * NT * W; };
+// 12 slots = AHEAD rows in flight + the U rows being consumed: with 16 the W = 2, P = 5, r = 13 kernel needs 38.5 KB per CTA and only 5 CTAs
+// fit an SM; 12 slots bring it to 37.6 KB = 6 CTAs (the kernel is bound by resident warps).
+template <int NT, int W> struct VStage { static constexpr int AHEAD = 8, SLOTS = 12, WORDS = SLOTS * NT * W; };
 
 template <typename T, int P, int MODE, int NT, int W>
 __global__ void __launch_bounds__(NT) blur_v_kernel(const BatchJob job, const AxisParams ap) {
@@ -477,7 +479,8 @@ __global__ void __launch_bounds__(NT) blur_v_kernel(const BatchJob job, const Ax
     const int t_fast = min(pipe.fast_begin(), n);
 
     // one commit group per input row, AHEAD rows in flight
-    auto staged = [&](int row) -> V& { return *reinterpret_cast<V*>(stage + (row & (ST::SLOTS - 1)) * (NT * W)); };
+    auto slot_at = [&](int sl) -> V& { return *reinterpret_cast<V*>(stage + sl * (NT * W)); };
+    auto staged = [&](int row) -> V& { return slot_at((int)((unsigned)row % (unsigned)ST::SLOTS)); };
     auto fetch = [&](int row) {
         cp_async<4 * W>(&staged(row), src + (size_t)min(row, n - 1) * sp);
         cp_async_commit();
@@ -518,18 +521,21 @@ __global__ void __launch_bounds__(NT) blur_v_kernel(const BatchJob job, const Ax
     {
         const char* fsrc = src + (size_t)(t + ST::AHEAD) * sp;  // next row to prefetch
         char* fdst = dst + (size_t)(t - lag) * dp;              // next row to store
+        int sr = (int)((unsigned)t % (unsigned)ST::SLOTS), sf = (int)((unsigned)(t + ST::AHEAD) % (unsigned)ST::SLOTS);  // running slots
         for (; t + ST::AHEAD + U <= n; t += U) {
 #pragma unroll
             for (int i = 0; i < U; ++i) {
-                cp_async<4 * W>(&staged(t + ST::AHEAD + i), fsrc);
+                cp_async<4 * W>(&slot_at(sf), fsrc);
                 cp_async_commit();
                 fsrc += sp;
+                sf = (sf + 1 == ST::SLOTS) ? 0 : sf + 1;
             }
             cp_async_wait<ST::AHEAD>();
 #pragma unroll
             for (int i = 0; i < U; ++i) {
-                *reinterpret_cast<V*>(fdst) = pipe.step_fast(staged(t + i));
+                *reinterpret_cast<V*>(fdst) = pipe.step_fast(slot_at(sr));
                 fdst += dp;
+                sr = (sr + 1 == ST::SLOTS) ? 0 : sr + 1;
             }
         }
     }
