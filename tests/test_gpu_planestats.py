@@ -141,6 +141,18 @@ def test_long_exclude_lists():
             props_close(av(clip, other, exclude=ex), oa.planeaverage(clip, ex, clipb=other))
 
 
+def test_exclude_duplicates_and_out_of_range_values():
+    """The packed 16-bit path removes excluded samples arithmetically, so duplicates must be folded and values
+    outside the sample range ignored (planeaverage.zig:120-139 compares u16 == i32)."""
+    clip = noise_clip("GRAY16", 333, 77, seed=8)
+    clip["planes"][0][::2, ::3] = 5
+    clip["planes"][0][1::4, 1::5] = 65535
+    for ex in ([5, 5, 70000, 5], [65535, -7, 65535, 5, 5], [1, 2, 3, 4, 5], [1, 2, 3, 4, 5, 5, 4], [-1, 65536]):
+        props_close(av(clip, exclude=ex), oa.planeaverage(clip, ex))
+    ten = {"format": "GRAY10", "planes": [(clip["planes"][0] >> 6).astype(np.uint16)]}
+    props_close(av(ten, exclude=[0, 1023, 77]), oa.planeaverage(ten, [0, 1023, 77]))
+
+
 def test_exclude_exact():
     """tests/test_planeaverage.py:118-128 of the reference."""
     two = np.vstack([np.full((32, 64), 1000, np.uint16), np.full((32, 64), 3000, np.uint16)])

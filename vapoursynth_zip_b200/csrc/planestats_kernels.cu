@@ -16,6 +16,7 @@
 #include <cuda_fp16.h>
 
 #include <algorithm>
+#include <type_traits>
 #include <cstdlib>
 
 #include "filter.h"
@@ -307,6 +308,77 @@ __global__ void __launch_bounds__(NT) stats_kernel(const StatsJob j) {
         r.isum = total.isum; r.idiff = total.idiff; r.fsum = total.fsum; r.fdiff = total.fdiff;
         r.excluded = total.excluded; r.bin_min = total.imin; r.bin_max = total.imax;
         r.fmin = total.fmin; r.fmax = total.fmax;
+        j.out[(size_t)frame * j.nplanes + k] = r;
+    }
+}
+
+// --------------------------------------------------------------------------- PlaneAverage, 16-bit integer clips, short lists
+// Two samples per instruction: IDP.2A adds both halves of a word to the running sum, and per distinct in-range exclude
+// value e one XOR + VIMNMX.U16x2 turns a word into "1 per half that differs from e", accumulated as packed counts.
+// The excluded samples are then removed arithmetically: count_e = seen - differing_e, sum -= e * count_e (all exact).
+template <int NEX>
+__global__ void __launch_bounds__(NT) average_u16_kernel(const StatsJob j) {
+    int k, local;
+    const StatsPlane& p = find_plane(j, blockIdx.x, k, local);
+    const int frame = blockIdx.y;
+    const char* a = j.a + (size_t)frame * j.a_fs + p.a_off;
+    int y0, y1;
+    rows_of_cta(p, local, y0, y1);
+    unsigned int ee[NEX > 0 ? NEX : 1], pk[NEX > 0 ? NEX : 1], differing[NEX > 0 ? NEX : 1];
+#pragma unroll
+    for (int e = 0; e < NEX; ++e) { ee[e] = (unsigned)j.excl_i[e] * 0x10001u; pk[e] = 0u; differing[e] = 0u; }
+    unsigned long long sum64 = 0ull;
+    unsigned int s32 = 0u, seen = 0u;
+    constexpr int G = 4;
+    const int nvec = p.w / 8;
+    for (int y = y0; y < y1; y += G) {
+        for (int v = threadIdx.x; v < nvec; v += NT) {
+            uint4 av[G];
+#pragma unroll
+            for (int g = 0; g < G; ++g) av[g] = __ldg(reinterpret_cast<const uint4*>(a + (size_t)min(y + g, y1 - 1) * p.a_pitch) + v);
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                if (y + g >= y1) break;
+                const unsigned int w[4] = {av[g].x, av[g].y, av[g].z, av[g].w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    s32 = __dp2a_lo(w[q], 0x0101u, s32);
+#pragma unroll
+                    for (int e = 0; e < NEX; ++e) pk[e] += __vminu2(w[q] ^ ee[e], 0x10001u);
+                }
+                seen += 8u;
+            }
+        }
+        const int x = nvec * 8 + threadIdx.x;  // scalar tail of each row
+        if (x < p.w) {
+            for (int g = 0; g < G && y + g < y1; ++g) {
+                const unsigned int v = reinterpret_cast<const uint16_t*>(a + (size_t)(y + g) * p.a_pitch)[x];
+                s32 += v;
+#pragma unroll
+                for (int e = 0; e < NEX; ++e) differing[e] += (v != (unsigned)j.excl_i[e]) ? 1u : 0u;
+                seen += 1u;
+            }
+        }
+        // per group a thread adds at most 4 * 32 * 4 to each packed half and 4 * 32 * 8 * 65535 to s32
+        sum64 += s32; s32 = 0u;
+#pragma unroll
+        for (int e = 0; e < NEX; ++e) { differing[e] += (pk[e] & 0xffffu) + (pk[e] >> 16); pk[e] = 0u; }
+    }
+    Partial acc = empty_partial();
+    unsigned long long removed = 0ull;
+    unsigned int excluded = 0u;
+#pragma unroll
+    for (int e = 0; e < NEX; ++e) {
+        const unsigned int cnt = seen - differing[e];
+        excluded += cnt;
+        removed += (unsigned long long)cnt * (unsigned)j.excl_i[e];
+    }
+    acc.isum = sum64 - removed;
+    acc.excluded = excluded;
+    Partial total;
+    if (block_finish(j, frame, k, local, p.nctas, j.counters + (size_t)frame * j.nplanes + k, acc, total) && threadIdx.x == 0) {
+        StatsRaw r{};
+        r.isum = total.isum; r.excluded = total.excluded;
         j.out[(size_t)frame * j.nplanes + k] = r;
     }
 }
@@ -1015,6 +1087,35 @@ template <typename T>
 static int launch_avg_t(const StatsJob& j, int count, bool has_b, cudaStream_t st) {
     if (count > 32768) { set_error("PlaneAverage: batches above 32768 frames are not supported"); return -2; }
     const dim3 grid(j.ctas_per_frame, count);
+    if constexpr (std::is_same<T, uint16_t>::value) {
+        if (!has_b) {  // packed path: needs at most 4 distinct exclude values inside the sample range
+            StatsJob q = j;
+            int m = 0;
+            bool fits = true;
+            for (int i = 0; i < j.nex && fits; ++i) {
+                const int32_t v = i < 16 ? j.excl_i[i] : 0;
+                if (i >= 16) { fits = false; break; }
+                if (v < 0 || v > 65535) continue;  // can never match a sample
+                bool dup = false;
+                for (int t = 0; t < m; ++t) dup = dup || q.excl_i[t] == v;
+                if (dup) continue;
+                if (m == 4) { fits = false; break; }
+                q.excl_i[m++] = v;
+            }
+            if (fits) {
+                switch (m) {
+                    case 0: average_u16_kernel<0><<<grid, NT, 0, st>>>(q); break;
+                    case 1: average_u16_kernel<1><<<grid, NT, 0, st>>>(q); break;
+                    case 2: average_u16_kernel<2><<<grid, NT, 0, st>>>(q); break;
+                    case 3: average_u16_kernel<3><<<grid, NT, 0, st>>>(q); break;
+                    default: average_u16_kernel<4><<<grid, NT, 0, st>>>(q); break;
+                }
+                count_launch();
+                VSZ_CUDA(cudaGetLastError());
+                return 0;
+            }
+        }
+    }
     if (j.nex > 4) {
         if (has_b) stats_kernel<T, true, true, true><<<grid, NT, 0, st>>>(j);
         else stats_kernel<T, false, true, true><<<grid, NT, 0, st>>>(j);
