@@ -5,6 +5,7 @@ R=${1:-r01}
 O=gpurun_out
 mkdir -p $O
 timeout 900 python -m pytest tests -m gpu -q --timeout 300 2>&1 | tail -5 > $O/pytest_gpu_$R.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke_$R.log 2>&1
 timeout 600 python bench.py > $O/bench_$R.json 2> $O/bench_$R.err
 timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > $O/bench_ref_$R.json 2>> $O/bench_$R.err
 timeout 300 python scripts/e2e_chain.py 8 4 > $O/e2e_chain_$R.txt 2>&1
