@@ -11,6 +11,8 @@
 //             is short): bit-identical weights;
 //   W_COMPUTE C * 2^(c2 * idx^2) on the MUFU unit when the LUT (up to 256 KB) does not fit in shared
 //             memory: weights within ~2 ulp, integer outputs within 1 LSB;
+//   W_SCALED  W_COMPUTE for integer clips whose LUT is never clamped (sigmaR >= 1/8): the tile is staged already multiplied
+//             by sqrt(-c2), so a tap's weight is 2^(-(a'-b')^2): FSUB, FMUL, MUFU instead of FSUB, FMNMX, FMUL, FMUL, MUFU;
 //   W_GLOBAL  gathers from the full LUT in HBM/L2: bit-identical, slow (validation / VSZIP_BILATERAL_EXACT=1).
 #include <cuda_fp16.h>
 
@@ -22,7 +24,7 @@
 
 namespace vsz {
 
-enum WeightMode { W_SMEM = 0, W_COMPUTE = 1, W_GLOBAL = 2 };
+enum WeightMode { W_SMEM = 0, W_COMPUTE = 1, W_GLOBAL = 2, W_SCALED = 3 };
 
 static constexpr int TW = 32, TH = 8, TILE = 32;
 
@@ -33,6 +35,7 @@ struct BilateralPlaneParams {
     int lut_len;       // entries [0, lut_len) are distinct; larger indices use gr[lut_len-1]
     int smem_lut;      // entries copied to shared memory (W_SMEM)
     float c2, cnorm;   // W_COMPUTE: weight = cnorm * exp2(c2 * idx^2)
+    float scale, inv_scale;  // W_SCALED: sqrt(-c2) and its reciprocal
 };
 
 struct BilateralParams {
@@ -126,8 +129,12 @@ __global__ void __launch_bounds__(TW * TH) bilateral_kernel(const BatchJob job, 
         for (int e = tid; e < tsize; e += TW * TH) {
             const int ly = (int)(((uint32_t)e * inv_tw) >> 20), lx = e - ly * tw;
             const int gy = min(max(y0 + ly - r, 0), pj.h - 1), gx = min(max(x0 + lx - r, 0), pj.w - 1);
-            s_src[e] = widen<T>(reinterpret_cast<const T*>(src + (size_t)gy * pj.src_pitch)[gx]);
-            if constexpr (JOINT) s_ref[e] = widen<T>(reinterpret_cast<const T*>(ref + (size_t)gy * pj.ref_pitch)[gx]);
+            const float sv = widen<T>(reinterpret_cast<const T*>(src + (size_t)gy * pj.src_pitch)[gx]);
+            s_src[e] = (WM == W_SCALED && !JOINT) ? __fmul_rn(sv, pp.scale) : sv;
+            if constexpr (JOINT) {
+                const float rv = widen<T>(reinterpret_cast<const T*>(ref + (size_t)gy * pj.ref_pitch)[gx]);
+                s_ref[e] = (WM == W_SCALED) ? __fmul_rn(rv, pp.scale) : rv;
+            }
         }
         __syncthreads();
         const int x = x0 + threadIdx.x;
@@ -137,7 +144,7 @@ __global__ void __launch_bounds__(TW * TH) bilateral_kernel(const BatchJob job, 
             if (x >= pj.w || y >= pj.h) continue;
             const int cxy = (lyo + r) * tw + threadIdx.x + r;
             const float cref = s_ref[cxy];
-            float wsum = __fmul_rn(s_gs[0], range_weight<WM>(0.0f, top, pp, s_lut));
+            float wsum = (WM == W_SCALED) ? s_gs[0] : __fmul_rn(s_gs[0], range_weight<WM == W_SCALED ? W_COMPUTE : WM>(0.0f, top, pp, s_lut));
             float sum = __fmul_rn(s_src[cxy], wsum);
             auto taps = [&](int yy, int xx) {
                 const int up = cxy - yy * tw, dn = cxy + yy * tw;
@@ -145,10 +152,17 @@ __global__ void __launch_bounds__(TW * TH) bilateral_kernel(const BatchJob job, 
                 const float r1 = s_ref[up + xx], r2v = s_ref[dn + xx], r3 = s_ref[up - xx], r4 = s_ref[dn - xx];
                 const float v1 = JOINT ? s_src[up + xx] : r1, v2 = JOINT ? s_src[dn + xx] : r2v;
                 const float v3 = JOINT ? s_src[up - xx] : r3, v4 = JOINT ? s_src[dn - xx] : r4;
-                const float g1 = range_weight<WM>(range_index_f<T>(cref, r1), top, pp, s_lut);
-                const float g2 = range_weight<WM>(range_index_f<T>(cref, r2v), top, pp, s_lut);
-                const float g3 = range_weight<WM>(range_index_f<T>(cref, r3), top, pp, s_lut);
-                const float g4 = range_weight<WM>(range_index_f<T>(cref, r4), top, pp, s_lut);
+                float g1, g2, g3, g4;
+                if constexpr (WM == W_SCALED) {
+                    const float d1 = __fsub_rn(cref, r1), d2 = __fsub_rn(cref, r2v), d3 = __fsub_rn(cref, r3), d4 = __fsub_rn(cref, r4);
+                    g1 = ex2_approx(__fmul_rn(-d1, d1)); g2 = ex2_approx(__fmul_rn(-d2, d2));
+                    g3 = ex2_approx(__fmul_rn(-d3, d3)); g4 = ex2_approx(__fmul_rn(-d4, d4));
+                } else {
+                    g1 = range_weight<WM>(range_index_f<T>(cref, r1), top, pp, s_lut);
+                    g2 = range_weight<WM>(range_index_f<T>(cref, r2v), top, pp, s_lut);
+                    g3 = range_weight<WM>(range_index_f<T>(cref, r3), top, pp, s_lut);
+                    g4 = range_weight<WM>(range_index_f<T>(cref, r4), top, pp, s_lut);
+                }
                 const float gsum = __fadd_rn(__fadd_rn(__fadd_rn(g1, g2), g3), g4);
                 wsum = __fadd_rn(wsum, __fmul_rn(sw, gsum));
                 const float p1 = __fmul_rn(v1, g1), p2 = __fmul_rn(v2, g2), p3 = __fmul_rn(v3, g3), p4 = __fmul_rn(v4, g4);
@@ -164,7 +178,8 @@ __global__ void __launch_bounds__(TW * TH) bilateral_kernel(const BatchJob job, 
                 for (int yy = 1; yy < r2; yy += step)
                     for (int xx = 1; xx < r2; xx += step) taps(yy, xx);
             }
-            const float q = __fdiv_rn(sum, wsum);
+            float q = __fdiv_rn(sum, wsum);
+            if constexpr (WM == W_SCALED && !JOINT) q = __fmul_rn(q, pp.inv_scale);  // the values were staged scaled
             T* out = reinterpret_cast<T*>(dst + (size_t)y * pj.dst_pitch) + x;
             if constexpr (std::is_same<T, float>::value) *out = q;
             else if constexpr (std::is_same<T, __half>::value) *out = __float2half_rn(q);
@@ -201,12 +216,14 @@ static int launch_mode(int wm, int samples, int step, const BatchJob& j, const B
         if (samples == SA && step == SE) {                                                                          \
             if (wm == W_SMEM) return launch_one<T, false, W_SMEM, SA, SE>(j, prm, nf, smem, st);                     \
             if (wm == W_COMPUTE) return launch_one<T, false, W_COMPUTE, SA, SE>(j, prm, nf, smem, st);               \
+            if (wm == W_SCALED) return launch_one<T, false, W_SCALED, SA, SE>(j, prm, nf, smem, st);                 \
         }
         VSZ_BL(1, 1) VSZ_BL(2, 1) VSZ_BL(2, 2) VSZ_BL(3, 2) VSZ_BL(3, 3) VSZ_BL(4, 3)
 #undef VSZ_BL
     }
     if (wm == W_SMEM) return launch_one<T, JOINT, W_SMEM, 0, 0>(j, prm, nf, smem, st);
     if (wm == W_COMPUTE) return launch_one<T, JOINT, W_COMPUTE, 0, 0>(j, prm, nf, smem, st);
+    if (wm == W_SCALED) return launch_one<T, JOINT, W_SCALED, 0, 0>(j, prm, nf, smem, st);
     return launch_one<T, JOINT, W_GLOBAL, 0, 0>(j, prm, nf, smem, st);
 }
 
@@ -224,9 +241,15 @@ static int run_bilateral_t(const FrameLayout& l, const bool mask[3], const char*
         pp.gs = bp.gs[p]; pp.gr = bp.gr[p];
         pp.radius = bp.radius[p]; pp.step = bp.step[p];
         pp.lut_len = bp.lut_len[p];
-        const int wm = weight_mode_for(pp.lut_len);
+        int wm = weight_mode_for(pp.lut_len);
         pp.smem_lut = wm == W_SMEM ? pp.lut_len : 0;
         pp.c2 = bp.c2[p]; pp.cnorm = bp.cnorm[p];
+        // integer clip, computed weights and a LUT that is never clamped (its last distinct entry is the peak index)
+        if (wm == W_COMPUTE && !BTr<T>::flt && pp.lut_len - 1 >= (int)bp.peak) {
+            wm = W_SCALED;
+            pp.scale = std::sqrt(-pp.c2);
+            pp.inv_scale = 1.0f / pp.scale;
+        }
         const int r = pp.radius;
         // strip length: whole tile rows when the batch alone fills the GPU, shorter strips for single frames
         const int tiles_x = (l.pl[p].w + TILE - 1) / TILE, tiles_y = (l.pl[p].h + TILE - 1) / TILE;
