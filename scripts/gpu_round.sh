@@ -13,6 +13,6 @@ timeout 600 python scripts/bench_extras.py --frames 128 --out $O/bench_extras_$R
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_$R.csv python bench.py --steps 2 --warmup 1 --no-cpu > $O/launches_bench_$R.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:blur_ -s 2 -c 2 -o $O/ncu_boxblur_$R python scripts/prof_run.py boxblur 128 2 > /dev/null 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:bilateral -s 3 -c 1 -o $O/ncu_bilateral_$R python scripts/prof_run.py bilateral 32 2 > /dev/null 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:stats_kernel -s 1 -c 1 -o $O/ncu_average_$R python scripts/prof_run.py average 32 2 > /dev/null 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k "regex:stats_kernel|average_u16" -s 1 -c 1 -o $O/ncu_average_$R python scripts/prof_run.py average 32 2 > /dev/null 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k "regex:hist_sample|minmax_bracket" -s 2 -c 2 -o $O/ncu_minmax_$R python scripts/prof_run.py minmax 32 2 > /dev/null 2>&1
 cat $O/pytest_gpu_$R.log; cat $O/bench_$R.json | cut -c1-400; tail -3 $O/bench_$R.err
