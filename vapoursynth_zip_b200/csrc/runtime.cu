@@ -124,20 +124,51 @@ static bool is_pinned_host(const void* p) {
     return a.type == cudaMemoryTypeHost;
 }
 
+// Pinned planes go by DMA straight from/to the application's memory.  Fewer, larger copies keep the copy engines
+// busier: a plane whose host stride equals the device pitch is one linear copy, and a run of planes that sit in host
+// memory exactly as they do in the device frame (same pitch, back to back - e.g. a frame carved out of one pinned
+// buffer) is a single copy.  Returns the index after the last plane covered by the copy issued for plane p.
+static int pinned_copy(Slot* s, int dev_buf, const FrameLayout& l, const vszip_frame* host, const bool mask[3], const bool pinned[3], int p,
+                       bool to_device, cudaError_t* err) {
+    const PlaneGeom& g = l.pl[p];
+    const size_t row_bytes = (size_t)g.w * l.bps;
+    char* hp = (char*)host->data[p];
+    char* dp = s->dev[dev_buf] + g.offset;
+    if (host->stride[p] != (ptrdiff_t)g.pitch) {
+        *err = to_device ? cudaMemcpy2DAsync(dp, g.pitch, hp, host->stride[p], row_bytes, g.h, cudaMemcpyHostToDevice, s->stream)
+                         : cudaMemcpy2DAsync(hp, host->stride[p], dp, g.pitch, row_bytes, g.h, cudaMemcpyDeviceToHost, s->stream);
+        return p + 1;
+    }
+    int q = p;  // extend over planes laid out identically and contiguously on both sides
+    while (q + 1 < l.nplanes && mask[q + 1] && pinned[q + 1] && host->stride[q + 1] == (ptrdiff_t)l.pl[q + 1].pitch &&
+           (size_t)l.pl[q].pitch * l.pl[q].h == (size_t)l.pl[q].w * l.bps * l.pl[q].h &&               // no row padding
+           l.pl[q].offset + (size_t)l.pl[q].pitch * l.pl[q].h == l.pl[q + 1].offset &&                 // no gap on the device
+           (char*)host->data[q + 1] == (char*)host->data[q] + (size_t)l.pl[q].pitch * l.pl[q].h)        // nor on the host
+        ++q;
+    const PlaneGeom& e = l.pl[q];
+    const size_t bytes = (e.offset - g.offset) + (size_t)e.pitch * (e.h - 1) + (size_t)e.w * l.bps;  // not past the last sample
+    *err = to_device ? cudaMemcpyAsync(dp, hp, bytes, cudaMemcpyHostToDevice, s->stream)
+                     : cudaMemcpyAsync(hp, dp, bytes, cudaMemcpyDeviceToHost, s->stream);
+    return q + 1;
+}
+
 int stage_in(Slot* s, int which, const FrameLayout& l, const vszip_frame* host, const bool mask[3]) {
-    for (int p = 0; p < l.nplanes; ++p) {
-        if (!mask[p]) continue;
+    bool pinned[3] = {false, false, false};
+    for (int p = 0; p < l.nplanes; ++p) pinned[p] = mask[p] && is_pinned_host(host->data[p]);
+    for (int p = 0; p < l.nplanes;) {
+        if (!mask[p]) { ++p; continue; }
         const PlaneGeom& g = l.pl[p];
-        const size_t row_bytes = (size_t)g.w * l.bps;
-        if (is_pinned_host(host->data[p])) {
-            VSZ_CUDA(cudaMemcpy2DAsync(s->dev[which] + g.offset, g.pitch, host->data[p], host->stride[p], row_bytes, g.h,
-                                       cudaMemcpyHostToDevice, s->stream));
+        if (pinned[p]) {
+            cudaError_t e = cudaSuccess;
+            p = pinned_copy(s, which, l, host, mask, pinned, p, true, &e);
+            VSZ_CUDA(e);
             continue;
         }
         // pageable VapourSynth memory -> pinned staging (same layout as the device frame)
-        copy_rows(s->pin[which] + g.offset, g.pitch, (const char*)host->data[p], host->stride[p], row_bytes, g.h);
+        copy_rows(s->pin[which] + g.offset, g.pitch, (const char*)host->data[p], host->stride[p], (size_t)g.w * l.bps, g.h);
         VSZ_CUDA(cudaMemcpyAsync(s->dev[which] + g.offset, s->pin[which] + g.offset, (size_t)g.pitch * g.h,
                                  cudaMemcpyHostToDevice, s->stream));
+        ++p;
     }
     return 0;
 }
@@ -145,18 +176,20 @@ int stage_in(Slot* s, int which, const FrameLayout& l, const vszip_frame* host, 
 // D2H of the result planes: straight into the destination when it is pinned, else into the slot's
 // pinned buffer (stage_out_finish then copies it out after the stream has been synchronised).
 int stage_out_begin(Slot* s, const FrameLayout& l, vszip_frame* host, const bool mask[3], bool direct[3]) {
-    for (int p = 0; p < l.nplanes; ++p) {
-        direct[p] = false;
-        if (!mask[p]) continue;
+    bool pinned[3] = {false, false, false};
+    for (int p = 0; p < l.nplanes; ++p) { pinned[p] = mask[p] && is_pinned_host(host->data[p]); direct[p] = pinned[p]; }
+    for (int p = 0; p < l.nplanes;) {
+        if (!mask[p]) { ++p; continue; }
         const PlaneGeom& g = l.pl[p];
-        if (is_pinned_host(host->data[p])) {
-            direct[p] = true;
-            VSZ_CUDA(cudaMemcpy2DAsync(host->data[p], host->stride[p], s->dev[2] + g.offset, g.pitch, (size_t)g.w * l.bps, g.h,
-                                       cudaMemcpyDeviceToHost, s->stream));
+        if (pinned[p]) {
+            cudaError_t e = cudaSuccess;
+            p = pinned_copy(s, 2, l, host, mask, pinned, p, false, &e);
+            VSZ_CUDA(e);
             continue;
         }
         VSZ_CUDA(cudaMemcpyAsync(s->pin[2] + g.offset, s->dev[2] + g.offset, (size_t)g.pitch * g.h,
                                  cudaMemcpyDeviceToHost, s->stream));
+        ++p;
     }
     return 0;
 }
