@@ -7,12 +7,14 @@
 //       histogram with two cumulative scans using strict '>' against trunc(total*thr).
 //
 // Design: both are single-read streaming reductions (16-byte loads, warp-shuffle trees, one partial per
-// CTA, combined in CTA order by the last CTA to finish so float sums are run-to-run deterministic).
-// The threshold path never materialises 65536 bins: it is an exact two-level radix select.  Pass 1
-// builds the histogram of the top 8 bits of the bin index, pass 2 re-reads the plane (L2-resident for
-// planes up to ~100 MB) and histograms the remaining low bits of only the two coarse bins that contain
-// the requested ranks; the last CTA of pass 2 resolves the exact bins.  Integer counts are exact, so the
-// result is bit-identical to the reference's full histogram scan.
+// CTA, combined in CTA order by the last CTA to finish so float sums are run-to-run deterministic);
+// 16-bit integer PlaneAverage with a short exclude list runs two samples per instruction (average_u16_kernel).
+// The threshold path never materialises 65536 bins.  Default: a 1/16 line sample brackets both ranks, then ONE
+// full read counts exactly what lies outside the brackets (packed 16-bit clamps) and histograms only what lies
+// inside; the exact counts prove the result or hand the plane to the fallback.  Fallback (and
+// VSZIP_MINMAX_EXACT=1): an exact two-level radix select - pass 1 histograms the top 8 bits of the bin index,
+// pass 2 re-reads the plane and histograms the low bits of only the two coarse bins that contain the requested
+// ranks.  Integer counts are exact on both routes, so the result is bit-identical to the reference's full scan.
 #include <cuda_fp16.h>
 
 #include <algorithm>
