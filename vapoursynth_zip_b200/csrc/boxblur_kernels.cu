@@ -802,7 +802,6 @@ __global__ void __launch_bounds__(CTF_NT) ctf_kernel(const BatchJob job, int r, 
     const char* src = job.src + (size_t)blockIdx.y * job.src_fs + pj.src_off;
     char* dst = job.dst + (size_t)blockIdx.y * job.dst_fs + pj.dst_off;
     float* P = ctf_smem;                               // [cnt][129] products
-    float* O = ctf_smem + (CTF_TL + 2 * r) * CTF_PITCH;  // [TL][129] outputs (H pass only)
     const int c = threadIdx.x;
     const bool live = (c0 + c) < ncross;
 
@@ -843,7 +842,34 @@ __global__ void __launch_bounds__(CTF_NT) ctf_kernel(const BatchJob job, int r, 
 
     if (live) {
         const float* Pc = P + c;
-        for (int i0 = l0; i0 < l1; i0 += 4) {
+        // four results of one line leave as a vector (H: the thread owns row c0 + c; the other half of the 32-byte
+        // sector follows with the next group, so L2 merges them) or as four coalesced row stores (V)
+        auto emit4 = [&](int i0, float r0, float r1, float r2, float r3) {
+            const float res[4] = {r0, r1, r2, r3};
+            if constexpr (HORIZ) {
+                T* out = reinterpret_cast<T*>(dst + (size_t)(c0 + c) * pj.dst_pitch) + i0;
+                if (i0 + 3 < l1) {
+                    if constexpr (sizeof(T) == 4) {
+                        *reinterpret_cast<float4*>(out) = make_float4(res[0], res[1], res[2], res[3]);
+                    } else {
+                        const __half2 h01 = __floats2half2_rn(res[0], res[1]), h23 = __floats2half2_rn(res[2], res[3]);
+                        uint2 pk;
+                        pk.x = *reinterpret_cast<const uint32_t*>(&h01); pk.y = *reinterpret_cast<const uint32_t*>(&h23);
+                        *reinterpret_cast<uint2*>(out) = pk;
+                    }
+                } else {
+                    for (int g = 0; g < 4 && i0 + g < l1; ++g) out[g] = st_f<T>(res[g]);
+                }
+            } else {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const int i = i0 + g;
+                    if (i < l1) reinterpret_cast<T*>(dst + (size_t)i * pj.dst_pitch)[c0 + c] = st_f<T>(res[g]);
+                }
+            }
+        };
+        // outputs i0 .. i0+3: one sweep over products i0-r .. i0+3+r, each output adding its 2r+1 taps in tap order
+        auto group4 = [&](int i0) {
             float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
             const bool interior4 = (i0 >= r) && (i0 + 3 + r < n) && (i0 + 3 < l1);
             if (interior4) {
@@ -870,24 +896,43 @@ __global__ void __launch_bounds__(CTF_NT) ctf_kernel(const BatchJob job, int r, 
                     *acc[g] = a;
                 }
             }
-            const float res[4] = {a0, a1, a2, a3};
+            emit4(i0, a0, a1, a2, a3);
+        };
+        // outputs i0 .. i0+7 away from the edges, r >= 4: every product is read once per 8 outputs
+        auto group8 = [&](int i0) {
+            float a[8];
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-                const int i = i0 + g;
-                if (i < l1) {
-                    if constexpr (HORIZ) O[(i - l0) * CTF_PITCH + c] = res[g];
-                    else reinterpret_cast<T*>(dst + (size_t)i * pj.dst_pitch)[c0 + c] = st_f<T>(res[g]);
-                }
+            for (int g = 0; g < 8; ++g) a[g] = 0.f;
+            const float* q = Pc + (i0 - r - lo) * CTF_PITCH;
+            const int m = 2 * r;  // >= 8
+#pragma unroll
+            for (int t = 0; t < 7; ++t) {  // products 0..6: output g takes product t iff g <= t
+                const float v = q[t * CTF_PITCH];
+#pragma unroll
+                for (int g = 0; g < 8; ++g) if (g <= t) a[g] = __fadd_rn(a[g], v);
             }
-        }
-    }
-    if constexpr (HORIZ) {
-        __syncthreads();
-        const int lane = c & 31, warp = c >> 5;
-        for (int rr = warp; rr < CTF_NT; rr += CTF_NT / 32) {
-            if (c0 + rr >= ncross) break;
-            T* row = reinterpret_cast<T*>(dst + (size_t)(c0 + rr) * pj.dst_pitch) + l0;
-            for (int j = lane; j < l1 - l0; j += 32) row[j] = st_f<T>(O[j * CTF_PITCH + rr]);
+            q += 7 * CTF_PITCH;
+            for (int t = 7; t <= m; ++t, q += CTF_PITCH) {
+                const float v = q[0];
+#pragma unroll
+                for (int g = 0; g < 8; ++g) a[g] = __fadd_rn(a[g], v);
+            }
+#pragma unroll
+            for (int u = 1; u <= 7; ++u) {  // products m+1..m+7: output g takes product m+u iff g >= u
+                const float v = q[(u - 1) * CTF_PITCH];
+#pragma unroll
+                for (int g = 0; g < 8; ++g) if (g >= u) a[g] = __fadd_rn(a[g], v);
+            }
+            emit4(i0, a[0], a[1], a[2], a[3]);
+            emit4(i0 + 4, a[4], a[5], a[6], a[7]);
+        };
+        for (int i0 = l0; i0 < l1; i0 += 8) {
+            if (r >= 4 && i0 >= r && i0 + 7 + r < n && i0 + 7 < l1) {
+                group8(i0);
+            } else {
+                group4(i0);
+                if (i0 + 4 < l1) group4(i0 + 4);
+            }
         }
     }
 }
@@ -1104,7 +1149,7 @@ static int run_ct_float(const FrameLayout& l, const bool mask[3], const char* sr
         (k == 0 ? lbh.x : (k == 1 ? lbh.y : lbh.z)) = blocks(jh.pl[k].w);
     }
     const size_t smem_v = (size_t)(CTF_TL + 2 * r) * CTF_PITCH * sizeof(float);
-    const size_t smem_h = smem_v + (size_t)CTF_TL * CTF_PITCH * sizeof(float);
+    const size_t smem_h = smem_v;  // the H pass stores its outputs straight from registers
     VSZ_CUDA(cudaFuncSetAttribute(ctf_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v));
     VSZ_CUDA(cudaFuncSetAttribute(ctf_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h));
     for (int f0 = 0; f0 < count; f0 += 65535) {
