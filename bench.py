@@ -30,7 +30,7 @@ sys.path.insert(0, str(ROOT))
 
 W, H, FMT = 1920, 1080, "YUV420P16"
 ARGS = dict(hradius=13, hpasses=5, vradius=13, vpasses=5)
-FRAMES_PER_STEP = 256
+FRAMES_PER_STEP = 1024
 FRAME_BYTES = (W * H + 2 * (W // 2) * (H // 2)) * 2          # 6,220,800 B read per frame
 ALGO_BYTES = 2 * FRAME_BYTES                                  # read once + written once
 METRIC = "fps @1080p YUV420P16, vszip.BoxBlur(hradius=13,hpasses=5,vradius=13,vpasses=5), device-resident"

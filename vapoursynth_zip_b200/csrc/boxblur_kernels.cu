@@ -465,11 +465,11 @@ __global__ void __launch_bounds__(NT) blur_v_kernel(const BatchJob job, const Ax
     using V = Vec<W>;
     using ST = VStage<NT, W>;
     int local;
-    const PlaneJob& pj = find_plane(job, blockIdx.x, local);
+    const PlaneJob& pj = find_plane(job, blockIdx.y, local);
     const int g = local * NT + threadIdx.x;  // (32*W)-bit column group
     if (g * NL * W >= pj.w) return;           // no block-level sync in this kernel
-    const char* src = job.src + (size_t)blockIdx.y * job.src_fs + pj.src_off + (size_t)g * 4 * W;
-    char* dst = job.dst + (size_t)blockIdx.y * job.dst_fs + pj.dst_off + (size_t)g * 4 * W;
+    const char* src = job.src + (size_t)blockIdx.x * job.src_fs + pj.src_off + (size_t)g * 4 * W;
+    char* dst = job.dst + (size_t)blockIdx.x * job.dst_fs + pj.dst_off + (size_t)g * 4 * W;
     const int sp = pj.src_pitch, dp = pj.dst_pitch;
 
     uint32_t* stage = smem + threadIdx.x * W;               // [SLOTS][NT] input rows in flight
@@ -585,11 +585,11 @@ __global__ void __launch_bounds__(NT) blur_h_kernel(const BatchJob job, const Ax
     constexpr int ROWS = NT * NL;
     constexpr int NWARP = NT / 32;
     int local;
-    const PlaneJob& pj = find_plane(job, blockIdx.x, local);
+    const PlaneJob& pj = find_plane(job, blockIdx.y, local);
     const int row0 = local * ROWS;
     const int nrows = min(ROWS, pj.h - row0);
-    const char* src = job.src + (size_t)blockIdx.y * job.src_fs + pj.src_off + (size_t)row0 * pj.src_pitch;
-    char* dst = job.dst + (size_t)blockIdx.y * job.dst_fs + pj.dst_off + (size_t)row0 * pj.dst_pitch;
+    const char* src = job.src + (size_t)blockIdx.x * job.src_fs + pj.src_off + (size_t)row0 * pj.src_pitch;
+    char* dst = job.dst + (size_t)blockIdx.x * job.dst_fs + pj.dst_off + (size_t)row0 * pj.dst_pitch;
     const int sp = pj.src_pitch, dp = pj.dst_pitch;
 
     uint32_t* ring = smem;
@@ -979,7 +979,9 @@ static int launch_v(const FrameLayout& l, const bool mask[3], const char* src, s
         const int nf = std::min(65535, count - f0);
         BatchJob j = job;
         j.src += (size_t)f0 * src_fs; j.dst += (size_t)f0 * dst_fs;
-        kern<<<dim3(job.ctas_per_frame, nf), NT, smem, st>>>(j, ap);
+        // grid.x = frame, grid.y = CTA within the frame: CTAs are scheduled x-fastest, so every frame's (long) luma CTAs
+        // start before any (short) chroma CTA and the tail of the launch is made of short CTAs
+        kern<<<dim3(nf, job.ctas_per_frame), NT, smem, st>>>(j, ap);
         count_launch();
     }
     VSZ_CUDA(cudaGetLastError());
@@ -1003,7 +1005,7 @@ static int launch_h(const FrameLayout& l, const bool mask[3], const char* src, s
         const int nf = std::min(65535, count - f0);
         BatchJob j = job;
         j.src += (size_t)f0 * src_fs; j.dst += (size_t)f0 * dst_fs;
-        kern<<<dim3(job.ctas_per_frame, nf), NT_H, smem, st>>>(j, ap);
+        kern<<<dim3(nf, job.ctas_per_frame), NT_H, smem, st>>>(j, ap);  // see launch_v for the grid order
         count_launch();
     }
     VSZ_CUDA(cudaGetLastError());

@@ -114,9 +114,8 @@ template <typename T> __device__ __forceinline__ double abs_diff(T a, T b, unsig
 template <typename T> __device__ __forceinline__ unsigned int bin_of(T v) {
     if constexpr (El<T>::flt) {
         const float f = __fadd_rn(__fmul_rn(as_float<T>(v), 65535.0f), 0.5f);
-        if (!(f > 0.0f)) return 0u;  // NaN and <= 0
-        if (f >= 65535.0f) return 65535u;
-        return (unsigned int)f;
+        // NaN and <= 0 -> 0 (fmaxf returns the non-NaN operand), >= 65535 -> 65535, else truncation: two FMNMX + F2I
+        return __float2uint_rz(fminf(fmaxf(f, 0.0f), 65535.0f));
     } else {
         return (unsigned int)v;
     }
