@@ -37,7 +37,12 @@ if lf.exists():
     shutil.copy(lf, P / f"launches_{R}.csv")
 
 # ---- ncu --set full summaries
+# (gpu_round.sh already summarises the captures on the box; a .ncu-rep that travelled back is summarised here)
+for md in sorted(G.glob(f"ncu_*_{R}.md")):
+    (P / md.name).write_text(f"# {md.stem}.ncu-rep (ncu --set full --clock-control none)\n\n" + md.read_text())
 for rep in sorted(G.glob(f"ncu_*_{R}.ncu-rep")):
+    if (G / (rep.stem + ".md")).exists():
+        continue
     out = subprocess.run([sys.executable, str(ROOT / "scripts" / "ncu_summary.py"), str(rep)], capture_output=True, text=True).stdout
     (P / (rep.stem + ".md")).write_text(f"# {rep.name} (ncu --set full --clock-control none)\n\n" + out)
 print("profiles updated:", sorted(p.name for p in P.iterdir()))
