@@ -339,15 +339,16 @@ __global__ void __launch_bounds__(NT) average_u16_kernel(const StatsJob j) {
             for (int g = 0; g < G; ++g) av[g] = __ldg(reinterpret_cast<const uint4*>(a + (size_t)min(y + g, y1 - 1) * p.a_pitch) + v);
 #pragma unroll
             for (int g = 0; g < G; ++g) {
-                if (y + g >= y1) break;
-                const unsigned int w[4] = {av[g].x, av[g].y, av[g].z, av[g].w};
+                if (y + g < y1) {
+                    const unsigned int w[4] = {av[g].x, av[g].y, av[g].z, av[g].w};
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    s32 = __dp2a_lo(w[q], 0x0101u, s32);
+                    for (int q = 0; q < 4; ++q) {
+                        s32 = __dp2a_lo(w[q], 0x0101u, s32);
 #pragma unroll
-                    for (int e = 0; e < NEX; ++e) pk[e] += __vminu2(w[q] ^ ee[e], 0x10001u);
+                        for (int e = 0; e < NEX; ++e) pk[e] += __vminu2(w[q] ^ ee[e], 0x10001u);
+                    }
+                    seen += 8u;
                 }
-                seen += 8u;
             }
         }
         const int x = nvec * 8 + threadIdx.x;  // scalar tail of each row
@@ -969,6 +970,8 @@ static StatsJob make_job(const FrameLayout& l, const bool mask[3], const char* a
         // per-thread u32 partial sums
         const long long px = (long long)s.w * s.h;
         int n = (int)std::min<long long>(MAX_CTAS_PER_PLANE, std::max<long long>(1, (px + 32767) / 32768));
+        // once the batch alone fills the GPU many times over, 4x longer CTAs amortise the per-CTA reduction epilogue
+        if ((long long)count * n >= 4096) n = std::max(1, n / 4);
         n = std::min(n, s.h);
         s.cta_begin = cta; s.nctas = n;
         cta += n;
@@ -983,8 +986,7 @@ static StatsJob make_job(const FrameLayout& l, const bool mask[3], const char* a
         s.s_nctas = (int)std::min<long long>(16, std::max<long long>(1, nsl / (NT / 8 * 8)));
         s.s_cta_begin = scta;
         scta += s.s_nctas;
-        // bracket kernel: 4x longer CTAs once the batch alone fills the GPU several times over
-        s.b_nctas = (long long)count * n >= 4096 ? std::max(1, n / 4) : n;
+        s.b_nctas = n;  // the bracket kernel keeps its own plane map (historical; same partition as the other kernels now)
         s.b_cta_begin = bcta;
         bcta += s.b_nctas;
     }

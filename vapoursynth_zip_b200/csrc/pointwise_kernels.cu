@@ -13,7 +13,7 @@ struct LimiterParams {
     uint32_t lo_w[3], hi_w[3];  // bounds replicated into a 32-bit word of samples (u8 x4, u16 x2, f16 x2, f32 x1)
 };
 
-static constexpr int LNT = 256, LROWS = 4;
+static constexpr int LNT = 256, LROWS = 4, LGROUPS = 4;  // a CTA streams LGROUPS groups of LROWS rows
 
 template <typename T> __device__ __forceinline__ uint32_t clamp_word(uint32_t x, uint32_t lo, uint32_t hi);
 template <> __device__ __forceinline__ uint32_t clamp_word<uint8_t>(uint32_t x, uint32_t lo, uint32_t hi) { return __vminu4(__vmaxu4(lo, x), hi); }
@@ -33,12 +33,13 @@ __global__ void __launch_bounds__(LNT) limiter_kernel(const BatchJob job, const 
     while (k > 0 && (int)blockIdx.x < job.pl[k].cta_begin) --k;
     const PlaneJob& pj = job.pl[k];
     const int local = (int)blockIdx.x - pj.cta_begin;
-    const int y0 = local * LROWS;
+    const int yc = local * (LROWS * LGROUPS);
     const char* src = job.src + (size_t)blockIdx.y * job.src_fs + pj.src_off;
     char* dst = job.dst + (size_t)blockIdx.y * job.dst_fs + pj.dst_off;
     const uint32_t lo = prm.lo_w[pj.aux], hi = prm.hi_w[pj.aux];
     const int row_bytes = pj.w * (int)sizeof(T);
     const int nvec = row_bytes / 16;
+    for (int y0 = yc; y0 < min(yc + LROWS * LGROUPS, pj.h); y0 += LROWS) {
     for (int v = threadIdx.x; v < nvec; v += LNT) {
         uint4 x[LROWS];
 #pragma unroll
@@ -48,11 +49,12 @@ __global__ void __launch_bounds__(LNT) limiter_kernel(const BatchJob job, const 
         }
 #pragma unroll
         for (int r = 0; r < LROWS; ++r) {
-            if (y0 + r >= pj.h) break;
-            uint4 o;
-            o.x = clamp_word<T>(x[r].x, lo, hi); o.y = clamp_word<T>(x[r].y, lo, hi);
-            o.z = clamp_word<T>(x[r].z, lo, hi); o.w = clamp_word<T>(x[r].w, lo, hi);
-            reinterpret_cast<uint4*>(dst + (size_t)(y0 + r) * pj.dst_pitch)[v] = o;
+            if (y0 + r < pj.h) {  // (a `break` here would keep the loop from unrolling and serialise the loads)
+                uint4 o;
+                o.x = clamp_word<T>(x[r].x, lo, hi); o.y = clamp_word<T>(x[r].y, lo, hi);
+                o.z = clamp_word<T>(x[r].z, lo, hi); o.w = clamp_word<T>(x[r].w, lo, hi);
+                reinterpret_cast<uint4*>(dst + (size_t)(y0 + r) * pj.dst_pitch)[v] = o;
+            }
         }
     }
     // row tails (< 16 bytes): one sample per thread
@@ -67,6 +69,7 @@ __global__ void __launch_bounds__(LNT) limiter_kernel(const BatchJob job, const 
             const uint32_t o = clamp_word<T>(wv, lo, hi);
             reinterpret_cast<T*>(dst + (size_t)(y0 + r) * pj.dst_pitch)[x0] = reinterpret_cast<const T*>(&o)[0];
         }
+    }
     }
 }
 
@@ -87,7 +90,7 @@ static int launch_limiter_t(const BatchJob& job, const LimiterParams& prm, int c
 int run_limiter(const FrameLayout& l, const bool mask[3], const char* src, size_t src_fs, char* dst, size_t dst_fs, int count,
                 const double lo[3], const double hi[3], cudaStream_t st) {
     if (count <= 0) return 0;
-    BatchJob job = make_batch(l, mask, src, src_fs, nullptr, 0, dst, dst_fs, [](int, int h) { return (h + LROWS - 1) / LROWS; });
+    BatchJob job = make_batch(l, mask, src, src_fs, nullptr, 0, dst, dst_fs, [](int, int h) { return (h + LROWS * LGROUPS - 1) / (LROWS * LGROUPS); });
     if (job.ctas_per_frame == 0) return 0;
     LimiterParams prm{};
     for (int p = 0; p < 3; ++p) {
