@@ -122,18 +122,54 @@ __global__ void __launch_bounds__(TW * TH) bilateral_kernel(const BatchJob job, 
     const float top = (float)(pp.lut_len - 1);
 
     const int tile_end = min((sx + 1) * prm.strip, prm.tiles_x[k]);
+    // compile-time tap patterns: the tile size is a constant, so the NEXT tile's samples are fetched into registers
+    // before the current tile's math (their latency is covered by ~300 instructions per pixel) and only written to
+    // shared memory at the top of the next iteration
+    constexpr int TSIZE_C = FIXED ? (TILE + 2 * (1 + (SAMPLES - 1) * STEP)) * (TILE + 2 * (1 + (SAMPLES - 1) * STEP)) : 1;
+    constexpr int NPT = FIXED ? (TSIZE_C + TW * TH - 1) / (TW * TH) : 1;
+    T pre_s[NPT], pre_r[JOINT ? NPT : 1];
+    auto fetch_tile = [&](int tx) {
+        const int x0 = tx * TILE;
+#pragma unroll
+        for (int i = 0; i < NPT; ++i) {
+            const int e = tid + i * (TW * TH);
+            if (e < tsize) {
+                const int ly = (int)(((uint32_t)e * inv_tw) >> 20), lx = e - ly * tw;
+                const int gy = min(max(y0 + ly - r, 0), pj.h - 1), gx = min(max(x0 + lx - r, 0), pj.w - 1);
+                pre_s[i] = reinterpret_cast<const T*>(src + (size_t)gy * pj.src_pitch)[gx];
+                if constexpr (JOINT) pre_r[i] = reinterpret_cast<const T*>(ref + (size_t)gy * pj.ref_pitch)[gx];
+            }
+        }
+    };
+    if constexpr (FIXED) fetch_tile(sx * prm.strip);
     for (int tx = sx * prm.strip; tx < tile_end; ++tx) {
         const int x0 = tx * TILE;
         __syncthreads();  // previous tile fully consumed (and the tables visible on the first pass)
         // tile + halo, widened to f32, replicate edges (src/filters/bilateral.zig:281-289)
-        for (int e = tid; e < tsize; e += TW * TH) {
-            const int ly = (int)(((uint32_t)e * inv_tw) >> 20), lx = e - ly * tw;
-            const int gy = min(max(y0 + ly - r, 0), pj.h - 1), gx = min(max(x0 + lx - r, 0), pj.w - 1);
-            const float sv = widen<T>(reinterpret_cast<const T*>(src + (size_t)gy * pj.src_pitch)[gx]);
-            s_src[e] = (WM == W_SCALED && !JOINT) ? __fmul_rn(sv, pp.scale) : sv;
-            if constexpr (JOINT) {
-                const float rv = widen<T>(reinterpret_cast<const T*>(ref + (size_t)gy * pj.ref_pitch)[gx]);
-                s_ref[e] = (WM == W_SCALED) ? __fmul_rn(rv, pp.scale) : rv;
+        if constexpr (FIXED) {
+#pragma unroll
+            for (int i = 0; i < NPT; ++i) {
+                const int e = tid + i * (TW * TH);
+                if (e < tsize) {
+                    const float sv = widen<T>(pre_s[i]);
+                    s_src[e] = (WM == W_SCALED && !JOINT) ? __fmul_rn(sv, pp.scale) : sv;
+                    if constexpr (JOINT) {
+                        const float rv = widen<T>(pre_r[i]);
+                        s_ref[e] = (WM == W_SCALED) ? __fmul_rn(rv, pp.scale) : rv;
+                    }
+                }
+            }
+            if (tx + 1 < tile_end) fetch_tile(tx + 1);
+        } else {
+            for (int e = tid; e < tsize; e += TW * TH) {
+                const int ly = (int)(((uint32_t)e * inv_tw) >> 20), lx = e - ly * tw;
+                const int gy = min(max(y0 + ly - r, 0), pj.h - 1), gx = min(max(x0 + lx - r, 0), pj.w - 1);
+                const float sv = widen<T>(reinterpret_cast<const T*>(src + (size_t)gy * pj.src_pitch)[gx]);
+                s_src[e] = (WM == W_SCALED && !JOINT) ? __fmul_rn(sv, pp.scale) : sv;
+                if constexpr (JOINT) {
+                    const float rv = widen<T>(reinterpret_cast<const T*>(ref + (size_t)gy * pj.ref_pitch)[gx]);
+                    s_ref[e] = (WM == W_SCALED) ? __fmul_rn(rv, pp.scale) : rv;
+                }
             }
         }
         __syncthreads();
@@ -253,8 +289,10 @@ static int run_bilateral_t(const FrameLayout& l, const bool mask[3], const char*
         const int r = pp.radius;
         // strip length: whole tile rows when the batch alone fills the GPU, shorter strips for single frames
         const int tiles_x = (l.pl[p].w + TILE - 1) / TILE, tiles_y = (l.pl[p].h + TILE - 1) / TILE;
+        // and never fewer than ~8 waves of CTAs (8 CTAs fit an SM), so that the last partial wave stays a small share
         int strip = tiles_x;
         while (strip > 1 && (long long)((tiles_x + strip - 1) / strip) * tiles_y * count < 4 * 148) strip = (strip + 1) / 2;
+        while (strip > 8 && (long long)((tiles_x + strip - 1) / strip) * tiles_y * count < 8ll * 8 * 148) strip = (strip + 1) / 2;
         const int strips_x = (tiles_x + strip - 1) / strip;
         prm.strip = strip;
         prm.tiles_x[0] = tiles_x;
