@@ -200,10 +200,17 @@ __global__ void __launch_bounds__(TW * TH) bilateral_kernel(const BatchJob job, 
                     g4 = range_weight<WM>(range_index_f<T>(cref, r4), top, pp, s_lut);
                 }
                 const float gsum = __fadd_rn(__fadd_rn(__fadd_rn(g1, g2), g3), g4);
-                wsum = __fadd_rn(wsum, __fmul_rn(sw, gsum));
-                const float p1 = __fmul_rn(v1, g1), p2 = __fmul_rn(v2, g2), p3 = __fmul_rn(v3, g3), p4 = __fmul_rn(v4, g4);
-                const float psum = __fadd_rn(__fadd_rn(__fadd_rn(p1, p2), p3), p4);
-                sum = __fadd_rn(sum, __fmul_rn(sw, psum));
+                if constexpr (WM == W_SCALED) {
+                    // computed weights are approximate anyway (<= 1 LSB bar): fused multiply-adds save 5 of 30 instructions
+                    wsum = __fmaf_rn(sw, gsum, wsum);
+                    const float psum = __fmaf_rn(v4, g4, __fmaf_rn(v3, g3, __fmaf_rn(v2, g2, __fmul_rn(v1, g1))));
+                    sum = __fmaf_rn(sw, psum, sum);
+                } else {
+                    wsum = __fadd_rn(wsum, __fmul_rn(sw, gsum));
+                    const float p1 = __fmul_rn(v1, g1), p2 = __fmul_rn(v2, g2), p3 = __fmul_rn(v3, g3), p4 = __fmul_rn(v4, g4);
+                    const float psum = __fadd_rn(__fadd_rn(__fadd_rn(p1, p2), p3), p4);
+                    sum = __fadd_rn(sum, __fmul_rn(sw, psum));
+                }
             };
             if constexpr (FIXED) {
 #pragma unroll
