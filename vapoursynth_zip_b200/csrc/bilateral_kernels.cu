@@ -128,16 +128,28 @@ __global__ void __launch_bounds__(TW * TH) bilateral_kernel(const BatchJob job, 
     constexpr int TSIZE_C = FIXED ? (TILE + 2 * (1 + (SAMPLES - 1) * STEP)) * (TILE + 2 * (1 + (SAMPLES - 1) * STEP)) : 1;
     constexpr int NPT = FIXED ? (TSIZE_C + TW * TH - 1) / (TW * TH) : 1;
     T pre_s[NPT], pre_r[JOINT ? NPT : 1];
+    // per-thread staging geometry is the same for every tile of the strip: the (edge-clamped) row offset and the
+    // column relative to the tile are computed once, a tile then costs an add, a clamp and the address per sample
+    int row_off[NPT], ref_off[JOINT ? NPT : 1], lxr[NPT];
+    if constexpr (FIXED) {
+#pragma unroll
+        for (int i = 0; i < NPT; ++i) {
+            const int e = min(tid + i * (TW * TH), tsize - 1);
+            const int ly = (int)(((uint32_t)e * inv_tw) >> 20);
+            lxr[i] = e - ly * tw - r;
+            const int gy = min(max(y0 + ly - r, 0), pj.h - 1);
+            row_off[i] = gy * pj.src_pitch;
+            if constexpr (JOINT) ref_off[i] = gy * pj.ref_pitch;
+        }
+    }
     auto fetch_tile = [&](int tx) {
         const int x0 = tx * TILE;
 #pragma unroll
         for (int i = 0; i < NPT; ++i) {
-            const int e = tid + i * (TW * TH);
-            if (e < tsize) {
-                const int ly = (int)(((uint32_t)e * inv_tw) >> 20), lx = e - ly * tw;
-                const int gy = min(max(y0 + ly - r, 0), pj.h - 1), gx = min(max(x0 + lx - r, 0), pj.w - 1);
-                pre_s[i] = reinterpret_cast<const T*>(src + (size_t)gy * pj.src_pitch)[gx];
-                if constexpr (JOINT) pre_r[i] = reinterpret_cast<const T*>(ref + (size_t)gy * pj.ref_pitch)[gx];
+            if (tid + i * (TW * TH) < tsize) {
+                const int gx = min(max(x0 + lxr[i], 0), pj.w - 1);
+                pre_s[i] = reinterpret_cast<const T*>(src + row_off[i])[gx];
+                if constexpr (JOINT) pre_r[i] = reinterpret_cast<const T*>(ref + ref_off[i])[gx];
             }
         }
     };
