@@ -128,6 +128,13 @@ __global__ void __launch_bounds__(TW * TH) bilateral_kernel(const BatchJob job, 
     constexpr int TSIZE_C = FIXED ? (TILE + 2 * (1 + (SAMPLES - 1) * STEP)) * (TILE + 2 * (1 + (SAMPLES - 1) * STEP)) : 1;
     constexpr int NPT = FIXED ? (TSIZE_C + TW * TH - 1) / (TW * TH) : 1;
     T pre_s[NPT], pre_r[JOINT ? NPT : 1];
+    float sw_reg[FIXED ? SAMPLES : 1][FIXED ? SAMPLES : 1];  // the spatial weights of the pattern live in registers
+    if constexpr (FIXED) {
+#pragma unroll
+        for (int a = 0; a < SAMPLES; ++a)
+#pragma unroll
+            for (int b = 0; b < SAMPLES; ++b) sw_reg[a][b] = __ldg(pp.gs + (1 + a * STEP) * r2 + (1 + b * STEP));
+    }
     // per-thread staging geometry is the same for every tile of the strip: the (edge-clamped) row offset and the
     // column relative to the tile are computed once, a tile then costs an add, a clamp and the address per sample
     int row_off[NPT], ref_off[JOINT ? NPT : 1], lxr[NPT];
@@ -194,9 +201,8 @@ __global__ void __launch_bounds__(TW * TH) bilateral_kernel(const BatchJob job, 
             const float cref = s_ref[cxy];
             float wsum = (WM == W_SCALED) ? s_gs[0] : __fmul_rn(s_gs[0], range_weight<WM == W_SCALED ? W_COMPUTE : WM>(0.0f, top, pp, s_lut));
             float sum = __fmul_rn(s_src[cxy], wsum);
-            auto taps = [&](int yy, int xx) {
+            auto taps = [&](int yy, int xx, float sw) {
                 const int up = cxy - yy * tw, dn = cxy + yy * tw;
-                const float sw = s_gs[yy * r2 + xx];
                 const float r1 = s_ref[up + xx], r2v = s_ref[dn + xx], r3 = s_ref[up - xx], r4 = s_ref[dn - xx];
                 const float v1 = JOINT ? s_src[up + xx] : r1, v2 = JOINT ? s_src[dn + xx] : r2v;
                 const float v3 = JOINT ? s_src[up - xx] : r3, v4 = JOINT ? s_src[dn - xx] : r4;
@@ -228,10 +234,10 @@ __global__ void __launch_bounds__(TW * TH) bilateral_kernel(const BatchJob job, 
 #pragma unroll
                 for (int a = 0; a < SAMPLES; ++a)
 #pragma unroll
-                    for (int b = 0; b < SAMPLES; ++b) taps(1 + a * STEP, 1 + b * STEP);
+                    for (int b = 0; b < SAMPLES; ++b) taps(1 + a * STEP, 1 + b * STEP, sw_reg[a][b]);
             } else {
                 for (int yy = 1; yy < r2; yy += step)
-                    for (int xx = 1; xx < r2; xx += step) taps(yy, xx);
+                    for (int xx = 1; xx < r2; xx += step) taps(yy, xx, s_gs[yy * r2 + xx]);
             }
             float q = __fdiv_rn(sum, wsum);
             if constexpr (WM == W_SCALED && !JOINT) q = __fmul_rn(q, pp.inv_scale);  // the values were staged scaled
