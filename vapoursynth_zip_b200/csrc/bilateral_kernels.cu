@@ -239,8 +239,16 @@ __global__ void __launch_bounds__(TW * TH) bilateral_kernel(const BatchJob job, 
                 for (int yy = 1; yy < r2; yy += step)
                     for (int xx = 1; xx < r2; xx += step) taps(yy, xx, s_gs[yy * r2 + xx]);
             }
-            float q = __fdiv_rn(sum, wsum);
-            if constexpr (WM == W_SCALED && !JOINT) q = __fmul_rn(q, pp.inv_scale);  // the values were staged scaled
+            float q;
+            if constexpr (WM == W_SCALED) {
+                // approximate-weights mode: reciprocal on the MUFU unit (2 ulp) instead of the IEEE divide sequence;
+                // non-joint values were staged scaled, so the scale goes back in here
+                float rw;
+                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rw) : "f"(wsum));
+                q = __fmul_rn(sum, JOINT ? rw : __fmul_rn(rw, pp.inv_scale));
+            } else {
+                q = __fdiv_rn(sum, wsum);
+            }
             T* out = reinterpret_cast<T*>(dst + (size_t)y * pj.dst_pitch) + x;
             if constexpr (std::is_same<T, float>::value) *out = q;
             else if constexpr (std::is_same<T, __half>::value) *out = __float2half_rn(q);
