@@ -522,7 +522,14 @@ __global__ void __launch_bounds__(NT) blur_v_kernel(const BatchJob job, const Ax
         const char* fsrc = src + (size_t)(t + ST::AHEAD) * sp;  // next row to prefetch
         char* fdst = dst + (size_t)(t - lag) * dp;              // next row to store
         int sr = (int)((unsigned)t % (unsigned)ST::SLOTS), sf = (int)((unsigned)(t + ST::AHEAD) % (unsigned)ST::SLOTS);  // running slots
+        // 1-3 fused passes are close to memory-bound: an L2 prefetch 24 rows further ahead lets the cp.async find its line
+        // in L2 instead of HBM (V1 -6 %, V2 -12 %); with 4-5 passes the kernel is issue-bound and the extra instruction only costs
+        constexpr int L2_AHEAD = 24;
         for (; t + ST::AHEAD + U <= n; t += U) {
+            if (P <= 3 && t + ST::AHEAD + U + L2_AHEAD <= n) {
+#pragma unroll
+                for (int i = 0; i < U; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(fsrc + (size_t)(L2_AHEAD + i) * sp));
+            }
 #pragma unroll
             for (int i = 0; i < U; ++i) {
                 cp_async<4 * W>(&slot_at(sf), fsrc);
