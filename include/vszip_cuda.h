@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define VSZIP_CUDA_ABI_VERSION 2  /* 2: + vszip_chain_*, vszip_limiter_* */
+#define VSZIP_CUDA_ABI_VERSION 3  /* 2: + vszip_chain_*, vszip_limiter_*; 3: + vszip_limitfilter_*, vszip_adaptivebinarize_* */
 
 /* VapourSynth4.h values (VSColorFamily / VSSampleType) so the Zig glue can pass vi.format as is. */
 enum { VSZIP_CF_GRAY = 1, VSZIP_CF_RGB = 2, VSZIP_CF_YUV = 3 };
@@ -176,6 +176,41 @@ typedef struct vszip_limiter_args {
 vszip_filter* vszip_limiter_create(const vszip_video_info* vi, const vszip_limiter_args* args);
 int vszip_limiter_get_frame(const vszip_filter* f, int32_t n, const vszip_frame* src, vszip_frame* dst);
 
+/* ------------------------------------------------------------------ LimitFilter
+ * replaces limitFilterCreate / LimitFilter.getFrame (src/vapoursynth/limit_filter.zig:27-124) and
+ * src/filters/limit_filter.zig:3-34.  Argument string kept:
+ * "flt:vnode;src:vnode;ref:vnode:opt;dark_thr:float[]:opt;bright_thr:float[]:opt;elast:float[]:opt;planes:int[]:opt;"
+ * num_* = element count of each array key (0 = absent; planes: < 0 = absent).
+ * color_range: what hz.getColorRange(flt) returned on the Zig side (src/helper.zig:259-276: frame 0's _ColorRange,
+ * 0 = full, 1 = limited); < 0 = "prop absent", resolved here like the reference (RGB -> full, else limited).  It only
+ * matters for the 8-bit -> clip-depth scaling of dark_thr / bright_thr (hz.scaleValue, src/helper.zig:312-338). */
+typedef struct vszip_limitfilter_args {
+    const double* dark_thr; int32_t num_dark_thr;
+    const double* bright_thr; int32_t num_bright_thr;
+    const double* elast; int32_t num_elast;
+    const int64_t* planes; int32_t num_planes;
+    int32_t color_range;
+} vszip_limitfilter_args;
+/* src_vi is required, ref_vi == NULL: no ref clip (the difference is judged against src). */
+vszip_filter* vszip_limitfilter_create(const vszip_video_info* flt_vi, const vszip_video_info* src_vi,
+                                       const vszip_video_info* ref_vi, const vszip_limitfilter_args* args);
+int vszip_limitfilter_get_frame(const vszip_filter* f, int32_t n, const vszip_frame* flt, const vszip_frame* src,
+                                const vszip_frame* ref /* NULL unless created with ref_vi */, vszip_frame* dst);
+/* Thresholds after scaling, as the kernel uses them (for inspection/tests). */
+int vszip_limitfilter_get_info(const vszip_filter* f, float dark_thr[3], float bright_thr[3], float elast[3]);
+
+/* ------------------------------------------------------------------ AdaptiveBinarize
+ * replaces adaptiveBinarizeCreate / adaptiveBinarizeGetFrame (src/vapoursynth/adaptive_binarize.zig:28-116):
+ * every plane, dst = 255 where clip2 - clip >= c else 0, 8-bit integer clips only; the Zig side keeps setting
+ * _ColorRange = full on the output frame.  Argument string kept: "clip:vnode;clip2:vnode;c:int:opt;". */
+typedef struct vszip_adaptivebinarize_args {
+    int32_t has_c; int64_t c;
+} vszip_adaptivebinarize_args;
+vszip_filter* vszip_adaptivebinarize_create(const vszip_video_info* vi, const vszip_video_info* clip2_vi,
+                                            const vszip_adaptivebinarize_args* args);
+int vszip_adaptivebinarize_get_frame(const vszip_filter* f, int32_t n, const vszip_frame* clip, const vszip_frame* clip2,
+                                     vszip_frame* dst);
+
 /* ------------------------------------------------------------------ common filter calls */
 void vszip_filter_free(vszip_filter* f);                         /* replaces xxxFree */
 int vszip_filter_planes(const vszip_filter* f, int32_t process[3]); /* d.planes after create */
@@ -213,6 +248,10 @@ int vszip_planeaverage_device(const vszip_filter* f, const vszip_dev_clip* clipa
                               int32_t first, int32_t count, vszip_average_props* out, void* stream);
 int vszip_limiter_device(const vszip_filter* f, const vszip_dev_clip* src, vszip_dev_clip* dst,
                          int32_t first, int32_t count, void* stream);
+int vszip_limitfilter_device(const vszip_filter* f, const vszip_dev_clip* flt, const vszip_dev_clip* src,
+                             const vszip_dev_clip* ref, vszip_dev_clip* dst, int32_t first, int32_t count, void* stream);
+int vszip_adaptivebinarize_device(const vszip_filter* f, const vszip_dev_clip* clip, const vszip_dev_clip* clip2,
+                                  vszip_dev_clip* dst, int32_t first, int32_t count, void* stream);
 int vszip_cuda_stream_sync(int32_t device, void* stream);
 
 /* ------------------------------------------------------------------ fused chains of vszip filters

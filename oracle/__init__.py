@@ -64,6 +64,8 @@ def lib():
         _lib.vso_recursive_gaussian_params.argtypes = [C.c_double, C.c_void_p]
         _lib.vso_recursive_gaussian_params.restype = None
         _lib.vso_limiter_plane.argtypes = [C.c_int, C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_ssize_t, C.c_int, C.c_int, C.c_double, C.c_double]
+        _lib.vso_limitfilter_plane.argtypes = [C.c_int] + [C.c_void_p, C.c_ssize_t] * 4 + [C.c_int, C.c_int, C.c_float, C.c_float, C.c_float]
+        _lib.vso_adaptive_binarize_plane.argtypes = [C.c_void_p, C.c_ssize_t] * 3 + [C.c_int] * 3
         _lib.vso_bilateral_luts.argtypes = [C.c_double, C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         _lib.vso_bilateral_luts.restype = None
         _lib.vso_planeminmax_plane.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_ssize_t, C.c_int, C.c_int,
@@ -170,6 +172,31 @@ def limiter_plane(src: np.ndarray, lo: float, hi: float) -> np.ndarray:
     dst = np.empty_like(src, order="C")
     h, w = src.shape
     rc = lib().vso_limiter_plane(sample_type_of(src), _p(src), src.strides[0], _p(dst), dst.strides[0], w, h, float(lo), float(hi))
+    assert rc == 0
+    return dst
+
+
+def limitfilter_plane(flt: np.ndarray, src: np.ndarray, ref: np.ndarray | None, dark_thr: float, bright_thr: float, elast: float) -> np.ndarray:
+    """src/filters/limit_filter.zig:3-34; thresholds already scaled to the clip's depth."""
+    _chk2d(flt); _chk2d(src)
+    ref = src if ref is None else ref
+    _chk2d(ref)
+    assert flt.shape == src.shape == ref.shape and flt.dtype == src.dtype == ref.dtype
+    dst = np.empty_like(flt, order="C")
+    h, w = flt.shape
+    rc = lib().vso_limitfilter_plane(sample_type_of(flt), _p(flt), flt.strides[0], _p(src), src.strides[0], _p(ref), ref.strides[0],
+                                     _p(dst), dst.strides[0], w, h, float(dark_thr), float(bright_thr), float(elast))
+    assert rc == 0
+    return dst
+
+
+def adaptive_binarize_plane(a: np.ndarray, b: np.ndarray, c: int) -> np.ndarray:
+    """src/vapoursynth/adaptive_binarize.zig:48-60: 255 where b - a >= c."""
+    _chk2d(a); _chk2d(b)
+    assert a.dtype == np.uint8 and b.dtype == np.uint8 and a.shape == b.shape
+    dst = np.empty_like(a, order="C")
+    h, w = a.shape
+    rc = lib().vso_adaptive_binarize_plane(_p(a), a.strides[0], _p(b), b.strides[0], _p(dst), dst.strides[0], w, h, int(c))
     assert rc == 0
     return dst
 

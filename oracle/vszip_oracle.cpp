@@ -459,6 +459,44 @@ void limiter_plane_t(const void* src, ptrdiff_t sst, void* dst, ptrdiff_t dstt, 
 }
 
 // ---------------------------------------------------------------------------
+// LimitFilter (src/filters/limit_filter.zig:3-34): soft limit of flt towards src, judged on |flt - ref| in f32
+// ---------------------------------------------------------------------------
+template <class T>
+void limitfilter_plane_t(const void* flt, ptrdiff_t fst, const void* src, ptrdiff_t sst, const void* ref, ptrdiff_t rst, void* dst,
+                         ptrdiff_t dstt, int w, int h, float dark_thr, float bright_thr, float elast) {
+    for (int y = 0; y < h; ++y) {
+        const T* fp = row_ptr<T>(flt, fst, y);
+        const T* sp = row_ptr<T>(src, sst, y);
+        const T* rp = row_ptr<T>(ref, rst, y);
+        T* dp = row_ptr<T>(dst, dstt, y);
+        for (int x = 0; x < w; ++x) {
+            const float ff = (float)fp[x], sf = (float)sp[x], rf = (float)rp[x];
+            const float d = ff - rf;
+            const float ad = std::fabs(d);
+            const float t1 = d > 0.0f ? bright_thr : dark_thr;
+            const float t2 = t1 * elast;
+            float o;
+            if (ad <= t1) o = ff;                 // inside the threshold: keep the filtered sample
+            else if (ad >= t2) o = sf;            // beyond thr * elast: back to the source
+            else {
+                const float num = (ff - sf) * (t2 - ad);
+                o = sf + num / (t2 - t1);
+            }
+            if (is_flt<T>::value) dp[x] = (T)o;
+            else dp[x] = (T)(int32_t)std::trunc(o + 0.5f);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// AdaptiveBinarize (src/vapoursynth/adaptive_binarize.zig:48-60): 255 where clip2 - clip >= c, else 0 (8-bit only)
+// ---------------------------------------------------------------------------
+void adaptive_binarize_plane(const uint8_t* a, ptrdiff_t ast, const uint8_t* b, ptrdiff_t bst, uint8_t* dst, ptrdiff_t dstt, int w, int h, int c) {
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) dst[dstt * y + x] = ((int)b[bst * y + x] - (int)a[ast * y + x] >= c) ? 255 : 0;
+}
+
+// ---------------------------------------------------------------------------
 // PlaneMinMax / PlaneAverage
 // ---------------------------------------------------------------------------
 
@@ -742,6 +780,22 @@ int vso_limiter_plane(int st, const void* src, ptrdiff_t sstride, void* dst, ptr
         case ST_F32: limiter_plane_t<float>(src, sstride, dst, dstride, w, h, lo, hi); return 0;
     }
     return -1;
+}
+
+int vso_limitfilter_plane(int st, const void* flt, ptrdiff_t fst, const void* src, ptrdiff_t sst, const void* ref, ptrdiff_t rst, void* dst,
+                          ptrdiff_t dstt, int w, int h, float dark_thr, float bright_thr, float elast) {
+    switch (st) {
+        case ST_U8: limitfilter_plane_t<uint8_t>(flt, fst, src, sst, ref, rst, dst, dstt, w, h, dark_thr, bright_thr, elast); return 0;
+        case ST_U16: limitfilter_plane_t<uint16_t>(flt, fst, src, sst, ref, rst, dst, dstt, w, h, dark_thr, bright_thr, elast); return 0;
+        case ST_F16: limitfilter_plane_t<f16>(flt, fst, src, sst, ref, rst, dst, dstt, w, h, dark_thr, bright_thr, elast); return 0;
+        case ST_F32: limitfilter_plane_t<float>(flt, fst, src, sst, ref, rst, dst, dstt, w, h, dark_thr, bright_thr, elast); return 0;
+    }
+    return -1;
+}
+
+int vso_adaptive_binarize_plane(const void* a, ptrdiff_t ast, const void* b, ptrdiff_t bst, void* dst, ptrdiff_t dstt, int w, int h, int c) {
+    adaptive_binarize_plane((const uint8_t*)a, ast, (const uint8_t*)b, bst, (uint8_t*)dst, dstt, w, h, c);
+    return 0;
 }
 
 struct vso_minmax_out { long long imin, imax; double fmin, fmax, diff; };

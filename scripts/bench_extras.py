@@ -58,6 +58,17 @@ def pixel_cfg(name, fmt, w, h, frames, make_filter, noise=True):
     src.free(); dst.free()
 
 
+def multi_cfg(name, fmt, w, h, frames, nin, run):
+    """pointwise filters with several input clips: algorithmic bytes = nin reads + 1 write per sample"""
+    clips = [vz.DeviceClip(fmt, w, h, frames) for _ in range(nin + 1)]
+    for i, c in enumerate(clips[:nin]):
+        c.fill_noise(1234 + i)
+    ms = timed(lambda: run(clips), args.reps)
+    record(name, fmt, w, h, frames, (nin + 1) * clips[0].frame_bytes, ms)
+    for c in clips:
+        c.free()
+
+
 def stats_cfg(name, fmt, w, h, frames, make_filter):
     src = vz.DeviceClip(fmt, w, h, frames)
     src.fill_noise(1234)
@@ -81,6 +92,13 @@ pixel_cfg("C3' Bilateral default sigmaR=0.02 (exact smem LUT)", "YUV420P16", 192
 pixel_cfg("C3'' Bilateral(sigmaS=8, sigmaR=0.1): PBFIC luma (num=4) + alg 2 chroma", "YUV420P16", 1920, 1080, min(N, 32), lambda s: vz.BilateralFilter(s.info(), sigmaS=8, sigmaR=0.1, planes=[0, 1, 2]))
 pixel_cfg("C3'' Bilateral(sigmaS=3, sigmaR=0.02, algorithm=1): PBFIC num=12/13", "YUV420P16", 1920, 1080, min(N, 32), lambda s: vz.BilateralFilter(s.info(), sigmaS=3, sigmaR=0.02, algorithm=1, planes=[0, 1, 2]))
 pixel_cfg("C6 Limiter(tv_range=True) (pointwise neighbour, 8f rank 3)", "YUV420P16", 1920, 1080, N, lambda s: vz.LimiterFilter(s.info(), tv_range=True))
+_lf = {}
+multi_cfg("C7 LimitFilter(flt, src, dark_thr=8, bright_thr=8, elast=3) (8f rank 3)", "YUV420P16", 1920, 1080, N, 2,
+          lambda c: _lf.setdefault("a", vz.LimitFilterFilter(c[0].info(), c[0].info(), None, dark_thr=8, bright_thr=8, elast=3)).run_device(c[0], c[1], c[2], count=N, stream=st.cuda_stream))
+multi_cfg("C7 LimitFilter(flt, src, ref, ...) three inputs", "YUV420P16", 1920, 1080, N, 3,
+          lambda c: _lf.setdefault("b", vz.LimitFilterFilter(c[0].info(), c[0].info(), c[0].info(), dark_thr=8, bright_thr=8, elast=3)).run_device(c[0], c[1], c[3], ref=c[2], count=N, stream=st.cuda_stream))
+multi_cfg("C8 AdaptiveBinarize(clip, clip2, c=3) YUV420P8 (8f rank 3)", "YUV420P8", 1920, 1080, N, 2,
+          lambda c: _lf.setdefault("c", vz.AdaptiveBinarizeFilter(c[0].info(), c[0].info(), c=3)).run_device(c[0], c[1], c[2], count=N, stream=st.cuda_stream))
 M = max(8, N // 2)
 stats_cfg("C4 PlaneMinMax(minthr=.1,maxthr=.1) GRAY16 4K", "GRAY16", 3840, 2160, M, lambda s: vz.PlaneMinMaxFilter(s.info(), minthr=0.1, maxthr=0.1))
 stats_cfg("C4 PlaneMinMax(minthr=.1,maxthr=.1) GRAYS 4K", "GRAYS", 3840, 2160, M, lambda s: vz.PlaneMinMaxFilter(s.info(), minthr=0.1, maxthr=0.1))

@@ -5,7 +5,8 @@
 Outputs (committed, MIT-licensed test data from dnjulek/vapoursynth-zip):
   src_rgb_640x320.png   the reference suite's source fixture: tests/image.png cropped exactly
                         like tests/conftest.py:72-76 (left = width-640, bottom = height-320)
-  boxblur.json, bilateral.json, planeminmax.json, planeaverage.json, limiter.json
+  boxblur.json, bilateral.json, planeminmax.json, planeaverage.json, limiter.json, limitfilter.json,
+  adaptive_binarize.json
                         verbatim copies of tests/goldens/<name>.json (per-plane PlaneStats /
                         frame-prop snapshots recorded from the real Zig plugin)
 The GPU box has no /root/reference, so the tests only ever read these copies.
@@ -26,7 +27,7 @@ crop = im.crop((w - 640, 0, w, 320))  # Crop(left=w-640, bottom=h-320) keeps row
 assert crop.size == (640, 320)
 crop.save(out / "src_rgb_640x320.png", optimize=True)
 
-for name in ("boxblur", "bilateral", "planeminmax", "planeaverage", "limiter"):
+for name in ("boxblur", "bilateral", "planeminmax", "planeaverage", "limiter", "limitfilter", "adaptive_binarize"):
     data = json.loads((ref / "tests" / "goldens" / f"{name}.json").read_text())
     (out / f"{name}.json").write_text(json.dumps(data, indent=1, sort_keys=True) + "\n")
     print(name, len(data), "keys")

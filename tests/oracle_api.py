@@ -78,6 +78,59 @@ def limiter(clip, min=None, max=None, tv_range=False, mask=False, planes=None):
     return {"format": clip["format"], "planes": out}
 
 
+def scale_value(value, fam, st, bits, color_range=None):
+    """hz.scaleValue(value, node, {depth_in=8, Integer, chroma=false}) (src/helper.zig:312-338), f32 arithmetic.
+    color_range: 0 full / 1 limited as in frame 0's _ColorRange, None = prop absent (RGB -> full, else limited; helper.zig:259-276)."""
+    f32 = np.float32
+    v = f32(value)
+    if bits == 8:
+        return float(v)
+    limited = (fam != "RGB") if color_range is None else (color_range == 1)
+    in_peak, in_low = (f32(235), f32(16)) if limited else (f32(255), f32(0))
+    if st == "f":
+        out_peak, out_low = f32(1), f32(0)
+    elif limited:
+        out_peak, out_low = f32(235 << (bits - 8)), f32(16 << (bits - 8))
+    else:
+        out_peak, out_low = f32((1 << bits) - 1), f32(0)
+    v = f32(v * f32(f32(out_peak - out_low) / f32(in_peak - in_low)))
+    if st == "i":
+        r = f32(np.floor(np.abs(v) + f32(0.5)) * np.sign(v))  # @round: half away from zero
+        v = f32(max(min(r, f32((1 << bits) - 1)), f32(0)))
+    return float(v)
+
+
+def _array3(v, default):
+    """hz.getArray (src/helper.zig:340-404): up to 3 values, missing entries repeat the previous one."""
+    v = _listify(v)
+    out = []
+    for i in range(3):
+        out.append(v[i] if i < len(v) else (default if i == 0 else out[i - 1]))
+    return out
+
+
+def limitfilter(flt, src, ref=None, dark_thr=None, bright_thr=None, elast=None, planes=None, color_range=None):
+    """src/vapoursynth/limit_filter.zig:93-124 (valid arguments only) + src/filters/limit_filter.zig:3-34."""
+    fam, st, bits, ssw, ssh = _fmt(flt)
+    pm = _plane_mask(flt, planes)
+    dk = [scale_value(v, fam, st, bits, color_range) for v in _array3(dark_thr, 1.0)]
+    br = [scale_value(v, fam, st, bits, color_range) for v in _array3(bright_thr, 1.0)]
+    el = [float(np.float32(v)) for v in _array3(elast, 2.0)]
+    out = []
+    for i, (p, m) in enumerate(zip(flt["planes"], pm)):
+        if not m:
+            out.append(p.copy())
+            continue
+        out.append(oracle.limitfilter_plane(p, src["planes"][i], None if ref is None else ref["planes"][i], dk[i], br[i], el[i]))
+    return {"format": flt["format"], "planes": out}
+
+
+def adaptive_binarize(clip, clip2, c=3):
+    """src/vapoursynth/adaptive_binarize.zig:28-70,97-99: every plane, c clamped to [-256, 256]."""
+    c = int(np.clip(c, -256, 256))
+    return {"format": clip["format"], "planes": [oracle.adaptive_binarize_plane(a, b, c) for a, b in zip(clip["planes"], clip2["planes"])]}
+
+
 def _props(values_per_plane, keys, prop):
     """Append semantics of the reference: scalar for one processed plane, list for several."""
     res = {}

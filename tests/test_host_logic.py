@@ -197,3 +197,81 @@ def test_limiter_format_errors_come_last():
     raises("Limiter: not supported Int format", lambda: core.BlankClip("GRAY11", 64, 32).vszip.Limiter())
     # a bad min array is reported before the format (limiter.zig:121 vs :220)
     raises("min array must have", lambda: core.BlankClip("GRAY11", 64, 32).vszip.Limiter(min=[1, 2]))
+
+
+# --------------------------------------------------------------------------- LimitFilter (src/vapoursynth/limit_filter.zig:93-124)
+@pytest.mark.parametrize(("args", "msg"), [
+    (dict(dark_thr=[1, 2, 3, 4]), "dark_thr has too many elements \\(got 4, max 3\\)"),
+    (dict(dark_thr=-1), "dark_thr value -1 is below minimum 0"),
+    (dict(bright_thr=300.5), "bright_thr value 300.5 is above maximum 255"),
+    (dict(elast=70000), "elast value 70000 is above maximum 65535"),
+    (dict(elast=[2, -0.25]), "elast value -0.25 is below minimum 0"),
+    (dict(planes=[3]), "plane index out of range"),
+    (dict(planes=[1, 1]), "plane specified twice"),
+])
+def test_limitfilter_argument_errors(args, msg):
+    c = core.BlankClip("YUV444P16", 64, 32)
+    raises("LimitFilter: " + msg, lambda: c.vszip.LimitFilter(c, **args))
+
+
+@pytest.mark.parametrize(("other", "msg"), [
+    (("GRAY16", 62, 32, 1), "same width and height"),
+    (("YUV444P16", 64, 32, 1), "same color family"),
+    (("GRAY8", 64, 32, 1), "same bit depth"),
+    (("GRAY16", 64, 32, 2), "all input clips must have the same length"),
+])
+def test_limitfilter_clip_mismatch(other, msg):
+    flt = core.BlankClip("GRAY16", 64, 32)
+    fmt, w, h, n = other
+    bad = core.BlankClip(fmt, w, h, n)
+    raises("LimitFilter: .*" + msg, lambda: flt.vszip.LimitFilter(bad))
+    raises("LimitFilter: .*" + msg, lambda: flt.vszip.LimitFilter(flt, bad))
+    # DataType.select comes first (limit_filter.zig:101 vs :107)
+    raises("LimitFilter: not supported Int format", lambda: core.BlankClip("GRAY32", 64, 32).vszip.LimitFilter(flt))
+
+
+@pytest.mark.parametrize(("fmt", "cr", "want"), [
+    ("GRAY8", None, (4.0, 8.0)),               # depth_in == depth_out: untouched
+    ("GRAY16", 0, (1028.0, 2056.0)),           # full: 65535 / 255 = 257
+    ("GRAY16", 1, (1024.0, 2048.0)),           # limited: (60160 - 4096) / 219 = 256
+    ("GRAY16", None, (1024.0, 2048.0)),        # no _ColorRange: YUV/GRAY default to limited ...
+    ("RGB48", None, (1028.0, 2056.0)),         # ... RGB to full (src/helper.zig:259-276)
+    ("GRAY10", 0, (16.0, 32.0)),               # round(4 * 1023 / 255) = round(16.047)
+    ("GRAYS", 0, (4 / 255, 8 / 255)),
+    ("GRAYH", 1, (4 / 219, 8 / 219)),
+])
+def test_limitfilter_threshold_scaling(fmt, cr, want):
+    import numpy as np
+    if fmt not in ("GRAY8", "GRAY16", "GRAY10", "GRAYS", "GRAYH", "RGB48"):
+        pytest.skip(fmt)
+    try:
+        c = core.BlankClip(fmt, 64, 32)
+    except Exception:
+        pytest.skip(f"{fmt} is not in the mirror's format table")
+    f = vz.LimitFilterFilter(c._info(), c._info(), None, dark_thr=4, bright_thr=8, elast=[3, 1.5], color_range=cr)
+    info = f.info()
+    assert info["dark_thr"][0] == pytest.approx(want[0], rel=1e-6) and info["bright_thr"][2] == pytest.approx(want[1], rel=1e-6)
+    assert info["elast"] == [3.0, 1.5, 1.5]
+    # the same numbers as the oracle-side restatement of hz.scaleValue
+    import oracle_api as oa
+    from oracle.fixtures import FORMATS
+    if fmt in FORMATS:
+        fam, st, bits, _, _ = FORMATS[fmt]
+        assert np.float32(info["dark_thr"][1]) == np.float32(oa.scale_value(4, fam, st, bits, cr))
+        assert np.float32(info["bright_thr"][0]) == np.float32(oa.scale_value(8, fam, st, bits, cr))
+
+
+# --------------------------------------------------------------------------- AdaptiveBinarize (adaptive_binarize.zig:79-116)
+@pytest.mark.parametrize(("a", "b", "msg"), [
+    (("GRAY16", 64, 32, 1), ("GRAY16", 64, 32, 1), "only 8 bit int format supported"),
+    (("GRAYS", 64, 32, 1), ("GRAYS", 64, 32, 1), "only 8 bit int format supported"),
+    (("GRAY8", 64, 32, 1), ("GRAY8", 62, 32, 1), "all input clips must have the same width and height"),
+    (("GRAY8", 64, 32, 1), ("YUV444P8", 64, 32, 1), "all input clips must have the same color family"),
+    (("YUV420P8", 64, 32, 1), ("YUV444P8", 64, 32, 1), "all input clips must have the same subsampling"),
+    (("GRAY8", 64, 32, 1), ("GRAY16", 64, 32, 1), "all input clips must have the same bit depth"),
+    (("GRAY8", 64, 32, 2), ("GRAY8", 64, 32, 1), "second clip has less frames than input clip"),
+])
+def test_adaptive_binarize_validation(a, b, msg):
+    """tests/test_adaptive_binarize.py:112-134 of the reference."""
+    ca, cb = core.BlankClip(*a), core.BlankClip(*b)
+    raises("AdaptiveBinarize: " + msg, lambda: ca.vszip.AdaptiveBinarize(cb))

@@ -77,6 +77,52 @@ def test_limiter_golden(key):
     _assert_stats(oa.golden_stats(out), _load("limiter")[key], rel=1e-9 if fmt == "YUV420PS" else 1e-12)
 
 
+# --------------------------------------------------------------------------- LimitFilter
+# The reference tree holds tests/goldens/limitfilter.json but no longer the test that recorded it; the construction is the one its
+# parity tests still use (tests/test_int_parity.py:158-167, tests/test_f16_parity.py:211-244): flt = src.vszip.BoxBlur(2, 2),
+# ref = src.vszip.BoxBlur(4, 4) for the "ref" variant.  Every reproducible key matches exactly with the thresholds scaled on the
+# FULL-range rule (value * peak / 255), i.e. hz.getColorRange returned FULL for the fixture clips when the goldens were recorded.
+@pytest.mark.parametrize("key", sorted(_load("limitfilter")))
+def test_limitfilter_golden(key):
+    fmt, geo, args, variant = oa.parse_case_id(key)
+    if fmt not in fx.FORMATS:
+        pytest.skip(f"the fixture generator does not restate zimg's conversion to {fmt}")
+    src = fx.make_clip(fmt, geo)
+    flt = oa.boxblur(src, hradius=2, vradius=2)
+    ref = oa.boxblur(src, hradius=4, vradius=4) if variant == "ref" else None
+    out = oa.limitfilter(flt, src, ref, color_range=0, **args)
+    _assert_stats(oa.golden_stats(out), _load("limitfilter")[key])
+
+
+# --------------------------------------------------------------------------- AdaptiveBinarize
+@pytest.mark.parametrize("key", sorted(_load("adaptive_binarize")))
+def test_adaptive_binarize_golden(key):
+    pytest.skip("clip2 is built with VapourSynth's std.BoxBlur (not part of vszip); pinned by the known-answer tests below")
+
+
+@pytest.mark.parametrize("c", [0, 3, 10])
+def test_adaptive_binarize_threshold_rule(c):
+    """tests/test_adaptive_binarize.py:84-96 of the reference: a 0..255 ramp against a constant 128."""
+    import numpy as np
+    ramp = np.tile(np.arange(256, dtype=np.uint8), (2, 1))
+    out = oa.adaptive_binarize({"format": "GRAY8", "planes": [ramp]}, {"format": "GRAY8", "planes": [np.full_like(ramp, 128)]}, c=c)
+    assert out["planes"][0][0].tolist() == [255 if x <= 128 - c else 0 for x in range(256)]
+
+
+def test_adaptive_binarize_vszip_blur_mean():
+    """tests/test_adaptive_binarize.py:99-103 (higher c is stricter), with vszip's own BoxBlur as the companion clip."""
+    src = fx.make_clip("GRAY8", "full")
+    blur = oa.boxblur(src, hradius=5, vradius=5)
+    a3 = oa.adaptive_binarize(src, blur, c=3)["planes"][0].mean()
+    a10 = oa.adaptive_binarize(src, blur, c=10)["planes"][0].mean()
+    assert a10 < a3 and set(np_unique(oa.adaptive_binarize(src, blur)["planes"][0])) <= {0, 255}
+
+
+def np_unique(a):
+    import numpy as np
+    return np.unique(a).tolist()
+
+
 # --------------------------------------------------------------------------- PlaneMinMax
 @pytest.mark.parametrize("key", sorted(_load("planeminmax")))
 def test_planeminmax_golden(key):

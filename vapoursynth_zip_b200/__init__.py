@@ -78,6 +78,16 @@ class _LimiterArgs(C.Structure):
                 ("has_mask", C.c_int32), ("mask", C.c_int32)]
 
 
+class _LimitFilterArgs(C.Structure):
+    _fields_ = [("dark_thr", C.POINTER(C.c_double)), ("num_dark_thr", C.c_int32), ("bright_thr", C.POINTER(C.c_double)), ("num_bright_thr", C.c_int32),
+                ("elast", C.POINTER(C.c_double)), ("num_elast", C.c_int32), ("planes", C.POINTER(C.c_int64)), ("num_planes", C.c_int32),
+                ("color_range", C.c_int32)]
+
+
+class _AdaptiveBinarizeArgs(C.Structure):
+    _fields_ = [("has_c", C.c_int32), ("c", C.c_int64)]
+
+
 class _AverageProps(C.Structure):
     _fields_ = [("count", C.c_int32), ("plane", C.c_int32 * 3), ("has_diff", C.c_int32), ("avg", C.c_double * 3), ("diff", C.c_double * 3)]
 
@@ -117,6 +127,13 @@ ABI = {
     "vszip_limiter_create": (_P, [C.POINTER(_VideoInfo), C.POINTER(_LimiterArgs)]),
     "vszip_limiter_get_frame": (C.c_int, [_P, C.c_int32, C.POINTER(_Frame), C.POINTER(_Frame)]),
     "vszip_limiter_device": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, _P]),
+    "vszip_limitfilter_create": (_P, [C.POINTER(_VideoInfo), C.POINTER(_VideoInfo), C.POINTER(_VideoInfo), C.POINTER(_LimitFilterArgs)]),
+    "vszip_limitfilter_get_frame": (C.c_int, [_P, C.c_int32, C.POINTER(_Frame), C.POINTER(_Frame), C.POINTER(_Frame), C.POINTER(_Frame)]),
+    "vszip_limitfilter_get_info": (C.c_int, [_P, C.POINTER(C.c_float * 3), C.POINTER(C.c_float * 3), C.POINTER(C.c_float * 3)]),
+    "vszip_limitfilter_device": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P]),
+    "vszip_adaptivebinarize_create": (_P, [C.POINTER(_VideoInfo), C.POINTER(_VideoInfo), C.POINTER(_AdaptiveBinarizeArgs)]),
+    "vszip_adaptivebinarize_get_frame": (C.c_int, [_P, C.c_int32, C.POINTER(_Frame), C.POINTER(_Frame), C.POINTER(_Frame)]),
+    "vszip_adaptivebinarize_device": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, _P]),
     "vszip_chain_create": (_P, [C.POINTER(_P), C.c_int32]),
     "vszip_chain_free": (None, [_P]),
     "vszip_chain_planes": (C.c_int, [_P, C.POINTER(C.c_int32 * 3)]),
@@ -408,6 +425,41 @@ class LimiterFilter(_Filter):
         _check(load_library().vszip_limiter_device(self.handle, src.handle, dst.handle, first, count, stream))
 
 
+class LimitFilterFilter(_Filter):
+    """vszip.LimitFilter (src/vapoursynth/limit_filter.zig:93-124).  color_range: the flt clip's _ColorRange (0 full, 1 limited, None absent)."""
+
+    def __init__(self, flt_vi: _VideoInfo, src_vi: _VideoInfo, ref_vi: _VideoInfo | None = None, dark_thr=None, bright_thr=None, elast=None,
+                 planes=None, color_range=None):
+        dk, ndk = _f64(_as_list(dark_thr) or [])
+        br, nbr = _f64(_as_list(bright_thr) or [])
+        el, nel = _f64(_as_list(elast) or [])
+        pl, npl = _planes_arg(planes)
+        a = _LimitFilterArgs(dk, ndk, br, nbr, el, nel, pl, npl, -1 if color_range is None else int(color_range))
+        super().__init__(load_library().vszip_limitfilter_create(C.byref(flt_vi), C.byref(src_vi) if src_vi is not None else None,
+                                                                 C.byref(ref_vi) if ref_vi is not None else None, C.byref(a)))
+
+    def info(self):
+        d, b, e = (C.c_float * 3)(), (C.c_float * 3)(), (C.c_float * 3)()
+        _check(load_library().vszip_limitfilter_get_info(self.handle, C.byref(d), C.byref(b), C.byref(e)))
+        return {"dark_thr": list(d), "bright_thr": list(b), "elast": list(e)}
+
+    def run_device(self, flt, src, dst, ref=None, first=0, count=None, stream=None):
+        count = flt.num_frames - first if count is None else count
+        _check(load_library().vszip_limitfilter_device(self.handle, flt.handle, src.handle, ref.handle if ref else None, dst.handle, first, count, stream))
+
+
+class AdaptiveBinarizeFilter(_Filter):
+    """vszip.AdaptiveBinarize (src/vapoursynth/adaptive_binarize.zig:79-116)."""
+
+    def __init__(self, vi: _VideoInfo, clip2_vi: _VideoInfo, c=None):
+        a = _AdaptiveBinarizeArgs(c is not None, int(c or 0))
+        super().__init__(load_library().vszip_adaptivebinarize_create(C.byref(vi), C.byref(clip2_vi) if clip2_vi is not None else None, C.byref(a)))
+
+    def run_device(self, clip, clip2, dst, first=0, count=None, stream=None):
+        count = clip.num_frames - first if count is None else count
+        _check(load_library().vszip_adaptivebinarize_device(self.handle, clip.handle, clip2.handle, dst.handle, first, count, stream))
+
+
 class _Namespace:
     """`clip.vszip` / `core.vszip`: the plugin functions with the reference's argument names."""
 
@@ -429,6 +481,42 @@ class _Namespace:
         clip = self._c(clip)
         flt = LimiterFilter(clip._info(), min, max, tv_range, mask, planes)
         return _pixel_node(clip, None, flt, lambda n, s, r, d: load_library().vszip_limiter_get_frame(flt.handle, n, C.byref(s), C.byref(d)))
+
+    def _bind(self, names, pos, kw):
+        """VapourSynth binding rule: `clip.vszip.F(a, b)` puts the bound clip first and shifts the positional arguments."""
+        if self._clip is not None:
+            pos = (self._clip,) + tuple(pos)
+        if len(pos) > len(names):
+            raise Error("too many positional arguments")
+        args = dict(zip(names, pos))
+        for k, v in kw.items():
+            if k not in names:
+                raise Error(f"unknown argument {k}")
+            if k in args:
+                raise Error(f"argument {k} given twice")
+            args[k] = v
+        return [args.get(k) for k in names]
+
+    def LimitFilter(self, *pos, **kw) -> VideoNode:
+        flt, src, ref, dark_thr, bright_thr, elast, planes = self._bind(("flt", "src", "ref", "dark_thr", "bright_thr", "elast", "planes"), pos, kw)
+        if flt is None or src is None:
+            raise Error("LimitFilter: flt and src are required")
+        f = LimitFilterFilter(flt._info(), src._info(), ref._info() if ref is not None else None, dark_thr, bright_thr, elast, planes, None)
+        # hz.scaleValue -> hz.getColorRange reads frame 0 of flt (src/helper.zig:259-276), only when the depth is not 8 bits
+        if flt.format.bits_per_sample != 8 and flt.num_frames > 0:
+            cr = flt.get_frame(0).props.get("_ColorRange")
+            if cr is not None:
+                f = LimitFilterFilter(flt._info(), src._info(), ref._info() if ref is not None else None, dark_thr, bright_thr, elast, planes, cr)
+        return _multi_node(flt, [src] + ([ref] if ref is not None else []), f, lambda n, a, others, d: load_library().vszip_limitfilter_get_frame(
+            f.handle, n, C.byref(a), C.byref(others[0]), C.byref(others[1]) if len(others) > 1 else None, C.byref(d)))
+
+    def AdaptiveBinarize(self, *pos, **kw) -> VideoNode:
+        clip, clip2, c = self._bind(("clip", "clip2", "c"), pos, kw)
+        if clip is None or clip2 is None:
+            raise Error("AdaptiveBinarize: clip and clip2 are required")
+        f = AdaptiveBinarizeFilter(clip._info(), clip2._info(), c)
+        return _multi_node(clip, [clip2], f, lambda n, a, others, d: load_library().vszip_adaptivebinarize_get_frame(
+            f.handle, n, C.byref(a), C.byref(others[0]), C.byref(d)), {"_ColorRange": 0})  # dst_prop.setColorRange(.FULL)
 
     def Bilateral(self, clip=None, ref=None, sigmaS=None, sigmaR=None, planes=None, algorithm=None, PBFICnum=None) -> VideoNode:
         clip = self._c(clip)
@@ -484,6 +572,28 @@ def _pixel_node(clip: VideoNode, ref: VideoNode | None, flt: _Filter, call) -> V
     node = VideoNode(fmt, clip.width, clip.height, clip.num_frames, get)
     node.filter = flt
     node._chain_info = ("pixel", clip, ref, None)
+    return node
+
+
+def _multi_node(first: VideoNode, others, flt: _Filter, call, set_props=None) -> VideoNode:
+    """A pixel filter with several input clips (LimitFilter, AdaptiveBinarize): dst is allocated from `first`."""
+    fmt = first.format
+
+    def get(n):
+        core._ensure_init()
+        src = first.get_frame(n)
+        ofr = [_second_frame(o, n) for o in others]
+        out_planes = [np.empty_like(p, order="C") if flt.process[i] else p for i, p in enumerate(src.planes)]
+        keep = [[_rows(p) if flt.process[i] else None for i, p in enumerate(fr.planes)] for fr in [src] + ofr]
+        d = _cframe([p if flt.process[i] else None for i, p in enumerate(out_planes)])
+        _check(call(n, _cframe(keep[0]), [_cframe(k) for k in keep[1:]], d))
+        props = dict(src.props)
+        props.update(set_props or {})
+        return VideoFrame(fmt, first.width, first.height, out_planes, props)
+
+    node = VideoNode(fmt, first.width, first.height, first.num_frames, get)
+    node.filter = flt
+    node._chain_info = None  # several inputs: never part of a fused linear chain
     return node
 
 

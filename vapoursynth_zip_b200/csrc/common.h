@@ -59,9 +59,9 @@ size_t layout_algorithmic_bytes(const FrameLayout& l);
 // --------------------------------------------------------------------------- device runtime
 struct Slot {  // one in-flight getFrame request
     cudaStream_t stream = nullptr;
-    char* pin[3] = {nullptr, nullptr, nullptr};  // pinned host: src, ref/clipb, dst
-    char* dev[3] = {nullptr, nullptr, nullptr};  // device: src, ref/clipb, dst
-    size_t cap[3] = {0, 0, 0};
+    char* pin[4] = {nullptr, nullptr, nullptr, nullptr};  // pinned host: src, ref/clipb, dst, third input (LimitFilter ref)
+    char* dev[4] = {nullptr, nullptr, nullptr, nullptr};  // device: same roles
+    size_t cap[4] = {0, 0, 0, 0};
     void* pin_small = nullptr;  // 4 KB pinned scratch for tiny results
     void* dev_small = nullptr;  // 64 KB device scratch for reductions
 };

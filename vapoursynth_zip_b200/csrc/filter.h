@@ -6,7 +6,7 @@
 
 namespace vsz {
 
-enum FilterKind { F_BOXBLUR = 1, F_BILATERAL = 2, F_PLANEMINMAX = 3, F_PLANEAVERAGE = 4, F_LIMITER = 5 };
+enum FilterKind { F_BOXBLUR = 1, F_BILATERAL = 2, F_PLANEMINMAX = 3, F_PLANEAVERAGE = 4, F_LIMITER = 5, F_LIMITFILTER = 6, F_ADAPTIVEBINARIZE = 7 };
 
 struct BilateralPlane {
     double sigmaS = 0, sigmaR = 0;
@@ -53,6 +53,12 @@ struct vszip_filter {
     std::vector<int32_t*> exclude_i_dev;  // [device] copies of lists longer than 16 entries (lazy, guarded by lut_mu)
     std::vector<float*> exclude_f_dev;
     float avg_peak;
+
+    // LimitFilter (src/vapoursynth/limit_filter.zig:15-25): thresholds already scaled to the clip's depth
+    float lf_dark[3], lf_bright[3], lf_elast[3];
+    bool lf_has_ref;
+    // AdaptiveBinarize (src/vapoursynth/adaptive_binarize.zig:14-19)
+    int ab_c;
 };
 
 namespace vsz {
@@ -80,6 +86,13 @@ int run_pbfic(const FrameLayout& l, int plane, const char* src, size_t src_fs, c
 // pointwise_kernels.cu
 int run_limiter(const FrameLayout& l, const bool mask[3], const char* src, size_t src_fs, char* dst, size_t dst_fs, int count,
                 const double lo[3], const double hi[3], cudaStream_t st);
+
+// flt/src/ref share the layout l; ref == nullptr: the difference is judged against src
+int run_limitfilter(const FrameLayout& l, const bool mask[3], const char* flt, size_t flt_fs, const char* src, size_t src_fs,
+                    const char* ref, size_t ref_fs, char* dst, size_t dst_fs, int count, const float dark[3], const float bright[3],
+                    const float elast[3], cudaStream_t st);
+int run_adaptivebinarize(const FrameLayout& l, const char* a, size_t a_fs, const char* b, size_t b_fs, char* dst, size_t dst_fs, int count,
+                         int c, cudaStream_t st);
 
 // planestats_kernels.cu
 struct StatsRaw {  // one per (frame, processed plane), written by the kernels

@@ -32,11 +32,15 @@ bool parse_planes(const int64_t* planes, int n, int num_planes, const char* name
 }
 
 // hz.compareNodes(..., .BIGGER_THAN, ...) (src/helper.zig:166-215)
-bool compare_nodes(const vszip_video_info& a, const vszip_video_info& b, const char* name) {
+bool compare_nodes(const vszip_video_info& a, const vszip_video_info& b, const char* name, bool same_len = false) {
     if (a.width != b.width || a.height != b.height) { set_error("%s: all input clips must have the same width and height.", name); return false; }
     if (a.color_family != b.color_family) { set_error("%s: all input clips must have the same color family.", name); return false; }
     if (a.sub_sampling_w != b.sub_sampling_w || a.sub_sampling_h != b.sub_sampling_h) { set_error("%s: all input clips must have the same subsampling.", name); return false; }
     if (a.bits_per_sample != b.bits_per_sample) { set_error("%s: all input clips must have the same bit depth.", name); return false; }
+    if (same_len) {  // .SAME_LEN
+        if (a.num_frames != b.num_frames) { set_error("%s: all input clips must have the same length.", name); return false; }
+        return true;
+    }
     if (a.num_frames > b.num_frames) { set_error("%s: second clip has less frames than input clip.", name); return false; }
     return true;
 }
@@ -53,6 +57,48 @@ std::string fmt_num(double v) {  // Zig's {d}: shortest decimal that round-trips
     }
     if (strchr(buf, 'e')) snprintf(buf, sizeof buf, "%.17f", v);
     return buf;
+}
+
+std::string fmt_num_f32(float v) {  // {d} of an f32: shortest decimal that round-trips as f32
+    char buf[400];
+    if (v == std::floor(v) && std::fabs(v) < 1e15f) {
+        snprintf(buf, sizeof buf, "%.0f", (double)v);
+        return buf;
+    }
+    for (int prec = 1; prec <= 9; ++prec) {
+        snprintf(buf, sizeof buf, "%.*g", prec, (double)v);
+        if (strtof(buf, nullptr) == v) break;
+    }
+    if (strchr(buf, 'e')) snprintf(buf, sizeof buf, "%.9f", (double)v);
+    return buf;
+}
+
+// hz.getArray(f32, ...) as LimitFilter uses it (src/helper.zig:340-404): values narrowed to f32 before the range tests
+bool get_array_f32(const double* src, int n, float def, float lo, float hi, const char* key, const char* name, float out[3]) {
+    if (n > 3) { set_error("%s: %s has too many elements (got %d, max 3).", name, key, n); return false; }
+    for (int i = 0; i < 3; ++i) {
+        if (i < n) out[i] = (float)src[i];
+        else if (i == 0) out[i] = def;
+        else out[i] = out[i - 1];
+        if (out[i] < lo) { set_error("%s: %s value %s is below minimum %s.", name, key, fmt_num_f32(out[i]).c_str(), fmt_num_f32(lo).c_str()); return false; }
+        if (out[i] > hi) { set_error("%s: %s value %s is above maximum %s.", name, key, fmt_num_f32(out[i]).c_str(), fmt_num_f32(hi).c_str()); return false; }
+    }
+    return true;
+}
+
+// hz.scaleValue(value, node, .{}) (src/helper.zig:312-338): an 8-bit integer-scale value brought to the clip's depth, f32
+float scale_value8(float value, const vszip_video_info& vi, bool limited) {
+    if (vi.bits_per_sample == 8) return value;
+    const bool flt = vi.sample_type == VSZIP_ST_FLOAT;
+    const int bits = vi.bits_per_sample, sh = bits - 8;
+    const float full_peak = (float)((1ll << bits) - 1);
+    const float in_peak = limited ? 235.0f : 255.0f, in_low = limited ? 16.0f : 0.0f;
+    const float out_peak = flt ? 1.0f : (limited ? (float)(235ll << sh) : full_peak);
+    const float out_low = flt ? 0.0f : (limited ? (float)(16ll << sh) : 0.0f);
+    const float scale = (out_peak - out_low) / (in_peak - in_low);
+    float v = value * scale;
+    if (!flt) v = std::fmax(std::fmin(std::round(v), full_peak), 0.0f);
+    return v;
 }
 
 // hz.getArray (src/helper.zig:340-404)
@@ -769,6 +815,144 @@ int vszip_limiter_device(const vszip_filter* f, const vszip_dev_clip* src, vszip
     cudaStream_t st = stream ? (cudaStream_t)stream : d->batch_stream;
     const size_t fs = src->layout.frame_stride;
     return run_limiter(f->layout, f->process, src->base + (size_t)first * fs, fs, dst->base + (size_t)first * fs, fs, count, f->lim_lo, f->lim_hi, st);
+}
+
+// =========================================================================== LimitFilter
+vszip_filter* vszip_limitfilter_create(const vszip_video_info* flt_vi, const vszip_video_info* src_vi, const vszip_video_info* ref_vi,
+                                       const vszip_limitfilter_args* a) {
+    static const char* name = "LimitFilter";
+    if (!basic_vi_ok(flt_vi, name)) return nullptr;
+    if (!src_vi) { set_error("LimitFilter: the src clip is required"); return nullptr; }
+    SampleKind kind;
+    if (!select_kind(*flt_vi, name, false, &kind)) return nullptr;                     // limit_filter.zig:101
+    if (!compare_nodes(*flt_vi, *src_vi, name, true)) return nullptr;                  // :107-108, SAME_LEN
+    if (ref_vi && !compare_nodes(*flt_vi, *ref_vi, name, true)) return nullptr;
+    bool process[3] = {true, true, true};
+    if (!parse_planes(a->planes, a->num_planes, flt_vi->num_planes, name, process)) return nullptr;
+    float dark[3], bright[3], elast[3];
+    if (!get_array_f32(a->dark_thr, a->num_dark_thr, 1.0f, 0.0f, 255.0f, "dark_thr", name, dark)) return nullptr;
+    if (!get_array_f32(a->bright_thr, a->num_bright_thr, 1.0f, 0.0f, 255.0f, "bright_thr", name, bright)) return nullptr;
+    if (!get_array_f32(a->elast, a->num_elast, 2.0f, 0.0f, 65535.0f, "elast", name, elast)) return nullptr;
+    // getColorRange (src/helper.zig:259-276) when the frame carries no _ColorRange
+    const bool limited = a->color_range < 0 ? flt_vi->color_family != VSZIP_CF_RGB : a->color_range == 1;
+    vszip_filter* f = new vszip_filter();
+    f->kind = F_LIMITFILTER;
+    f->vi = *flt_vi;
+    f->sample = kind;
+    f->layout = make_layout(*flt_vi, kind);
+    for (int i = 0; i < 3; ++i) {
+        f->process[i] = process[i] && i < flt_vi->num_planes;
+        f->lf_dark[i] = scale_value8(dark[i], *flt_vi, limited);                       // :114-118
+        f->lf_bright[i] = scale_value8(bright[i], *flt_vi, limited);
+        f->lf_elast[i] = elast[i];
+    }
+    f->lf_has_ref = ref_vi != nullptr;
+    f->has_ref = true;  // multi-input: not fusable into a linear chain
+    return f;
+}
+
+int vszip_limitfilter_get_info(const vszip_filter* f, float dark_thr[3], float bright_thr[3], float elast[3]) {
+    if (!f || f->kind != F_LIMITFILTER) { set_error("LimitFilter: bad filter handle"); return -1; }
+    for (int i = 0; i < 3; ++i) { dark_thr[i] = f->lf_dark[i]; bright_thr[i] = f->lf_bright[i]; elast[i] = f->lf_elast[i]; }
+    return 0;
+}
+
+int vszip_limitfilter_get_frame(const vszip_filter* f, int32_t n, const vszip_frame* flt, const vszip_frame* src, const vszip_frame* ref,
+                                vszip_frame* dst) {
+    if (!f || f->kind != F_LIMITFILTER) { set_error("LimitFilter: bad filter handle"); return -1; }
+    if (!flt || !src || !dst) { set_error("LimitFilter: flt, src and dst frames are required"); return -1; }
+    if (f->lf_has_ref != (ref != nullptr)) { set_error("LimitFilter: ref frame presence does not match the filter instance"); return -1; }
+    DeviceCtx* d = route(n, "LimitFilter");
+    if (!d) return -1;
+    SlotGuard g(d);
+    Slot* s = g.s;
+    VSZ_CUDA(cudaSetDevice(d->ordinal));
+    const size_t bytes = f->layout.frame_stride;
+    if (slot_reserve(d, s, 0, bytes) || slot_reserve(d, s, 1, bytes) || slot_reserve(d, s, 2, bytes) || (ref && slot_reserve(d, s, 3, bytes))) return -1;
+    if (stage_in(s, 0, f->layout, flt, f->process) || stage_in(s, 1, f->layout, src, f->process)) return -1;
+    if (ref && stage_in(s, 3, f->layout, ref, f->process)) return -1;
+    int rc = run_limitfilter(f->layout, f->process, s->dev[0], 0, s->dev[1], 0, ref ? s->dev[3] : nullptr, 0, s->dev[2], 0, 1, f->lf_dark,
+                             f->lf_bright, f->lf_elast, s->stream);
+    if (rc) return rc;
+    bool direct[3];
+    if (stage_out_begin(s, f->layout, dst, f->process, direct)) return -1;
+    VSZ_CUDA(cudaStreamSynchronize(s->stream));
+    stage_out_finish(s, f->layout, dst, f->process, direct);
+    return 0;
+}
+
+int vszip_limitfilter_device(const vszip_filter* f, const vszip_dev_clip* flt, const vszip_dev_clip* src, const vszip_dev_clip* ref,
+                             vszip_dev_clip* dst, int32_t first, int32_t count, void* stream) {
+    static const char* name = "LimitFilter";
+    if (!f || f->kind != F_LIMITFILTER) { set_error("LimitFilter: bad filter handle"); return -1; }
+    if (f->lf_has_ref != (ref != nullptr)) { set_error("LimitFilter: ref clip presence does not match the filter instance"); return -1; }
+    if (!same_clip_shape(flt, f, name) || !same_clip_shape(src, f, name) || !same_clip_shape(dst, f, name) || (ref && !same_clip_shape(ref, f, name))) return -1;
+    if (!range_ok(flt, first, count, name) || !range_ok(src, first, count, name) || !range_ok(dst, first, count, name) || (ref && !range_ok(ref, first, count, name))) return -1;
+    if (flt->device_index != dst->device_index || src->device_index != dst->device_index || (ref && ref->device_index != dst->device_index)) {
+        set_error("LimitFilter: clips live on different devices");
+        return -1;
+    }
+    DeviceCtx* d = device_ctx(dst->device_index);
+    if (!d) { set_error("LimitFilter: library not initialised"); return -1; }
+    VSZ_CUDA(cudaSetDevice(d->ordinal));
+    cudaStream_t st = stream ? (cudaStream_t)stream : d->batch_stream;
+    const size_t fs = dst->layout.frame_stride, off = (size_t)first * fs;
+    return run_limitfilter(f->layout, f->process, flt->base + off, fs, src->base + off, fs, ref ? ref->base + off : nullptr, fs, dst->base + off, fs,
+                           count, f->lf_dark, f->lf_bright, f->lf_elast, st);
+}
+
+// =========================================================================== AdaptiveBinarize
+vszip_filter* vszip_adaptivebinarize_create(const vszip_video_info* vi, const vszip_video_info* clip2_vi, const vszip_adaptivebinarize_args* a) {
+    static const char* name = "AdaptiveBinarize";
+    if (!basic_vi_ok(vi, name)) return nullptr;
+    if (!clip2_vi) { set_error("AdaptiveBinarize: clip2 is required"); return nullptr; }
+    if (!compare_nodes(*vi, *clip2_vi, name)) return nullptr;                          // adaptive_binarize.zig:88-89, BIGGER_THAN
+    if (vi->sample_type != VSZIP_ST_INTEGER || vi->bits_per_sample != 8) { set_error("AdaptiveBinarize: only 8 bit int format supported."); return nullptr; }
+    const int64_t c = a && a->has_c ? (int64_t)sat_i32(a->c) : 3;                      // getValue(i32, "c") orelse 3
+    vszip_filter* f = new vszip_filter();
+    f->kind = F_ADAPTIVEBINARIZE;
+    f->vi = *vi;
+    f->sample = K_U8;
+    f->layout = make_layout(*vi, K_U8);
+    for (int i = 0; i < 3; ++i) f->process[i] = i < vi->num_planes;
+    f->ab_c = (int)std::min<int64_t>(std::max<int64_t>(c, -256), 256);               // :97-99
+    f->has_ref = true;
+    return f;
+}
+
+int vszip_adaptivebinarize_get_frame(const vszip_filter* f, int32_t n, const vszip_frame* clip, const vszip_frame* clip2, vszip_frame* dst) {
+    if (!f || f->kind != F_ADAPTIVEBINARIZE) { set_error("AdaptiveBinarize: bad filter handle"); return -1; }
+    if (!clip || !clip2 || !dst) { set_error("AdaptiveBinarize: clip, clip2 and dst frames are required"); return -1; }
+    DeviceCtx* d = route(n, "AdaptiveBinarize");
+    if (!d) return -1;
+    SlotGuard g(d);
+    Slot* s = g.s;
+    VSZ_CUDA(cudaSetDevice(d->ordinal));
+    const size_t bytes = f->layout.frame_stride;
+    if (slot_reserve(d, s, 0, bytes) || slot_reserve(d, s, 1, bytes) || slot_reserve(d, s, 2, bytes)) return -1;
+    if (stage_in(s, 0, f->layout, clip, f->process) || stage_in(s, 1, f->layout, clip2, f->process)) return -1;
+    int rc = run_adaptivebinarize(f->layout, s->dev[0], 0, s->dev[1], 0, s->dev[2], 0, 1, f->ab_c, s->stream);
+    if (rc) return rc;
+    bool direct[3];
+    if (stage_out_begin(s, f->layout, dst, f->process, direct)) return -1;
+    VSZ_CUDA(cudaStreamSynchronize(s->stream));
+    stage_out_finish(s, f->layout, dst, f->process, direct);
+    return 0;
+}
+
+int vszip_adaptivebinarize_device(const vszip_filter* f, const vszip_dev_clip* clip, const vszip_dev_clip* clip2, vszip_dev_clip* dst,
+                                  int32_t first, int32_t count, void* stream) {
+    static const char* name = "AdaptiveBinarize";
+    if (!f || f->kind != F_ADAPTIVEBINARIZE) { set_error("AdaptiveBinarize: bad filter handle"); return -1; }
+    if (!same_clip_shape(clip, f, name) || !same_clip_shape(clip2, f, name) || !same_clip_shape(dst, f, name)) return -1;
+    if (!range_ok(clip, first, count, name) || !range_ok(clip2, first, count, name) || !range_ok(dst, first, count, name)) return -1;
+    if (clip->device_index != dst->device_index || clip2->device_index != dst->device_index) { set_error("AdaptiveBinarize: clips live on different devices"); return -1; }
+    DeviceCtx* d = device_ctx(dst->device_index);
+    if (!d) { set_error("AdaptiveBinarize: library not initialised"); return -1; }
+    VSZ_CUDA(cudaSetDevice(d->ordinal));
+    cudaStream_t st = stream ? (cudaStream_t)stream : d->batch_stream;
+    const size_t fs = dst->layout.frame_stride, off = (size_t)first * fs;
+    return run_adaptivebinarize(f->layout, clip->base + off, fs, clip2->base + off, fs, dst->base + off, fs, count, f->ab_c, st);
 }
 
 // =========================================================================== fused chains

@@ -297,7 +297,7 @@ void vszip_cuda_shutdown(void) {
         cudaSetDevice(d->ordinal);
         cudaDeviceSynchronize();
         for (Slot* s : d->all) {
-            for (int i = 0; i < 3; ++i) { if (s->pin[i]) cudaFreeHost(s->pin[i]); if (s->dev[i]) cudaFree(s->dev[i]); }
+            for (int i = 0; i < 4; ++i) { if (s->pin[i]) cudaFreeHost(s->pin[i]); if (s->dev[i]) cudaFree(s->dev[i]); }
             if (s->pin_small) cudaFreeHost(s->pin_small);
             if (s->dev_small) cudaFree(s->dev_small);
             cudaStreamDestroy(s->stream);
