@@ -58,11 +58,13 @@ def pixel_cfg(name, fmt, w, h, frames, make_filter, noise=True):
     src.free(); dst.free()
 
 
-def multi_cfg(name, fmt, w, h, frames, nin, run):
+def multi_cfg(name, fmt, w, h, frames, nin, run, prep=None):
     """pointwise filters with several input clips: algorithmic bytes = nin reads + 1 write per sample"""
     clips = [vz.DeviceClip(fmt, w, h, frames) for _ in range(nin + 1)]
     for i, c in enumerate(clips[:nin]):
         c.fill_noise(1234 + i)
+    if prep:
+        prep(clips)
     ms = timed(lambda: run(clips), args.reps)
     record(name, fmt, w, h, frames, (nin + 1) * clips[0].frame_bytes, ms)
     for c in clips:
@@ -97,6 +99,23 @@ multi_cfg("C7 LimitFilter(flt, src, dark_thr=8, bright_thr=8, elast=3) (8f rank 
           lambda c: _lf.setdefault("a", vz.LimitFilterFilter(c[0].info(), c[0].info(), None, dark_thr=8, bright_thr=8, elast=3)).run_device(c[0], c[1], c[2], count=N, stream=st.cuda_stream))
 multi_cfg("C7 LimitFilter(flt, src, ref, ...) three inputs", "YUV420P16", 1920, 1080, N, 3,
           lambda c: _lf.setdefault("b", vz.LimitFilterFilter(c[0].info(), c[0].info(), c[0].info(), dark_thr=8, bright_thr=8, elast=3)).run_device(c[0], c[1], c[3], ref=c[2], count=N, stream=st.cuda_stream))
+def _image_like(c):
+    """src = noise smoothed by BoxBlur(13, 3 passes) (image-like gradients), flt = BoxBlur(src, 2), ref = BoxBlur(src, 4):
+    the reference's own LimitFilter usage (tests/test_int_parity.py:158-167)"""
+    tmp = vz.DeviceClip("YUV420P16", 1920, 1080, c[0].num_frames)
+    tmp.fill_noise(99)
+    vz.BoxBlurFilter(tmp.info(), hradius=13, hpasses=3, vradius=13, vpasses=3).run_device(tmp, c[1], stream=st.cuda_stream)   # src
+    vz.BoxBlurFilter(tmp.info(), hradius=2, vradius=2).run_device(c[1], c[0], stream=st.cuda_stream)                             # flt
+    if len(c) > 3:
+        vz.BoxBlurFilter(tmp.info(), hradius=4, vradius=4).run_device(c[1], c[2], stream=st.cuda_stream)                         # ref
+    torch.cuda.synchronize()
+    tmp.free()
+
+
+multi_cfg("C7' LimitFilter(flt=BoxBlur(src,2), src, dark_thr=1, bright_thr=1, elast=2) image-like content", "YUV420P16", 1920, 1080, N, 2,
+          lambda c: _lf.setdefault("d", vz.LimitFilterFilter(c[0].info(), c[0].info(), None, dark_thr=1, bright_thr=1, elast=2)).run_device(c[0], c[1], c[2], count=N, stream=st.cuda_stream), _image_like)
+multi_cfg("C7' LimitFilter(flt, src, ref=BoxBlur(src,4), ...) image-like content", "YUV420P16", 1920, 1080, N, 3,
+          lambda c: _lf.setdefault("e", vz.LimitFilterFilter(c[0].info(), c[0].info(), c[0].info(), dark_thr=1, bright_thr=1, elast=2)).run_device(c[0], c[1], c[3], ref=c[2], count=N, stream=st.cuda_stream), _image_like)
 multi_cfg("C8 AdaptiveBinarize(clip, clip2, c=3) YUV420P8 (8f rank 3)", "YUV420P8", 1920, 1080, N, 2,
           lambda c: _lf.setdefault("c", vz.AdaptiveBinarizeFilter(c[0].info(), c[0].info(), c=3)).run_device(c[0], c[1], c[2], count=N, stream=st.cuda_stream))
 M = max(8, N // 2)
