@@ -124,6 +124,22 @@ stats_cfg("C4 PlaneMinMax(minthr=.1,maxthr=.1) GRAYS 4K", "GRAYS", 3840, 2160, M
 stats_cfg("C4 PlaneMinMax no threshold GRAY16 4K", "GRAY16", 3840, 2160, M, lambda s: vz.PlaneMinMaxFilter(s.info()))
 stats_cfg("C4 PlaneAverage(exclude=[0,32768]) GRAY16 4K", "GRAY16", 3840, 2160, M, lambda s: vz.PlaneAverageFilter(s.info(), exclude=[0, 32768]))
 stats_cfg("C4 PlaneAverage(exclude=[0,1]) GRAYS 4K", "GRAYS", 3840, 2160, M, lambda s: vz.PlaneAverageFilter(s.info(), exclude=[0, 1]))
+def both_stats_cfg(fmt, w, h, frames, mm_args, excl):
+    """config 4 runs PlaneMinMax and PlaneAverage over the same plane: the two batch calls back to back (two HBM reads)"""
+    src = vz.DeviceClip(fmt, w, h, frames)
+    src.fill_noise(1234)
+    mmf, avf = vz.PlaneMinMaxFilter(src.info(), **mm_args), vz.PlaneAverageFilter(src.info(), exclude=excl)
+    lib = vz.load_library()
+
+    def separate():
+        vz._check(lib.vszip_planeminmax_device(mmf.handle, src.handle, None, 0, frames, None, st.cuda_stream))
+        vz._check(lib.vszip_planeaverage_device(avf.handle, src.handle, None, 0, frames, None, st.cuda_stream))
+    record(f"C4 PlaneMinMax(thr)+PlaneAverage {fmt} 4K, both batch calls back to back", fmt, w, h, frames, src.frame_bytes, timed(separate, args.reps))
+    src.free()
+
+
+both_stats_cfg("GRAY16", 3840, 2160, M, dict(minthr=0.1, maxthr=0.1), [0, 32768])
+both_stats_cfg("GRAYS", 3840, 2160, M, dict(minthr=0.1, maxthr=0.1), [0, 1])
 K = max(4, N // 16)
 pixel_cfg("C5a BoxBlur(13,1,13,1) YUV444PS 4K (comptime float)", "YUV444PS", 3840, 2160, K, lambda s: vz.BoxBlurFilter(s.info(), hradius=13, vradius=13))
 pixel_cfg("C5b Bilateral(2,2) YUV444PS 4K", "YUV444PS", 3840, 2160, K, lambda s: vz.BilateralFilter(s.info(), sigmaS=2, sigmaR=2))

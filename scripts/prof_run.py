@@ -1,5 +1,5 @@
 """Small driver for ncu captures: runs one filter over a device-resident noise batch a few times.
-usage: python scripts/prof_run.py boxblur|boxblur_ct|bilateral|pbfic|minmax|average [frames] [reps]"""
+usage: python scripts/prof_run.py boxblur|boxblur_ct|bilateral|pbfic|limitfilter|binarize|minmax|average [frames] [reps]"""
 import sys
 from pathlib import Path
 
@@ -35,6 +35,20 @@ elif what == "bilateral":
 elif what == "pbfic":
     f = vz.BilateralFilter(src.info(), sigmaS=8, sigmaR=0.1, planes=[0])
     run = lambda: f.run_device(src, dst)
+elif what == "limitfilter":   # image-like content: src = smoothed noise, flt = BoxBlur(src, 2), ref = BoxBlur(src, 4)
+    tmp, flt, ref = (vz.DeviceClip(fmt, w, h, frames) for _ in range(3))
+    vz.BoxBlurFilter(src.info(), hradius=13, hpasses=3, vradius=13, vpasses=3).run_device(src, tmp)
+    vz.BoxBlurFilter(src.info(), hradius=2, vradius=2).run_device(tmp, flt)
+    vz.BoxBlurFilter(src.info(), hradius=4, vradius=4).run_device(tmp, ref)
+    f = vz.LimitFilterFilter(src.info(), src.info(), src.info(), dark_thr=1, bright_thr=1, elast=2)
+    run = lambda: f.run_device(flt, tmp, dst, ref=ref)
+elif what == "binarize":
+    src.free(); dst.free()
+    src, dst = vz.DeviceClip("YUV420P8", w, h, frames), vz.DeviceClip("YUV420P8", w, h, frames)
+    b2 = vz.DeviceClip("YUV420P8", w, h, frames)
+    src.fill_noise(seed=1234); b2.fill_noise(seed=99)
+    f = vz.AdaptiveBinarizeFilter(src.info(), src.info(), c=3)
+    run = lambda: f.run_device(src, b2, dst)
 elif what == "minmax":
     f = vz.PlaneMinMaxFilter(src.info(), minthr=0.1, maxthr=0.1)
     run = lambda: f.run_device(src)

@@ -229,3 +229,4 @@ def test_device_batch():
         cb = {"format": fmt, "planes": b.download(i)}
         props_close(got_mm[i], oa.planeminmax(ca, minthr=0.1, maxthr=0.2, clipb=cb))
         props_close(got_av[i], oa.planeaverage(ca, [7, 9], clipb=cb))
+

@@ -134,3 +134,32 @@ def test_adaptive_binarize_with_vszip_blur_and_device_batch():
     for i in range(n):
         x, y = ({"format": fmt, "planes": c.download(i)} for c in (a, b))
         assert_same_planes(d.download(i), oa.adaptive_binarize(x, y, c=6)["planes"], f"frame {i}")
+
+
+# --------------------------------------------------------------------------- BASELINE-size frames, size-independent properties
+def test_full_size_properties_1080p():
+    """1920x1080 YUV420P16 / YUV420P8 device batches (too large for the scalar oracle to be the only check):
+    LimitFilter(flt, flt) == flt;  thr = 0, elast = 0 returns src wherever flt != ref;  an infinite elast with thr = 255 on 8-bit-scale
+    noise keeps flt wherever |flt - src| <= thr;  AdaptiveBinarize(a, a, c=0) is all 255, c=1 all 0;  one frame against the oracle."""
+    fmt, w, h, n = "YUV420P16", 1920, 1080, 4
+    a, b, d = (vz.DeviceClip(fmt, w, h, n) for _ in range(3))
+    a.fill_noise(seed=31)
+    b.fill_noise(seed=32)
+    vi = a.info()
+    vz.LimitFilterFilter(vi, vi, None, dark_thr=7, bright_thr=3, elast=2.5).run_device(a, a, d)
+    for i in (0, n - 1):
+        assert_same_planes(d.download(i), a.download(i), "LimitFilter(flt, flt) == flt")
+    vz.LimitFilterFilter(vi, vi, None, dark_thr=0, bright_thr=0, elast=0).run_device(a, b, d)
+    for i in (0, n - 1):
+        assert_same_planes(d.download(i), b.download(i), "thr = 0: src everywhere (flt == src returns flt == src)")
+    f = vz.LimitFilterFilter(vi, vi, None, dark_thr=16, bright_thr=4, elast=3, color_range=0)
+    f.run_device(a, b, d)
+    flt, src = ({"format": fmt, "planes": c.download(1)} for c in (a, b))
+    assert_same_planes(d.download(1), oa.limitfilter(flt, src, None, dark_thr=16, bright_thr=4, elast=3, color_range=0)["planes"], "1080p frame vs oracle")
+    fmt8 = "YUV420P8"
+    a8, d8 = vz.DeviceClip(fmt8, w, h, n), vz.DeviceClip(fmt8, w, h, n)
+    a8.fill_noise(seed=33)
+    vz.AdaptiveBinarizeFilter(a8.info(), a8.info(), c=0).run_device(a8, a8, d8)
+    assert all(int(p.min()) == 255 for p in d8.download(n - 1))
+    vz.AdaptiveBinarizeFilter(a8.info(), a8.info(), c=1).run_device(a8, a8, d8)
+    assert all(int(p.max()) == 0 for p in d8.download(0))
