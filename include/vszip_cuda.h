@@ -261,7 +261,10 @@ int vszip_cuda_stream_sync(int32_t device, void* stream);
  * chain's SOURCE frame instead of its immediate input and calls this.  Results are identical to calling the
  * per-filter get_frame functions one after the other.
  *  - filters: 1..16 handles in evaluation order, all created for the same video format and without ref/clipb;
- *    the chain borrows them (they must outlive it).
+ *    the chain borrows them (they must outlive it).  Two "diamond" elements are accepted as well, with the chain's
+ *    SOURCE frame as their second clip: a LimitFilter created without ref (flt = the chain's current value, src = the
+ *    source frame: `flt = src.vszip.X(); flt.vszip.LimitFilter(src)`) and an AdaptiveBinarize (clip = the source frame,
+ *    clip2 = the current value: `src.vszip.AdaptiveBinarize(src.vszip.BoxBlur())`, the reference's own usage).
  *  - props_out[i]: for a PlaneMinMax / PlaneAverage element a pointer to its vszip_minmax_props /
  *    vszip_average_props (required), for pixel filters ignored (may be NULL).
  *  - dst: receives the planes reported by vszip_chain_planes (the union of the planes the pixel filters process);

@@ -9,6 +9,7 @@ timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke_$R.log
 timeout 600 python bench.py > $O/bench_$R.json 2> $O/bench_$R.err
 timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > $O/bench_ref_$R.json 2>> $O/bench_$R.err
 timeout 300 python scripts/e2e_chain.py 8 4 > $O/e2e_chain_$R.txt 2>&1
+timeout 300 python scripts/e2e_diamond.py 32 8 > $O/e2e_diamond_$R.txt 2>&1
 timeout 600 python scripts/bench_extras.py --frames 128 --out $O/bench_extras_$R.json > /dev/null 2> $O/bench_extras_$R.txt
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_$R.csv python bench.py --steps 2 --warmup 1 --no-cpu > $O/launches_bench_$R.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:blur_ -s 2 -c 2 -o $O/ncu_boxblur_$R python scripts/prof_run.py boxblur 128 2 > /dev/null 2>&1

@@ -13,7 +13,7 @@ ROOT = Path(__file__).resolve().parents[1]
 G, P = ROOT / "gpurun_out", ROOT / "profiles"
 P.mkdir(exist_ok=True)
 
-for name in (f"bench_{R}.json", f"bench_ref_{R}.json", f"bench_extras_{R}.json", f"bench_extras_{R}.txt", f"pytest_gpu_{R}.log", f"e2e_chain_{R}.txt", f"smoke_{R}.log"):
+for name in (f"bench_{R}.json", f"bench_ref_{R}.json", f"bench_extras_{R}.json", f"bench_extras_{R}.txt", f"pytest_gpu_{R}.log", f"e2e_chain_{R}.txt", f"e2e_diamond_{R}.txt", f"smoke_{R}.log"):
     if (G / name).exists():
         shutil.copy(G / name, P / name)
 

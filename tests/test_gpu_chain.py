@@ -86,3 +86,44 @@ def test_chain_rejects_second_clips():
     n = a.vszip.BoxBlur().vszip.PlaneMinMax(clipb=b)
     out = n.get_frame(0)                      # evaluated unfused: the second clip keeps it out of a chain
     assert getattr(n, "_chain", None) is None and "psmDiff" in out.props
+
+
+# --------------------------------------------------------------------------- diamond elements: the second clip is the chain's source
+def test_fused_chain_limitfilter_reads_the_chain_source():
+    """`flt = src.vszip.BoxBlur(); flt.vszip.LimitFilter(src)` (the reference's usage, tests/test_int_parity.py:158-167) as one chain:
+    one upload, one download; identical to the two separate calls and to the oracle."""
+    def build(c):
+        return c.vszip.BoxBlur(hradius=2, vradius=2).vszip.LimitFilter(c, dark_thr=[16, 4], bright_thr=[8, 4], elast=[3, 2], planes=[0, 2]) \
+                .vszip.PlaneMinMax(minthr=0.05, maxthr=0.05)
+    f = _chain_case("YUV420P16", 322, 182, build)
+    clip = noise_clip("YUV420P16", 322, 182, seed=71)
+    want = oa.limitfilter(oa.boxblur(clip, hradius=2, vradius=2), clip, None, dark_thr=[16, 4], bright_thr=[8, 4], elast=[3, 2], planes=[0, 2])
+    assert_same_planes(f.planes, want["planes"], "BoxBlur -> LimitFilter(src) chain vs oracle")
+    # three pixel filters: the source must survive the ping-pong of the intermediates
+    _chain_case("GRAYS", 200, 120, lambda c: c.vszip.BoxBlur(hradius=1, vradius=1).vszip.BoxBlur(hradius=3, vradius=0, vpasses=0)
+                .vszip.Limiter(min=[0.1], max=[0.9]).vszip.LimitFilter(c, dark_thr=8, bright_thr=8, elast=1.5))
+
+
+def test_fused_chain_adaptive_binarize():
+    """`src.vszip.AdaptiveBinarize(src.vszip.BoxBlur(5, 5))` (tests/test_adaptive_binarize.py:59-63 with vszip's own blur)."""
+    for fmt in ("GRAY8", "YUV420P8"):
+        f = _chain_case(fmt, 322, 182, lambda c: c.vszip.AdaptiveBinarize(c.vszip.BoxBlur(hradius=5, vradius=5), c=2))
+        clip = noise_clip(fmt, 322, 182, seed=71)
+        assert_same_planes(f.planes, oa.adaptive_binarize(clip, oa.boxblur(clip, hradius=5, vradius=5), c=2)["planes"], fmt)
+        assert f.props["_ColorRange"] == 0
+
+
+def test_diamond_needs_the_chain_source():
+    """A LimitFilter whose src is NOT the chain's source, or that has a ref clip, is evaluated unfused (and still correct)."""
+    a = noise_clip("GRAY16", 200, 120, seed=1)
+    b = noise_clip("GRAY16", 200, 120, seed=2)
+    na, nb = to_node(a), to_node(b)
+    flt = na.vszip.BoxBlur(hradius=2, vradius=2)
+    n1 = flt.vszip.LimitFilter(nb, dark_thr=8)
+    out1 = n1.get_frame(0)
+    assert getattr(n1, "_chain", None) is None
+    assert_same_planes(out1.planes, oa.limitfilter(oa.boxblur(a, hradius=2, vradius=2), b, None, dark_thr=8)["planes"], "foreign src")
+    n2 = flt.vszip.LimitFilter(na, nb, dark_thr=8)
+    out2 = n2.get_frame(0)
+    assert getattr(n2, "_chain", None) is None
+    assert_same_planes(out2.planes, oa.limitfilter(oa.boxblur(a, hradius=2, vradius=2), a, b, dark_thr=8)["planes"], "ref clip")

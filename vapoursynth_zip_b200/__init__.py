@@ -508,7 +508,8 @@ class _Namespace:
             if cr is not None:
                 f = LimitFilterFilter(flt._info(), src._info(), ref._info() if ref is not None else None, dark_thr, bright_thr, elast, planes, cr)
         return _multi_node(flt, [src] + ([ref] if ref is not None else []), f, lambda n, a, others, d: load_library().vszip_limitfilter_get_frame(
-            f.handle, n, C.byref(a), C.byref(others[0]), C.byref(others[1]) if len(others) > 1 else None, C.byref(d)))
+            f.handle, n, C.byref(a), C.byref(others[0]), C.byref(others[1]) if len(others) > 1 else None, C.byref(d)),
+            through=flt if ref is None else None, needs_source=src)
 
     def AdaptiveBinarize(self, *pos, **kw) -> VideoNode:
         clip, clip2, c = self._bind(("clip", "clip2", "c"), pos, kw)
@@ -516,7 +517,8 @@ class _Namespace:
             raise Error("AdaptiveBinarize: clip and clip2 are required")
         f = AdaptiveBinarizeFilter(clip._info(), clip2._info(), c)
         return _multi_node(clip, [clip2], f, lambda n, a, others, d: load_library().vszip_adaptivebinarize_get_frame(
-            f.handle, n, C.byref(a), C.byref(others[0]), C.byref(d)), {"_ColorRange": 0})  # dst_prop.setColorRange(.FULL)
+            f.handle, n, C.byref(a), C.byref(others[0]), C.byref(d)), {"_ColorRange": 0},  # dst_prop.setColorRange(.FULL)
+            through=clip2, needs_source=clip)
 
     def Bilateral(self, clip=None, ref=None, sigmaS=None, sigmaR=None, planes=None, algorithm=None, PBFICnum=None) -> VideoNode:
         clip = self._c(clip)
@@ -575,7 +577,7 @@ def _pixel_node(clip: VideoNode, ref: VideoNode | None, flt: _Filter, call) -> V
     return node
 
 
-def _multi_node(first: VideoNode, others, flt: _Filter, call, set_props=None) -> VideoNode:
+def _multi_node(first: VideoNode, others, flt: _Filter, call, set_props=None, through=None, needs_source=None) -> VideoNode:
     """A pixel filter with several input clips (LimitFilter, AdaptiveBinarize): dst is allocated from `first`."""
     fmt = first.format
 
@@ -593,7 +595,11 @@ def _multi_node(first: VideoNode, others, flt: _Filter, call, set_props=None) ->
 
     node = VideoNode(fmt, first.width, first.height, first.num_frames, get)
     node.filter = flt
-    node._chain_info = None  # several inputs: never part of a fused linear chain
+    # "diamond" element of a fused chain: `through` is the input that continues the chain, `needs_source` the clip that must turn
+    # out to be the chain's source (checked in _fusable_chain); anything else (a ref clip, ...) is never fused
+    node._chain_info = ("pixel", through, None, None) if through is not None else None
+    node._needs_source = needs_source
+    node._set_props = set_props
     return node
 
 
@@ -647,7 +653,9 @@ def _fusable_chain(node: "VideoNode"):
     while getattr(cur, "_chain_info", None) is not None and cur._chain_info[2] is None and len(nodes) < 16:
         nodes.append(cur)
         cur = cur._chain_info[1]
-    node._chain = (_Chain(nodes[::-1]), cur) if len(nodes) >= 2 else None
+    # diamond elements (LimitFilter's src, AdaptiveBinarize's clip) must read exactly the chain's source
+    ok = all(getattr(nd, "_needs_source", None) is None or nd._needs_source is cur for nd in nodes)
+    node._chain = (_Chain(nodes[::-1]), cur) if len(nodes) >= 2 and ok else None
     return node._chain
 
 
@@ -674,6 +682,8 @@ def _fused_get(chain_and_source, n: int) -> "VideoFrame":
             for k in drop_keys:
                 props.pop(k, None)
             props.update(to_props(o))
+    for nd in chain.nodes:
+        props.update(getattr(nd, "_set_props", None) or {})
     return VideoFrame(source.format, source.width, source.height, out_planes, props)
 
 

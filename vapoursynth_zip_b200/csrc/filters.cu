@@ -969,7 +969,9 @@ vszip_chain* vszip_chain_create(const vszip_filter* const* filters, int32_t coun
     for (int i = 0; i < count; ++i) {
         const vszip_filter* f = filters[i];
         if (!f) { set_error("chain: filter %d is NULL", i); return nullptr; }
-        if (f->has_ref) { set_error("chain: filter %d takes a second clip (ref/clipb); only single-input filters can be fused", i); return nullptr; }
+        // LimitFilter (without ref) and AdaptiveBinarize take the chain's SOURCE frame as their second clip ("diamond" elements)
+        const bool diamond = (f->kind == F_LIMITFILTER && !f->lf_has_ref) || f->kind == F_ADAPTIVEBINARIZE;
+        if (f->has_ref && !diamond) { set_error("chain: filter %d takes a second clip (ref/clipb); only single-input filters can be fused", i); return nullptr; }
         const vszip_video_info &a = f0->vi, &b = f->vi;
         if (a.width != b.width || a.height != b.height || a.color_family != b.color_family || a.sample_type != b.sample_type ||
             a.bits_per_sample != b.bits_per_sample || a.sub_sampling_w != b.sub_sampling_w || a.sub_sampling_h != b.sub_sampling_h ||
@@ -984,7 +986,7 @@ vszip_chain* vszip_chain_create(const vszip_filter* const* filters, int32_t coun
     c->npixel = 0;
     for (int p = 0; p < 3; ++p) c->written[p] = false;
     for (const vszip_filter* f : c->fl) {
-        if (f->kind == F_BOXBLUR || f->kind == F_BILATERAL || f->kind == F_LIMITER) {
+        if (f->kind == F_BOXBLUR || f->kind == F_BILATERAL || f->kind == F_LIMITER || f->kind == F_LIMITFILTER || f->kind == F_ADAPTIVEBINARIZE) {
             ++c->npixel;
             for (int p = 0; p < 3; ++p) c->written[p] = c->written[p] || f->process[p];
         }
@@ -1018,8 +1020,9 @@ int vszip_chain_get_frame(const vszip_chain* c, int32_t n, const vszip_frame* sr
     char* stats_scratch = nullptr;
     for (size_t i = 0; i < c->fl.size(); ++i) {
         const vszip_filter* f = c->fl[i];
-        if (f->kind == F_BOXBLUR || f->kind == F_BILATERAL || f->kind == F_LIMITER) {
-            // the last pixel filter must land in dev[2] (the D2H source), the ones before alternate 1 / 2
+        if (f->kind == F_BOXBLUR || f->kind == F_BILATERAL || f->kind == F_LIMITER || f->kind == F_LIMITFILTER || f->kind == F_ADAPTIVEBINARIZE) {
+            // the last pixel filter must land in dev[2] (the D2H source), the ones before alternate 1 / 2;
+            // dev[0] is never written, so the source frame stays available to the diamond elements
             const int nxt = ((c->npixel - 1 - pixel_seen) % 2 == 0) ? 2 : 1;
             ++pixel_seen;
             for (int p = 0; p < l.nplanes; ++p) {  // planes this filter passes through
@@ -1032,6 +1035,10 @@ int vszip_chain_get_frame(const vszip_chain* c, int32_t n, const vszip_frame* sr
                 rc = run_boxblur(l, f->process, s->dev[cur], 0, s->dev[nxt], 0, 1, (int)f->hradius, f->hpasses, (int)f->vradius, f->vpasses, s->stream);
             } else if (f->kind == F_LIMITER) {
                 rc = run_limiter(l, f->process, s->dev[cur], 0, s->dev[nxt], 0, 1, f->lim_lo, f->lim_hi, s->stream);
+            } else if (f->kind == F_LIMITFILTER) {       // flt = the chain's current value, src = the chain's source frame
+                rc = run_limitfilter(l, f->process, s->dev[cur], 0, s->dev[0], 0, nullptr, 0, s->dev[nxt], 0, 1, f->lf_dark, f->lf_bright, f->lf_elast, s->stream);
+            } else if (f->kind == F_ADAPTIVEBINARIZE) {  // clip = the chain's source frame, clip2 = the chain's current value
+                rc = run_adaptivebinarize(l, s->dev[0], 0, s->dev[cur], 0, s->dev[nxt], 0, 1, f->ab_c, s->stream);
             } else {
                 if (bilateral_upload(f, dev_index)) return -1;
                 rc = bilateral_run(f, dev_index, s->dev[cur], 0, nullptr, 0, s->dev[nxt], 0, 1, s->stream);
