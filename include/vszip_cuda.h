@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define VSZIP_CUDA_ABI_VERSION 3  /* 2: + vszip_chain_*, vszip_limiter_*; 3: + vszip_limitfilter_*, vszip_adaptivebinarize_* */
+#define VSZIP_CUDA_ABI_VERSION 3  /* 2: + vszip_chain_*, vszip_limiter_*; 3: + vszip_limitfilter_*, vszip_adaptivebinarize_*, vszip_planestats_device */
 
 /* VapourSynth4.h values (VSColorFamily / VSSampleType) so the Zig glue can pass vi.format as is. */
 enum { VSZIP_CF_GRAY = 1, VSZIP_CF_RGB = 2, VSZIP_CF_YUV = 3 };
@@ -246,6 +246,15 @@ int vszip_planeminmax_device(const vszip_filter* f, const vszip_dev_clip* clipa,
                              int32_t first, int32_t count, vszip_minmax_props* out, void* stream);
 int vszip_planeaverage_device(const vszip_filter* f, const vszip_dev_clip* clipa, const vszip_dev_clip* clipb,
                               int32_t first, int32_t count, vszip_average_props* out, void* stream);
+/* PlaneMinMax + PlaneAverage over the same frames (BASELINE config 4 runs both over the same plane).
+ * When the pair is eligible - 9..16-bit integer clip, both filters created without clipb and for the same planes, thresholds
+ * set, at most 4 distinct exclude values inside the sample range - ONE kernel reads each plane once and produces both
+ * results; otherwise the two reductions run one after the other.  Results are identical to the two separate calls either
+ * way.  *fused_out (may be NULL) reports which route ran.  Either out pointer may be NULL (results stay on the device and
+ * the stream is not synchronised when both are). */
+int vszip_planestats_device(const vszip_filter* minmax, const vszip_filter* average, const vszip_dev_clip* clipa,
+                            int32_t first, int32_t count, vszip_minmax_props* minmax_out, vszip_average_props* average_out,
+                            int32_t* fused_out, void* stream);
 int vszip_limiter_device(const vszip_filter* f, const vszip_dev_clip* src, vszip_dev_clip* dst,
                          int32_t first, int32_t count, void* stream);
 int vszip_limitfilter_device(const vszip_filter* f, const vszip_dev_clip* flt, const vszip_dev_clip* src,

@@ -135,6 +135,9 @@ def both_stats_cfg(fmt, w, h, frames, mm_args, excl):
         vz._check(lib.vszip_planeminmax_device(mmf.handle, src.handle, None, 0, frames, None, st.cuda_stream))
         vz._check(lib.vszip_planeaverage_device(avf.handle, src.handle, None, 0, frames, None, st.cuda_stream))
     record(f"C4 PlaneMinMax(thr)+PlaneAverage {fmt} 4K, both batch calls back to back", fmt, w, h, frames, src.frame_bytes, timed(separate, args.reps))
+    _, fused = vz.plane_stats_device(mmf, avf, src, count=frames, stream=st.cuda_stream, fetch=False)
+    ms = timed(lambda: vz.plane_stats_device(mmf, avf, src, count=frames, stream=st.cuda_stream, fetch=False), args.reps)
+    record(f"C4 vszip_planestats_device {fmt} 4K ({'ONE read, fused kernel' if fused else 'not eligible: two reads'}) (8f rank 4)", fmt, w, h, frames, src.frame_bytes, ms)
     src.free()
 
 

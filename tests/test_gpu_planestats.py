@@ -230,3 +230,44 @@ def test_device_batch():
         props_close(got_mm[i], oa.planeminmax(ca, minthr=0.1, maxthr=0.2, clipb=cb))
         props_close(got_av[i], oa.planeaverage(ca, [7, 9], clipb=cb))
 
+
+
+@pytest.mark.parametrize(("fmt", "w", "h", "n"), [("GRAY16", 1920, 1080, 5), ("YUV420P16", 640, 360, 4), ("GRAY10", 517, 243, 3), ("GRAYS", 640, 360, 2), ("GRAY8", 517, 243, 2)])
+def test_minmax_and_average_from_one_read(fmt, w, h, n):
+    """vszip_planestats_device - one kernel reads each plane once and yields both filters' props when the pair is
+    eligible (16-bit integer storage, thresholds, <= 4 distinct in-range exclude values); identical to the separate calls and the oracle."""
+    base = "GRAY16" if fmt == "GRAY10" else fmt
+    a = vz.DeviceClip(fmt, w, h, n)
+    if fmt == "GRAY10":
+        src = [noise_clip(base, w, h, seed=40 + i)["planes"][0] >> 6 for i in range(n)]
+        for i, p in enumerate(src):
+            a.upload(i, [p])
+    else:
+        a.fill_noise(seed=21)
+    planes = [0, 1, 2] if fmt.startswith("YUV") else [0]
+    is16 = fmt in ("GRAY16", "YUV420P16", "GRAY10")
+    cases = [(dict(minthr=0.1, maxthr=0.2), [0, 32768], is16), (dict(minthr=0.1, maxthr=0.2), [], is16), (dict(minthr=0.05, maxthr=0.3), [7], is16),
+             (dict(minthr=0.1, maxthr=0.0), [1, 2, 3, 4], is16), (dict(minthr=0.2, maxthr=0.1), [70000, -1, 5, 5, 9], is16),
+             (dict(minthr=0.1, maxthr=0.2), [1, 2, 3, 4, 5], False), (dict(), [0, 1], False)]
+    for mm_args, excl, want_fused in cases:
+        if fmt == "GRAYS":
+            excl = [e for e in excl if 0 <= e <= 1] or [0]
+        mmf = vz.PlaneMinMaxFilter(a.info(), None, planes=planes, **mm_args)
+        avf = vz.PlaneAverageFilter(a.info(), None, exclude=excl, planes=planes)
+        sep_mm, sep_av = mmf.run_device(a), avf.run_device(a)
+        got, fused = vz.plane_stats_device(mmf, avf, a)
+        assert fused == want_fused, (fmt, mm_args, excl, fused)
+        for i in range(n):
+            want = dict(sep_mm[i]); want.update(sep_av[i])
+            props_close(got[i], want)
+            if fused:
+                assert got[i] == want, (fmt, mm_args, excl, i)     # integer clips: exact
+        ca = {"format": fmt, "planes": a.download(n - 1)}
+        props_close({k: v for k, v in got[n - 1].items() if k in ("psmMin", "psmMax")}, oa.planeminmax(ca, planes=planes, **mm_args))
+        props_close({k: v for k, v in got[n - 1].items() if k == "psmAvg"}, oa.planeaverage(ca, excl, planes=planes))
+    # different plane sets are not fused; a sub-range of the clip
+    if fmt == "YUV420P16":
+        mmf = vz.PlaneMinMaxFilter(a.info(), None, planes=[0], minthr=0.1, maxthr=0.1)
+        avf = vz.PlaneAverageFilter(a.info(), None, exclude=[3], planes=[0, 1])
+        got, fused = vz.plane_stats_device(mmf, avf, a, first=1, count=2)
+        assert not fused and len(got) == 2 and got[1]["psmMax"] == mmf.run_device(a)[2]["psmMax"] and got[0]["psmAvg"] == avf.run_device(a)[1]["psmAvg"]

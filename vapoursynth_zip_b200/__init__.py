@@ -17,7 +17,7 @@ from pathlib import Path
 
 import numpy as np
 
-__all__ = ["Error", "core", "VideoFormat", "VideoFrame", "VideoNode", "DeviceClip", "GRAY", "RGB", "YUV", "INTEGER", "FLOAT"]
+__all__ = ["Error", "core", "plane_stats_device", "VideoFormat", "VideoFrame", "VideoNode", "DeviceClip", "GRAY", "RGB", "YUV", "INTEGER", "FLOAT"]
 
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ.get("VSZIP_CUDA_LIB") or (_PKG / "lib" / "libvszip_cuda.so"))  # override: A/B builds only
@@ -115,6 +115,7 @@ ABI = {
     "vszip_planeaverage_create": (_P, [C.POINTER(_VideoInfo), C.POINTER(_VideoInfo), C.POINTER(_AverageArgs)]),
     "vszip_planeaverage_get_frame": (C.c_int, [_P, C.c_int32, C.POINTER(_Frame), C.POINTER(_Frame), C.POINTER(_AverageProps)]),
     "vszip_planeaverage_device": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.POINTER(_AverageProps), _P]),
+    "vszip_planestats_device": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.POINTER(_MinMaxProps), C.POINTER(_AverageProps), C.POINTER(C.c_int32), _P]),
     "vszip_filter_free": (None, [_P]),
     "vszip_filter_planes": (C.c_int, [_P, C.POINTER(C.c_int32 * 3)]),
     "vszip_dev_clip_alloc": (_P, [C.POINTER(_VideoInfo), C.c_int32, C.c_int32]),
@@ -410,6 +411,24 @@ class PlaneAverageFilter(_Filter):
         out = (_AverageProps * max(count, 1))()
         _check(load_library().vszip_planeaverage_device(self.handle, clipa.handle, clipb.handle if clipb else None, first, count, out, stream))
         return [self.to_props(out[i], prop) for i in range(count)]
+
+
+def plane_stats_device(minmax: "PlaneMinMaxFilter", average: "PlaneAverageFilter", clipa, first=0, count=None, stream=None, prop="psm", fetch=True):
+    """PlaneMinMax + PlaneAverage over the same device-resident frames (vszip_planestats_device): one read of each plane when the pair
+    is eligible.  Returns (props per frame - both filters' props merged, like `clip.vszip.PlaneMinMax().vszip.PlaneAverage()` -, fused)."""
+    count = clipa.num_frames - first if count is None else count
+    mm = (_MinMaxProps * max(count, 1))() if fetch else None
+    av = (_AverageProps * max(count, 1))() if fetch else None
+    fused = C.c_int32(0)
+    _check(load_library().vszip_planestats_device(minmax.handle, average.handle, clipa.handle, first, count, mm, av, C.byref(fused), stream))
+    if not fetch:
+        return None, bool(fused.value)
+    out = []
+    for i in range(count):
+        p = PlaneMinMaxFilter.to_props(mm[i], prop)
+        p.update(PlaneAverageFilter.to_props(av[i], prop))
+        out.append(p)
+    return out, bool(fused.value)
 
 
 class LimiterFilter(_Filter):

@@ -704,6 +704,57 @@ int vszip_planeaverage_device(const vszip_filter* f, const vszip_dev_clip* a, co
     return rc;
 }
 
+// =========================================================================== PlaneMinMax + PlaneAverage from one read
+int vszip_planestats_device(const vszip_filter* fm, const vszip_filter* fa, const vszip_dev_clip* a, int32_t first, int32_t count,
+                            vszip_minmax_props* mm_out, vszip_average_props* avg_out, int32_t* fused_out, void* stream) {
+    static const char* name = "PlaneStats";
+    if (fused_out) *fused_out = 0;
+    if (!fm || fm->kind != F_PLANEMINMAX || !fa || fa->kind != F_PLANEAVERAGE) { set_error("PlaneStats: a PlaneMinMax and a PlaneAverage handle are required"); return -1; }
+    if (fm->has_ref || fa->has_ref) { set_error("PlaneStats: filters created with clipb cannot be combined"); return -1; }
+    if (!same_clip_shape(a, fm, name) || !same_clip_shape(a, fa, name) || !range_ok(a, first, count, name)) return -1;
+    DeviceCtx* d = device_ctx(a->device_index);
+    if (!d) { set_error("PlaneStats: library not initialised"); return -1; }
+    VSZ_CUDA(cudaSetDevice(d->ordinal));
+    cudaStream_t st = stream ? (cudaStream_t)stream : d->batch_stream;
+    const int npm = processed_planes(fm), npa = processed_planes(fa);
+    if (count == 0) return 0;
+    const size_t fs = a->layout.frame_stride;
+    const char* base = a->base + (size_t)first * fs;
+    const bool same_planes = fm->process[0] == fa->process[0] && fm->process[1] == fa->process[1] && fm->process[2] == fa->process[2];
+    const size_t sbm = stats_scratch_bytes(count, std::max(npm, 1)), sba = stats_scratch_bytes(count, std::max(npa, 1));
+    const size_t rbm = sizeof(StatsRaw) * (size_t)count * npm, rba = sizeof(StatsRaw) * (size_t)count * npa;
+    const size_t rbm_al = (rbm + 255) & ~(size_t)255;
+    char* scratch = nullptr;
+    VSZ_CUDA(cudaMallocAsync((void**)&scratch, sbm + sba + rbm_al + rba + 256, st));
+    StatsRaw* raw_m = (StatsRaw*)(scratch + sbm + sba);
+    StatsRaw* raw_a = (StatsRaw*)(scratch + sbm + sba + rbm_al);
+    int rc = 1;
+    if (same_planes && npm > 0 && !fm->no_thr && fa->exclude_i.size() <= 16)
+        rc = run_planestats_fused(fm->layout, fm->process, base, fs, count, fm->minthr, fm->maxthr, fm->hist_size, fa->exclude_i.data(),
+                                  (int)fa->exclude_i.size(), scratch, raw_m, raw_a, st);
+    if (rc == 0 && fused_out) *fused_out = 1;
+    if (rc == 1) {  // not eligible: the two reductions one after the other (two reads)
+        rc = 0;
+        if (npm) rc = run_planeminmax(fm->layout, fm->process, base, fs, nullptr, fs, count, fm->no_thr, fm->minthr, fm->maxthr, fm->hist_size, scratch, raw_m, st);
+        const int32_t* xi; const float* xf;
+        if (!rc && npa && average_upload(fa, a->device_index, &xi, &xf)) rc = -1;
+        if (!rc && npa) rc = run_planeaverage(fa->layout, fa->process, base, fs, nullptr, fs, count, fa->exclude_i.data(), fa->exclude_f.data(),
+                                               (int)fa->exclude_i.size(), xi, xf, scratch + sbm, raw_a, st);
+    }
+    if (!rc && (mm_out || avg_out)) {
+        std::vector<StatsRaw> hm((size_t)count * npm), ha((size_t)count * npa);
+        if (mm_out && npm) VSZ_CUDA(cudaMemcpyAsync(hm.data(), raw_m, rbm, cudaMemcpyDeviceToHost, st));
+        if (avg_out && npa) VSZ_CUDA(cudaMemcpyAsync(ha.data(), raw_a, rba, cudaMemcpyDeviceToHost, st));
+        VSZ_CUDA(cudaStreamSynchronize(st));
+        for (int i = 0; i < count; ++i) {
+            if (mm_out) minmax_finalize(fm, hm.data() + (size_t)i * npm, mm_out + i);
+            if (avg_out) average_finalize(fa, ha.data() + (size_t)i * npa, avg_out + i);
+        }
+    }
+    VSZ_CUDA(cudaFreeAsync(scratch, st));
+    return rc;
+}
+
 // =========================================================================== Limiter
 // Range tables of src/filters/limiter.zig:66-91: [lo|hi][plane] for full / tv-range YUV / tv-range RGB at 8 bits;
 // deeper integer formats are the 8-bit values shifted left by (bits - 8), full range is (1 << bits) - 1.

@@ -71,6 +71,7 @@ struct StatsJob {
     int sample_ctas_per_frame, bracket_ctas_per_frame;
     int sshift;               // sample bin = bin >> sshift
     StatsRaw* out;            // [frame][plane]
+    StatsRaw* out_avg;        // [frame][plane] PlaneAverage results of the fused bracket kernel
     // parameters
     int nex;
     int32_t excl_i[16];
@@ -744,9 +745,19 @@ __device__ __forceinline__ PackedThr packed_thr(unsigned int t) {
 // TRACK = false: every bin is valid (full-depth integer or float clip) and both ranks are > 0, so the exact
 // min/max tracking drops out of the per-sample work.  With TRACK the packed min/max give the answers for zero
 // ranks and detect samples above the format's peak (such planes are left to the exact two-pass kernels).
-template <typename T, bool HAS_B, bool TRACK>
+// AVG >= 0 (16-bit integer clips without clipb): the same single read also yields PlaneAverage with AVG distinct in-range exclude
+// values - IDP.2A sums both halves of a word, one XOR + VIMNMX.U16x2 per exclude value counts the halves that
+// differ from it (the arithmetic of average_u16_kernel); sum and excluded count travel in the Partial's idiff / excluded fields.
+template <typename T, bool HAS_B, bool TRACK, int AVG = -1>
 __global__ void __launch_bounds__(NT) minmax_bracket_kernel(const StatsJob j) {
+    static_assert(AVG < 0 || (std::is_same<T, uint16_t>::value && !HAS_B), "the fused average is for 16-bit integer clips without clipb");
     constexpr int V = El<T>::PER16, NW = V / 2, G = HAS_B ? 2 : 4;
+    constexpr int NEX = AVG > 0 ? AVG : 1;
+    unsigned int ee[NEX], pk_ne[NEX], differing[NEX];
+#pragma unroll
+    for (int e = 0; e < NEX; ++e) { ee[e] = AVG > 0 ? (unsigned)j.excl_i[e] * 0x10001u : 0u; pk_ne[e] = 0u; differing[e] = 0u; }
+    unsigned int s32 = 0u, seen = 0u;
+    unsigned long long sum64 = 0ull;
     __shared__ unsigned int s_fine[2][FINE_W];
     __shared__ uint4 s_q[NT / 32][G * 32];  // per warp: the vectors of one step that hold a sample inside a bracket
     // own plane map: in large batches this kernel uses fewer, longer-running CTAs than the other reductions
@@ -792,7 +803,13 @@ __global__ void __launch_bounds__(NT) minmax_bracket_kernel(const StatsJob j) {
             pk_ge_umax += m3 - t3.C;
             any |= (m0 - m1 + k01) | (m2 - m3 + k23);  // per half: 1 if inside the min / max bracket
             if constexpr (TRACK) { pk_min = __vminu2(pk_min, w[q]); pk_max = __vmaxu2(pk_max, w[q]); }
+            if constexpr (AVG >= 0) {
+                s32 = __dp2a_lo(w[q], 0x0101u, s32);
+#pragma unroll
+                for (int e = 0; e < AVG; ++e) pk_ne[e] += __vminu2(w[q] ^ ee[e], 0x10001u);
+            }
         }
+        if constexpr (AVG >= 0) seen += (unsigned)V;
         if constexpr (HAS_B) {
             const T* ae = reinterpret_cast<const T*>(&av);
             const T* be = reinterpret_cast<const T*>(&bv);
@@ -808,6 +825,12 @@ __global__ void __launch_bounds__(NT) minmax_bracket_kernel(const StatsJob j) {
         fine_add(bin, 1u);
         if constexpr (TRACK) { pk_min = __vminu2(pk_min, bin * 0x10001u); pk_max = __vmaxu2(pk_max, bin * 0x10001u); }
         if constexpr (HAS_B) acc.fdiff += abs_diff<T>(at, bt, idiff32);
+        if constexpr (AVG >= 0) {
+            s32 += bin;
+#pragma unroll
+            for (int e = 0; e < AVG; ++e) differing[e] += (bin != (unsigned)j.excl_i[e]) ? 1u : 0u;
+            seen += 1u;
+        }
     };
 
     const int nvec = p.w / V;
@@ -875,6 +898,23 @@ __global__ void __launch_bounds__(NT) minmax_bracket_kernel(const StatsJob j) {
         ge_umax += (pk_ge_umax & 0xffffu) + (pk_ge_umax >> 16);
         pk_ge_lmin = pk_ge_umax = 0u;
         acc.idiff += idiff32; idiff32 = 0;
+        if constexpr (AVG >= 0) {  // same bounds: <= 4 * 32 * 4 per packed half, <= 4 * 32 * 8 * 65535 in s32 per group of rows
+            sum64 += s32; s32 = 0u;
+#pragma unroll
+            for (int e = 0; e < AVG; ++e) { differing[e] += (pk_ne[e] & 0xffffu) + (pk_ne[e] >> 16); pk_ne[e] = 0u; }
+        }
+    }
+    if constexpr (AVG >= 0) {
+        unsigned long long removed = 0ull;
+        unsigned int excluded = 0u;
+#pragma unroll
+        for (int e = 0; e < AVG; ++e) {
+            const unsigned int cnt = seen - differing[e];
+            excluded += cnt;
+            removed += (unsigned long long)cnt * (unsigned)j.excl_i[e];
+        }
+        acc.idiff = sum64 - removed;  // (no clipb here: the diff field is free)
+        acc.excluded = excluded;
     }
     acc.isum = (unsigned long long)ge_lmin + ((unsigned long long)ge_umax << 32);
     acc.imin = min(pk_min & 0xffffu, pk_min >> 16);
@@ -892,7 +932,13 @@ __global__ void __launch_bounds__(NT) minmax_bracket_kernel(const StatsJob j) {
     __shared__ int s_okk[2];
     if (threadIdx.x == 0) {
         StatsRaw& r = j.out[fp];
-        r.idiff = total.idiff; r.fdiff = total.fdiff;
+        if constexpr (AVG >= 0) {
+            StatsRaw ra{};
+            ra.isum = total.idiff; ra.excluded = total.excluded;
+            j.out_avg[fp] = ra;
+        } else {
+            r.idiff = total.idiff; r.fdiff = total.fdiff;
+        }
         const unsigned long long npx0 = (unsigned long long)p.w * p.h;
         s_cnt[0] = (unsigned int)(npx0 - (total.isum & 0xffffffffull));  // samples below l_min
         s_cnt[1] = (unsigned int)(total.isum >> 32);                     // samples at or above u_max
@@ -1084,6 +1130,68 @@ int run_planeminmax(const FrameLayout& l, const bool mask[3], const char* a, siz
         case K_F32: return launch_minmax_t<float>(j, count, no_thr, has_b, fb, st);
     }
     return -1;
+}
+
+// PlaneMinMax (threshold path) + PlaneAverage of the same planes from ONE read.  Returns 1 when the
+// combination is not eligible (the caller then runs the two reductions separately), 0 on success, < 0 on error.
+// Eligible: 16-bit integer storage, no clipb, thresholds set, sampled fast path enabled, at most 4 distinct in-range exclude values.
+int run_planestats_fused(const FrameLayout& l, const bool mask[3], const char* a, size_t a_fs, int count, float minthr, float maxthr,
+                         uint32_t hist_size, const int32_t* excl, int nex, void* scratch, StatsRaw* out_mm, StatsRaw* out_avg, cudaStream_t st) {
+    if (l.kind != K_U16 || count <= 0 || count > 32768) return 1;
+    const char* ev = getenv("VSZIP_MINMAX_EXACT");
+    if (ev && ev[0] == '1') return 1;
+    int32_t ex[4];
+    int m = 0;
+    for (int i = 0; i < nex; ++i) {
+        const int32_t v = excl[i];
+        if (v < 0 || v > 65535) continue;  // can never match a sample
+        bool dup = false;
+        for (int t = 0; t < m; ++t) dup = dup || ex[t] == v;
+        if (dup) continue;
+        if (m == 4) return 1;
+        ex[m++] = v;
+    }
+    size_t zero = 0;
+    StatsJob j = make_job(l, mask, a, a_fs, nullptr, 0, count, scratch, out_mm, &zero);
+    if (j.ctas_per_frame == 0) return 1;
+    for (int k = 0; k < j.nplanes; ++k)
+        if ((long long)j.pl[k].w * j.pl[k].h >= (1ll << 31)) return 1;
+    VSZ_CUDA(cudaMemsetAsync(scratch, 0, zero, st));
+    VSZ_CUDA(cudaMemsetAsync(out_mm, 0, sizeof(StatsRaw) * (size_t)count * j.nplanes, st));
+    j.out_avg = out_avg;
+    j.hist_size = hist_size;
+    int bits = 0;
+    while ((1u << bits) < hist_size) ++bits;
+    j.shift = bits > 8 ? bits - 8 : 0;
+    j.sshift = bits > 12 ? bits - 12 : 0;
+    for (int k = 0; k < j.nplanes; ++k) {
+        const double total = (double)((uint32_t)j.pl[k].w * (uint32_t)j.pl[k].h);
+        j.pl[k].tmin = (unsigned int)(total * (double)minthr);
+        j.pl[k].tmax = (unsigned int)(total * (double)maxthr);
+    }
+    j.nex = m;
+    for (int i = 0; i < m; ++i) j.excl_i[i] = ex[i];
+    bool lean = j.hist_size == 65536u;
+    for (int k = 0; k < j.nplanes; ++k) lean = lean && j.pl[k].tmin > 0u && j.pl[k].tmax > 0u;
+    hist_sample_kernel<uint16_t><<<dim3(j.sample_ctas_per_frame, count), NT, 0, st>>>(j);
+    const dim3 bgrid(j.bracket_ctas_per_frame, count);
+#define VSZ_FUSED(M) (lean ? (void)(minmax_bracket_kernel<uint16_t, false, false, M><<<bgrid, NT, 0, st>>>(j)) \
+                           : (void)(minmax_bracket_kernel<uint16_t, false, true, M><<<bgrid, NT, 0, st>>>(j)))
+    switch (m) {
+        case 0: VSZ_FUSED(0); break;
+        case 1: VSZ_FUSED(1); break;
+        case 2: VSZ_FUSED(2); break;
+        case 3: VSZ_FUSED(3); break;
+        default: VSZ_FUSED(4); break;
+    }
+#undef VSZ_FUSED
+    // exact two-pass select for the planes the sampled path could not resolve (immediate exit otherwise)
+    const dim3 xgrid(j.ctas_per_frame, std::min(count, 8));
+    hist_coarse_kernel<uint16_t, false><<<xgrid, NT, 0, st>>>(j, count);
+    hist_fine_kernel<uint16_t><<<xgrid, NT, 0, st>>>(j, count);
+    count_launch(4);
+    VSZ_CUDA(cudaGetLastError());
+    return 0;
 }
 
 template <typename T>
