@@ -874,6 +874,8 @@ vszip_filter* vszip_limitfilter_create(const vszip_video_info* flt_vi, const vsz
     static const char* name = "LimitFilter";
     if (!basic_vi_ok(flt_vi, name)) return nullptr;
     if (!src_vi) { set_error("LimitFilter: the src clip is required"); return nullptr; }
+    static const vszip_limitfilter_args none = {nullptr, 0, nullptr, 0, nullptr, 0, nullptr, -1, -1};
+    if (!a) a = &none;
     SampleKind kind;
     if (!select_kind(*flt_vi, name, false, &kind)) return nullptr;                     // limit_filter.zig:101
     if (!compare_nodes(*flt_vi, *src_vi, name, true)) return nullptr;                  // :107-108, SAME_LEN
