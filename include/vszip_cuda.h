@@ -247,7 +247,7 @@ int vszip_planeminmax_device(const vszip_filter* f, const vszip_dev_clip* clipa,
 int vszip_planeaverage_device(const vszip_filter* f, const vszip_dev_clip* clipa, const vszip_dev_clip* clipb,
                               int32_t first, int32_t count, vszip_average_props* out, void* stream);
 /* PlaneMinMax + PlaneAverage over the same frames (BASELINE config 4 runs both over the same plane).
- * When the pair is eligible - 9..16-bit integer clip, both filters created without clipb and for the same planes, thresholds
+ * When the pair is eligible - 8..16-bit integer clip, both filters created without clipb and for the same planes, thresholds
  * set, at most 4 distinct exclude values inside the sample range - ONE kernel reads each plane once and produces both
  * results; otherwise the two reductions run one after the other.  Results are identical to the two separate calls either
  * way.  *fused_out (may be NULL) reports which route ran.  Either out pointer may be NULL (results stay on the device and

@@ -245,8 +245,10 @@ def test_minmax_and_average_from_one_read(fmt, w, h, n):
     else:
         a.fill_noise(seed=21)
     planes = [0, 1, 2] if fmt.startswith("YUV") else [0]
-    is16 = fmt in ("GRAY16", "YUV420P16", "GRAY10")
-    cases = [(dict(minthr=0.1, maxthr=0.2), [0, 32768], is16), (dict(minthr=0.1, maxthr=0.2), [], is16), (dict(minthr=0.05, maxthr=0.3), [7], is16),
+    is16 = fmt in ("GRAY16", "YUV420P16", "GRAY10", "GRAY8")   # integer clips are eligible for the one-read kernel
+    if fmt == "GRAY8":
+        a.upload(0, [np.full((h, w), 200, np.uint8)])   # a flat frame next to the noise frames
+    cases = [(dict(minthr=0.1, maxthr=0.2), [0, 32768], is16), (dict(minthr=0.1, maxthr=0.2), [200, 7, 255], is16), (dict(minthr=0.1, maxthr=0.2), [], is16), (dict(minthr=0.05, maxthr=0.3), [7], is16),
              (dict(minthr=0.1, maxthr=0.0), [1, 2, 3, 4], is16), (dict(minthr=0.2, maxthr=0.1), [70000, -1, 5, 5, 9], is16),
              (dict(minthr=0.1, maxthr=0.2), [1, 2, 3, 4, 5], False), (dict(), [0, 1], False)]
     for mm_args, excl, want_fused in cases:

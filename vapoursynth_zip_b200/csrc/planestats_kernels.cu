@@ -745,12 +745,12 @@ __device__ __forceinline__ PackedThr packed_thr(unsigned int t) {
 // TRACK = false: every bin is valid (full-depth integer or float clip) and both ranks are > 0, so the exact
 // min/max tracking drops out of the per-sample work.  With TRACK the packed min/max give the answers for zero
 // ranks and detect samples above the format's peak (such planes are left to the exact two-pass kernels).
-// AVG >= 0 (16-bit integer clips without clipb): the same single read also yields PlaneAverage with AVG distinct in-range exclude
+// AVG >= 0 (8..16-bit integer clips without clipb): the same single read also yields PlaneAverage with AVG distinct in-range exclude
 // values - IDP.2A sums both halves of a word, one XOR + VIMNMX.U16x2 per exclude value counts the halves that
 // differ from it (the arithmetic of average_u16_kernel); sum and excluded count travel in the Partial's idiff / excluded fields.
 template <typename T, bool HAS_B, bool TRACK, int AVG = -1>
 __global__ void __launch_bounds__(NT) minmax_bracket_kernel(const StatsJob j) {
-    static_assert(AVG < 0 || (std::is_same<T, uint16_t>::value && !HAS_B), "the fused average is for 16-bit integer clips without clipb");
+    static_assert(AVG < 0 || (!El<T>::flt && !HAS_B), "the fused average is for integer clips without clipb");
     constexpr int V = El<T>::PER16, NW = V / 2, G = HAS_B ? 2 : 4;
     constexpr int NEX = AVG > 0 ? AVG : 1;
     unsigned int ee[NEX], pk_ne[NEX], differing[NEX];
@@ -1134,17 +1134,43 @@ int run_planeminmax(const FrameLayout& l, const bool mask[3], const char* a, siz
 
 // PlaneMinMax (threshold path) + PlaneAverage of the same planes from ONE read.  Returns 1 when the
 // combination is not eligible (the caller then runs the two reductions separately), 0 on success, < 0 on error.
-// Eligible: 16-bit integer storage, no clipb, thresholds set, sampled fast path enabled, at most 4 distinct in-range exclude values.
+// Eligible: 8..16-bit integer clips, no clipb, thresholds set, sampled fast path enabled, at most 4 distinct in-range exclude values.
+template <typename T>
+static int launch_fused_t(const StatsJob& j, int count, int m, cudaStream_t st) {
+    bool lean = (j.hist_size == 65536u) || (sizeof(T) == 1 && j.hist_size == 256u);
+    for (int k = 0; k < j.nplanes; ++k) lean = lean && j.pl[k].tmin > 0u && j.pl[k].tmax > 0u;
+    hist_sample_kernel<T><<<dim3(j.sample_ctas_per_frame, count), NT, 0, st>>>(j);
+    const dim3 bgrid(j.bracket_ctas_per_frame, count);
+#define VSZ_FUSED(M) (lean ? (void)(minmax_bracket_kernel<T, false, false, M><<<bgrid, NT, 0, st>>>(j)) \
+                           : (void)(minmax_bracket_kernel<T, false, true, M><<<bgrid, NT, 0, st>>>(j)))
+    switch (m) {
+        case 0: VSZ_FUSED(0); break;
+        case 1: VSZ_FUSED(1); break;
+        case 2: VSZ_FUSED(2); break;
+        case 3: VSZ_FUSED(3); break;
+        default: VSZ_FUSED(4); break;
+    }
+#undef VSZ_FUSED
+    // exact two-pass select for the planes the sampled path could not resolve (immediate exit otherwise)
+    const dim3 xgrid(j.ctas_per_frame, std::min(count, 8));
+    hist_coarse_kernel<T, false><<<xgrid, NT, 0, st>>>(j, count);
+    hist_fine_kernel<T><<<xgrid, NT, 0, st>>>(j, count);
+    count_launch(4);
+    VSZ_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int run_planestats_fused(const FrameLayout& l, const bool mask[3], const char* a, size_t a_fs, int count, float minthr, float maxthr,
                          uint32_t hist_size, const int32_t* excl, int nex, void* scratch, StatsRaw* out_mm, StatsRaw* out_avg, cudaStream_t st) {
-    if (l.kind != K_U16 || count <= 0 || count > 32768) return 1;
+    if ((l.kind != K_U16 && l.kind != K_U8) || count <= 0 || count > 32768) return 1;
     const char* ev = getenv("VSZIP_MINMAX_EXACT");
     if (ev && ev[0] == '1') return 1;
+    const int32_t top = l.kind == K_U8 ? 255 : 65535;
     int32_t ex[4];
     int m = 0;
     for (int i = 0; i < nex; ++i) {
         const int32_t v = excl[i];
-        if (v < 0 || v > 65535) continue;  // can never match a sample
+        if (v < 0 || v > top) continue;  // can never match a sample
         bool dup = false;
         for (int t = 0; t < m; ++t) dup = dup || ex[t] == v;
         if (dup) continue;
@@ -1171,27 +1197,7 @@ int run_planestats_fused(const FrameLayout& l, const bool mask[3], const char* a
     }
     j.nex = m;
     for (int i = 0; i < m; ++i) j.excl_i[i] = ex[i];
-    bool lean = j.hist_size == 65536u;
-    for (int k = 0; k < j.nplanes; ++k) lean = lean && j.pl[k].tmin > 0u && j.pl[k].tmax > 0u;
-    hist_sample_kernel<uint16_t><<<dim3(j.sample_ctas_per_frame, count), NT, 0, st>>>(j);
-    const dim3 bgrid(j.bracket_ctas_per_frame, count);
-#define VSZ_FUSED(M) (lean ? (void)(minmax_bracket_kernel<uint16_t, false, false, M><<<bgrid, NT, 0, st>>>(j)) \
-                           : (void)(minmax_bracket_kernel<uint16_t, false, true, M><<<bgrid, NT, 0, st>>>(j)))
-    switch (m) {
-        case 0: VSZ_FUSED(0); break;
-        case 1: VSZ_FUSED(1); break;
-        case 2: VSZ_FUSED(2); break;
-        case 3: VSZ_FUSED(3); break;
-        default: VSZ_FUSED(4); break;
-    }
-#undef VSZ_FUSED
-    // exact two-pass select for the planes the sampled path could not resolve (immediate exit otherwise)
-    const dim3 xgrid(j.ctas_per_frame, std::min(count, 8));
-    hist_coarse_kernel<uint16_t, false><<<xgrid, NT, 0, st>>>(j, count);
-    hist_fine_kernel<uint16_t><<<xgrid, NT, 0, st>>>(j, count);
-    count_launch(4);
-    VSZ_CUDA(cudaGetLastError());
-    return 0;
+    return l.kind == K_U8 ? launch_fused_t<uint8_t>(j, count, m, st) : launch_fused_t<uint16_t>(j, count, m, st);
 }
 
 template <typename T>
