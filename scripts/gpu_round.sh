@@ -18,7 +18,8 @@ timeout 600 ncu --set full --clock-control none --import-source on -k "regex:sta
 timeout 600 ncu --set full --clock-control none --import-source on -k "regex:hist_sample|minmax_bracket" -s 2 -c 2 -o $O/ncu_minmax_$R python scripts/prof_run.py minmax 32 2 > /dev/null 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k "regex:limitfilter_kernel" -s 1 -c 1 -o $O/ncu_limitfilter_$R python scripts/prof_run.py limitfilter 32 2 > /dev/null 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k "regex:adaptivebinarize" -s 1 -c 1 -o $O/ncu_binarize_$R python scripts/prof_run.py binarize 32 2 > /dev/null 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k "regex:minmax_bracket" -s 1 -c 1 -o $O/ncu_planestats_$R python scripts/prof_run.py planestats 32 2 > /dev/null 2>&1
 # summaries are made on the box; only the BoxBlur capture travels back as a .ncu-rep (gpurun merges at most 64 MiB)
 for f in $O/ncu_*_$R.ncu-rep; do python scripts/ncu_summary.py $f > ${f%.ncu-rep}.md 2>/dev/null; done
-for k in bilateral average minmax limitfilter binarize; do rm -f $O/ncu_${k}_$R.ncu-rep; done
+for k in bilateral average minmax limitfilter binarize planestats; do rm -f $O/ncu_${k}_$R.ncu-rep; done
 cat $O/pytest_gpu_$R.log; cat $O/bench_$R.json | cut -c1-400; tail -3 $O/bench_$R.err

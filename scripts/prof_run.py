@@ -1,5 +1,5 @@
 """Small driver for ncu captures: runs one filter over a device-resident noise batch a few times.
-usage: python scripts/prof_run.py boxblur|boxblur_ct|bilateral|pbfic|limitfilter|binarize|minmax|average [frames] [reps]"""
+usage: python scripts/prof_run.py boxblur|boxblur_ct|bilateral|pbfic|limitfilter|binarize|planestats|minmax|average [frames] [reps]"""
 import sys
 from pathlib import Path
 
@@ -10,7 +10,7 @@ what = sys.argv[1] if len(sys.argv) > 1 else "boxblur"
 frames = int(sys.argv[2]) if len(sys.argv) > 2 else 64
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 vz.core.init([0])
-if what in ("minmax", "average"):
+if what in ("minmax", "average", "planestats"):
     fmt, w, h = "GRAY16", 3840, 2160
 else:
     fmt, w, h = "YUV420P16", 1920, 1080
@@ -49,6 +49,10 @@ elif what == "binarize":
     src.fill_noise(seed=1234); b2.fill_noise(seed=99)
     f = vz.AdaptiveBinarizeFilter(src.info(), src.info(), c=3)
     run = lambda: f.run_device(src, b2, dst)
+elif what == "planestats":   # PlaneMinMax(thr) + PlaneAverage from one read (fused bracket kernel)
+    mmf = vz.PlaneMinMaxFilter(src.info(), minthr=0.1, maxthr=0.1)
+    avf = vz.PlaneAverageFilter(src.info(), exclude=[0, 32768])
+    run = lambda: vz.plane_stats_device(mmf, avf, src, fetch=False)
 elif what == "minmax":
     f = vz.PlaneMinMaxFilter(src.info(), minthr=0.1, maxthr=0.1)
     run = lambda: f.run_device(src)
