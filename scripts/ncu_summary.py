@@ -25,6 +25,15 @@ for r in rows[2:]:
     for k in want:
         if k in hdr:
             out.append(f"- {k}: {r[hdr.index(k)]} {units[hdr.index(k)]}")
+    pipes = []
+    for i, h in enumerate(hdr):
+        if h.startswith("sm__inst_executed_pipe_") and h.endswith(".sum") or (h.startswith("sm__pipe_") and "pct_of_peak_sustained_active" in h):
+            try:
+                if float(r[i].replace(",", "")) > 0:
+                    pipes.append(f"{h.replace('sm__inst_executed_pipe_', 'inst:').replace('.avg.pct_of_peak_sustained_active', '%').replace('sm__pipe_', 'busy:')}={r[i]}")
+            except ValueError:
+                pass
+    out.append("- pipes: " + ", ".join(pipes))
     stalls = []
     for i, h in enumerate(hdr):
         if h.startswith("smsp__pcsamp_warps_issue_stalled_") and not h.endswith("_not_issued"):

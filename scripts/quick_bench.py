@@ -25,8 +25,10 @@ cfgs = {"H5": dict(hradius=13, hpasses=5, vradius=0, vpasses=0), "V5": dict(hrad
 for p in (2, 3, 4):
     cfgs["H%d" % p] = dict(hradius=13, hpasses=p, vradius=0, vpasses=0)
     cfgs["V%d" % p] = dict(hradius=0, hpasses=0, vradius=13, vpasses=p)
+if len(sys.argv) > 3:
+    cfgs = {k: cfgs[k] for k in sys.argv[3].split(",")}
 out = {}
 for k, a in cfgs.items():
     ms = t(vz.BoxBlurFilter(src.info(), **a))
     out[k] = round(ms * 1000 / frames, 2)
-print("us/frame", out, "fps(HV5)=%d" % (1e6 / out["HV5"]))
+print("us/frame", out, ("fps(HV5)=%d" % (1e6 / out["HV5"])) if "HV5" in out else "")

@@ -22,7 +22,10 @@
 //   ctf_*_kernel  : comptime float path (direct sums, R101q).
 #include <cuda_fp16.h>
 
+#include <cstdlib>
+
 #include "common.h"
+#include "filter.h"
 
 namespace vsz {
 
@@ -1174,6 +1177,26 @@ static int run_ct_float(const FrameLayout& l, const bool mask[3], const char* sr
     return 0;
 }
 
+// 16-bit integer clips take the segment kernels (boxblur_seg_kernels.cu) where they apply; VSZIP_BOXBLUR_LEGACY=1 keeps
+// every clip on the streaming kernels of this file (A/B timing, and the parity tests run both).
+static bool use_seg_kernels() {
+    static const bool on = [] { const char* e = getenv("VSZIP_BOXBLUR_LEGACY"); return !(e && e[0] == '1'); }();
+    return on;
+}
+
+template <typename T, bool H>
+static int run_axis_any(const FrameLayout& l, const bool mask[3], const char* src, size_t sfs, char* dst, size_t dfs, int count, int r,
+                        int passes, cudaStream_t st) {
+    if constexpr (std::is_same<T, uint16_t>::value) {
+        if (use_seg_kernels()) {
+            const int rc = H ? run_seg_h_u16(l, mask, src, sfs, dst, dfs, count, r, passes, st)
+                             : run_seg_v_u16(l, mask, src, sfs, dst, dfs, count, r, passes, st);
+            if (rc <= 0) return rc;  // done, or a CUDA error; 1 = not applicable
+        }
+    }
+    return run_axis<T, H>(l, mask, src, sfs, dst, dfs, count, r, passes, st);
+}
+
 template <typename T>
 static int run_boxblur_t(const FrameLayout& l, const bool mask[3], const char* src, size_t sfs, char* dst, size_t dfs, int count,
                          int hr, int hp, int vr, int vp, cudaStream_t st) {
@@ -1182,8 +1205,8 @@ static int run_boxblur_t(const FrameLayout& l, const bool mask[3], const char* s
     if (use_rt) {
         const bool hb = hr > 0 && hp > 0, vb = vr > 0 && vp > 0;
         // "all H passes, then all V passes" (boxblur.zig:93-112), V in place on dst
-        if (hb) { const int rc = run_axis<T, true>(l, mask, src, sfs, dst, dfs, count, hr, hp, st); if (rc) return rc; }
-        if (vb) return run_axis<T, false>(l, mask, hb ? dst : src, hb ? dfs : sfs, dst, dfs, count, vr, vp, st);
+        if (hb) { const int rc = run_axis_any<T, true>(l, mask, src, sfs, dst, dfs, count, hr, hp, st); if (rc) return rc; }
+        if (vb) return run_axis_any<T, false>(l, mask, hb ? dst : src, hb ? dfs : sfs, dst, dfs, count, vr, vp, st);
         return 0;
     }
     if constexpr (Px<T>::flt) {
@@ -1194,7 +1217,13 @@ static int run_boxblur_t(const FrameLayout& l, const bool mask[3], const char* s
         VSZ_CUDA(cudaFreeAsync(tmp, st));
         return rc;
     } else {
-        // comptime integer path: exact R101q column sums + rounded mean, then the SYM H pass in place
+        // comptime integer path: exact R101q column sums + rounded mean, then the SYM H pass
+        if constexpr (std::is_same<T, uint16_t>::value) {
+            if (use_seg_kernels()) {  // one read, one write
+                const int rc = run_seg_ct_u16(l, mask, src, sfs, dst, dfs, count, hr, st);
+                if (rc <= 0) return rc;
+            }
+        }
         int rc = launch_v<T, 1, MODE_CTV>(l, mask, src, sfs, dst, dfs, count, hr, st);
         if (rc) return rc;
         return launch_h<T, 1>(l, mask, dst, dfs, dst, dfs, count, hr, st);

@@ -1,0 +1,186 @@
+// boxblur_seg_ct.cu — ctfused_kernel: the comptime path in one read and one write (see boxblur_seg.cuh for the design of the segment kernels).
+#include "boxblur_seg.cuh"
+
+namespace vsz {
+
+namespace {
+
+// =========================================================================== comptime path, fused
+constexpr int CTF_WARPS = 8;
+
+template <int CPT> struct ColVec;
+template <> struct ColVec<8> { using T = uint4; };
+template <> struct ColVec<4> { using T = uint2; };
+template <int CPT>
+__device__ __forceinline__ void colvec_words(const typename ColVec<CPT>::T& v, uint32_t (&w)[CPT / 2]) {
+    if constexpr (CPT == 8) { w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w; }
+    else { w[0] = v.x; w[1] = v.y; }
+}
+
+template <int R, int CPT>
+__global__ void __launch_bounds__(CTF_WARPS * 32, 2) ctfused_kernel(const SegJob job) {
+    using Gm = HGeom<R>;
+    using CV = typename ColVec<CPT>::T;
+    constexpr int CW = CPT / 2;
+    extern __shared__ __align__(128) unsigned char seg_smem[];
+    __shared__ uint64_t ring_bar;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int local;
+    const SegPlane& pj = seg_plane(job, blockIdx.y, local);
+    const int G = pj.G, RPW = 32 / G, sub = lane / G, sg0 = lane % G;
+    const int GR = CTF_WARPS * RPW;  // rows per group
+    const bool act = sg0 < pj.S;
+    const int sg = act ? sg0 : 0;
+    const int w = pj.w, h = pj.h;
+    const int y0 = local * pj.per_cta, y1 = min(y0 + pj.per_cta, h);
+    const uint32_t row_bytes = (uint32_t)((w * 2 + 15) & ~15);
+    unsigned char* ring = seg_smem;                                  // [2*GR][row_bytes]: rows entering (0..GR-1) and leaving (GR..) the window
+    unsigned char* tmpb = seg_smem + (size_t)2 * GR * row_bytes;     // [GR][rowbuf]: rounded column means, then the finished rows
+    const char* src = job.src + (size_t)blockIdx.x * job.src_fs + pj.src_off;
+    char* dst = job.dst + (size_t)blockIdx.x * job.dst_fs + pj.dst_off;
+    const int c0 = threadIdx.x * CPT;
+    const bool vact = c0 < w;
+
+    if (threadIdx.x == 0) {
+        mbar_init(&ring_bar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    // A row enters the window once and leaves it 2r+1 rows later: it is fetched from HBM the first time and kept in L2
+    // (evict_last) until the second, last read (evict_first); finished rows are written evict_first as well, so that the
+    // windows of all resident CTAs (~30 MB) are what stays in L2.
+    const uint64_t keep = l2_evict_last(), drop = l2_evict_first();
+    auto issue_ring = [&](int yg) {  // thread 0
+        mbar_expect_tx(&ring_bar, (uint32_t)(2 * GR) * row_bytes);
+        for (int j = 0; j < GR; ++j) {
+            const int y = min(yg + j, h - 1);
+            bulk_g2s_hint(ring + (size_t)j * row_bytes, src + (size_t)ct_add_row(y, R, h) * pj.src_pitch, row_bytes, &ring_bar, keep);
+            bulk_g2s_hint(ring + (size_t)(GR + j) * row_bytes, src + (size_t)ct_sub_row(y, R) * pj.src_pitch, row_bytes, &ring_bar, drop);
+        }
+    };
+    if (threadIdx.x == 0) issue_ring(y0);
+
+    // exact column sums of row y0: the 2r+1 R101q taps, straight from global memory
+    uint32_t col[CPT];
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) col[k] = 0u;
+    if (vact) {
+        constexpr int NB = 9;
+        for (int k0 = 0; k0 <= 2 * R; k0 += NB) {
+            CV v[NB];
+#pragma unroll
+            for (int u = 0; u < NB; ++u) {
+                const int k = min(k0 + u, 2 * R);
+                v[u] = *reinterpret_cast<const CV*>(src + (size_t)ct_tap_row(y0, k, R, h) * pj.src_pitch + (size_t)c0 * 2);
+            }
+#pragma unroll
+            for (int u = 0; u < NB; ++u) {
+                if (k0 + u <= 2 * R) {
+                    uint32_t ww[CW];
+                    colvec_words<CPT>(v[u], ww);
+#pragma unroll
+                    for (int m = 0; m < CW; ++m) { col[2 * m] = dp2a(ww[m], ADD_LO, col[2 * m]); col[2 * m + 1] += ww[m] >> 16; }
+                }
+            }
+        }
+    }
+
+    uint32_t e[Gm::NW], eo[Gm::NW];
+    int gi = 0;
+    for (int yg = y0; yg < y1; yg += GR, ++gi) {
+        // ---- V: rounded means of GR rows into tmpb, column sums stepped row by row
+        mbar_wait(&ring_bar, (uint32_t)gi & 1u);
+        if (vact) {
+            for (int j0 = 0; j0 < GR; j0 += 8) {
+#pragma unroll
+                for (int j8 = 0; j8 < 8; ++j8) {
+                    const int j = j0 + j8;
+                    uint32_t m[CPT];
+#pragma unroll
+                    for (int k = 0; k < CPT; ++k) m[k] = ct_mean(col[k], job.inv);
+                    CV t;
+                    if constexpr (CPT == 8) t = make_uint4(pack_lo(m[0], m[1]), pack_lo(m[2], m[3]), pack_lo(m[4], m[5]), pack_lo(m[6], m[7]));
+                    else t = make_uint2(pack_lo(m[0], m[1]), pack_lo(m[2], m[3]));
+                    *reinterpret_cast<CV*>(tmpb + (size_t)j * pj.rowbuf + (size_t)(Gm::PAD + c0) * 2) = t;
+                    uint32_t a[CW], b[CW];
+                    colvec_words<CPT>(*reinterpret_cast<const CV*>(ring + (size_t)j * row_bytes + (size_t)c0 * 2), a);
+                    colvec_words<CPT>(*reinterpret_cast<const CV*>(ring + (size_t)(GR + j) * row_bytes + (size_t)c0 * 2), b);
+#pragma unroll
+                    for (int q = 0; q < CW; ++q) {
+                        col[2 * q] = dp2a(b[q], SUB_LO, dp2a(a[q], ADD_LO, col[2 * q]));
+                        col[2 * q + 1] = col[2 * q + 1] + (a[q] >> 16) - (b[q] >> 16);
+                    }
+                }
+            }
+        }
+        __syncthreads();  // tmpb complete, ring consumed
+        if (threadIdx.x == 0 && yg + GR < y1) {
+            fence_proxy_async();
+            issue_ring(yg + GR);
+        }
+        // ---- H: each lane group blurs one row of means (SYM closed form), in place in tmpb
+        {
+            uint16_t* row = reinterpret_cast<uint16_t*>(tmpb + (size_t)(warp * RPW + sub) * pj.rowbuf);
+            hseg_pass<R>(e, eo, row, w, sg, G, pj.S, true, act, lane, job.inv, job.inv2);
+            if (act) h_store_own<R>(eo, row + Gm::PAD + L * sg);
+            __syncwarp();
+            // coalesced copy-out of the warp's rows
+            for (int s2 = 0; s2 < RPW; ++s2) {
+                const int y = yg + warp * RPW + s2;
+                if (y < y1) {
+                    const unsigned char* from = tmpb + (size_t)(warp * RPW + s2) * pj.rowbuf + Gm::PAD * 2;
+                    char* to = dst + (size_t)y * pj.dst_pitch;
+                    for (uint32_t off = lane * 16; off < row_bytes; off += 512) st_global_hint(to + off, *reinterpret_cast<const uint4*>(from + off), drop);
+                }
+            }
+        }
+        __syncthreads();  // tmpb free
+    }
+}
+
+template <int R>
+int launch_ctfused(const SegJob& whole, int count, cudaStream_t st) {
+    using Gm = HGeom<R>;
+    for (int k = 0; k < whole.nplanes; ++k)
+        if (whole.pl[k].w > CTF_WARPS * 32 * 8 || (whole.pl[k].w + L - 1) / L > 32) return 1;
+    return for_each_shape(whole, [&](SegJob job) {
+        const int w = job.pl[0].w, h = job.pl[0].h;
+        const int cpt = (w <= CTF_WARPS * 32 * 4) ? 4 : 8;
+        const int S = (w + L - 1) / L, G = lanes_per_row(S), RPW = 32 / G, GR = CTF_WARPS * RPW;
+        const int rowbuf = rowbuf_bytes(Gm::row_samples(S), G);
+        const size_t row_bytes = (size_t)((w * 2 + 15) & ~15);
+        const size_t smem = (size_t)2 * GR * row_bytes + (size_t)GR * rowbuf;
+        // rows per band: the first 2r rows of a band are read twice, so bands are as tall as the batch allows while the launch
+        // still has ~4 waves of CTAs (a whole plane per CTA for big batches, 2 groups per band for a lone frame)
+        const long planes = (long)count * job.nplanes;
+        int nb = (int)std::min<long>((4 * 296 + planes - 1) / planes, (h + 2 * GR - 1) / (2 * GR));
+        nb = std::max(nb, 1);
+        const int band = (((h + nb - 1) / nb + GR - 1) / GR) * GR;
+        int cta = 0;
+        for (int k = 0; k < job.nplanes; ++k) {
+            SegPlane& s = job.pl[k];
+            s.S = S; s.G = G; s.rowbuf = rowbuf; s.per_cta = band;
+            s.cta_begin = cta;
+            cta += (h + band - 1) / band;
+        }
+        job.ctas_per_frame = cta;
+        if (cpt == 4) return launch_frames(ctfused_kernel<R, 4>, job, count, CTF_WARPS * 32, smem, st);
+        return launch_frames(ctfused_kernel<R, 8>, job, count, CTF_WARPS * 32, smem, st);
+    });
+}
+
+}  // namespace
+
+// Entry points.  Return 0 = done, 1 = not applicable (the caller falls back to the streaming kernels), < 0 = error.
+int run_seg_ct_u16(const FrameLayout& l, const bool mask[3], const char* src, size_t sfs, char* dst, size_t dfs, int count, int r, cudaStream_t st) {
+    if (l.kind != K_U16 || src == dst) return 1;
+    const SegJob job = base_job(l, mask, src, sfs, dst, dfs, r, 1);
+    switch (r) {
+#define X(R) case R: return launch_ctfused<R>(job, count, st);
+        VSZ_SEG_RADII(X)
+#undef X
+    }
+    return 1;
+}
+
+}  // namespace vsz
