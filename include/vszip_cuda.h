@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define VSZIP_CUDA_ABI_VERSION 3  /* 2: + vszip_chain_*, vszip_limiter_*; 3: + vszip_limitfilter_*, vszip_adaptivebinarize_*, vszip_planestats_device */
+#define VSZIP_CUDA_ABI_VERSION 4  /* 2: + vszip_chain_*, vszip_limiter_*; 3: + vszip_limitfilter_*, vszip_adaptivebinarize_*, vszip_planestats_device; 4: + vszip_cuda_host_forget, vszip_cuda_host_registered_bytes */
 
 /* VapourSynth4.h values (VSColorFamily / VSSampleType) so the Zig glue can pass vi.format as is. */
 enum { VSZIP_CF_GRAY = 1, VSZIP_CF_RGB = 2, VSZIP_CF_YUV = 3 };
@@ -64,6 +64,15 @@ const char* vszip_cuda_last_error(void);
 int vszip_cuda_abi_version(void);
 /* Number of kernels this library has launched so far in this process (all threads). */
 uint64_t vszip_cuda_kernel_launches(void);
+
+/* Host frame buffers.  getFrame hands over pageable planes owned by the VapourSynth core (getReadPtr / getWritePtr,
+ * src/helper.zig:510-531), and the core recycles those buffers, so the library page-locks (cudaHostRegister) a plane buffer
+ * the second time it sees its address and DMAs it in place from then on (cap: VSZIP_HOST_REGISTER_MB, default 4096, 0 = never).
+ * Rule for the caller: before memory that was passed to a *_get_frame call is freed or unmapped, call
+ * vszip_cuda_host_forget(ptr) with the plane pointer that was passed, or with NULL to drop every entry (the filters' free
+ * callbacks do the latter once the last instance is gone).  vszip_cuda_shutdown() forgets everything. */
+void vszip_cuda_host_forget(const void* ptr);
+size_t vszip_cuda_host_registered_bytes(void);
 
 /* ------------------------------------------------------------------ BoxBlur
  * replaces boxBlurCreate / BoxBlurCT.getFrame / BoxBlurRT.getFrame (src/vapoursynth/boxblur.zig:27-212)

@@ -48,3 +48,35 @@ def test_pinned_frames(fmt, w, h, layout):
     assert vz.load_library().vszip_boxblur_get_frame(f.handle, 0, C.byref(fs), C.byref(fd)) == 0, vz._last_error()
     want = oa.boxblur(clip, hradius=3, hpasses=2, vradius=2, vpasses=1)
     assert_same_planes([np.ascontiguousarray(d) for d in dst], want["planes"], f"pinned {layout} {fmt}")
+
+
+def test_pageable_buffers_are_registered_on_second_sight_and_forgotten():
+    """The host pin cache (csrc/runtime.cu): a pageable plane buffer that comes back is page-locked and DMA'd in place; results
+    stay identical whichever path a call took, and vszip_cuda_host_forget releases the registration."""
+    lib = vz.load_library()
+    vz.core._ensure_init()
+    lib.vszip_cuda_host_forget(None)
+    assert lib.vszip_cuda_host_registered_bytes() == 0
+    fmt, w, h = "YUV420P16", 640, 360
+    clip = noise_clip(fmt, w, h, seed=5)
+    src = [np.array(p, copy=True) for p in clip["planes"]]       # plain pageable numpy memory, one allocation per plane
+    dst = [np.zeros_like(p) for p in src]
+    f = vz.BoxBlurFilter(vz._vi(vz.FORMATS[fmt], w, h, 1), hradius=4, hpasses=2, vradius=3, vpasses=2)
+    want = oa.boxblur(clip, hradius=4, hpasses=2, vradius=3, vpasses=2)["planes"]
+    fs, fd = vz._cframe(src), vz._cframe(dst)
+    seen = []
+    for call in range(4):
+        for d in dst:
+            d[...] = 0
+        assert lib.vszip_boxblur_get_frame(f.handle, call, C.byref(fs), C.byref(fd)) == 0, vz._last_error()
+        assert_same_planes(dst, want, f"call {call}")
+        seen.append(lib.vszip_cuda_host_registered_bytes())
+    assert seen[0] == 0                                            # first sighting: staged copy
+    assert seen[1] >= sum(p.nbytes for p in src + dst)             # second sighting: registered (page-rounded)
+    assert seen[2] == seen[1] == seen[3]                           # and kept, not re-registered
+    lib.vszip_cuda_host_forget(C.c_void_p(src[0].ctypes.data))
+    assert lib.vszip_cuda_host_registered_bytes() < seen[1]
+    lib.vszip_cuda_host_forget(None)
+    assert lib.vszip_cuda_host_registered_bytes() == 0
+    assert lib.vszip_boxblur_get_frame(f.handle, 9, C.byref(fs), C.byref(fd)) == 0   # back on the staging path, still correct
+    assert_same_planes(dst, want, "after forget")

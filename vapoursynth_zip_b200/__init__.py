@@ -102,6 +102,8 @@ ABI = {
     "vszip_cuda_abi_version": (C.c_int, []),
     "vszip_cuda_kernel_launches": (C.c_uint64, []),
     "vszip_cuda_stream_sync": (C.c_int, [C.c_int32, _P]),
+    "vszip_cuda_host_forget": (None, [_P]),
+    "vszip_cuda_host_registered_bytes": (C.c_size_t, []),
     "vszip_boxblur_create": (_P, [C.POINTER(_VideoInfo), C.POINTER(_BoxBlurArgs)]),
     "vszip_boxblur_get_frame": (C.c_int, [_P, C.c_int32, C.POINTER(_Frame), C.POINTER(_Frame)]),
     "vszip_boxblur_device": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, _P]),

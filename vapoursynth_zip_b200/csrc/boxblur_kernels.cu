@@ -1112,9 +1112,10 @@ static int run_axis(const FrameLayout& l, const bool mask[3], const char* src, s
     const int cap = max_fused(r, H);
     if (cap < 1) {
         // out-of-place passes from global memory, ping-ponging two scratch clips so the last pass lands in dst
-        char* t1 = nullptr;
+        AsyncScratch scratch;
         const size_t bytes = l.frame_stride * (size_t)count, tfs = l.frame_stride;
-        VSZ_CUDA(cudaMallocAsync((void**)&t1, 2 * bytes, st));
+        VSZ_CUDA(scratch.alloc(2 * bytes, st));
+        char* t1 = scratch.p;
         char* t2 = t1 + bytes;
         const char* cur = src;
         size_t cur_fs = sfs;
@@ -1131,7 +1132,6 @@ static int run_axis(const FrameLayout& l, const bool mask[3], const char* src, s
                     if (mask[pl] && cudaMemcpyAsync(dst + (size_t)f * dfs + l.pl[pl].offset, cur + (size_t)f * cur_fs + l.pl[pl].offset,
                                                     (size_t)l.pl[pl].pitch * l.pl[pl].h, cudaMemcpyDeviceToDevice, st) != cudaSuccess) rc = -1;
         }
-        VSZ_CUDA(cudaFreeAsync(t1, st));
         return rc;
     }
     const char* cur = src;
@@ -1210,12 +1210,9 @@ static int run_boxblur_t(const FrameLayout& l, const bool mask[3], const char* s
         return 0;
     }
     if constexpr (Px<T>::flt) {
-        char* tmp = nullptr;
-        const size_t bytes = l.frame_stride * (size_t)count;
-        VSZ_CUDA(cudaMallocAsync((void**)&tmp, bytes, st));
-        const int rc = run_ct_float<T>(l, mask, src, sfs, tmp, l.frame_stride, dst, dfs, count, hr, st);
-        VSZ_CUDA(cudaFreeAsync(tmp, st));
-        return rc;
+        AsyncScratch tmp;
+        VSZ_CUDA(tmp.alloc(l.frame_stride * (size_t)count, st));
+        return run_ct_float<T>(l, mask, src, sfs, tmp.p, l.frame_stride, dst, dfs, count, hr, st);
     } else {
         // comptime integer path: exact R101q column sums + rounded mean, then the SYM H pass
         if constexpr (std::is_same<T, uint16_t>::value) {

@@ -29,6 +29,18 @@ inline void count_launch(int n = 1) { g_launches.fetch_add((uint64_t)n, std::mem
         }                                                                                           \
     } while (0)
 
+// Stream-ordered scratch that is returned to the pool on every exit path (the error macros return early).
+struct AsyncScratch {
+    char* p = nullptr;
+    cudaStream_t st = nullptr;
+    AsyncScratch() = default;
+    AsyncScratch(const AsyncScratch&) = delete;
+    AsyncScratch& operator=(const AsyncScratch&) = delete;
+    ~AsyncScratch() { release(); }
+    cudaError_t alloc(size_t bytes, cudaStream_t s) { release(); st = s; return cudaMallocAsync((void**)&p, bytes, s); }
+    void release() { if (p) { cudaFreeAsync(p, st); p = nullptr; } }
+};
+
 // --------------------------------------------------------------------------- formats / layout
 // helper.zig DataType (src/helper.zig:59-97): selected by bytesPerSample, so 9..16-bit integer
 // clips are all u16.

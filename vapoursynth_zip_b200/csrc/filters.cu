@@ -139,7 +139,8 @@ DeviceCtx* route(int32_t n, const char* name) {
 bool same_clip_shape(const vszip_dev_clip* a, const vszip_filter* f, const char* name) {
     if (!a || a->vi.width != f->vi.width || a->vi.height != f->vi.height || a->layout.kind != f->sample ||
         a->vi.num_planes != f->vi.num_planes || a->vi.sub_sampling_w != f->vi.sub_sampling_w ||
-        a->vi.sub_sampling_h != f->vi.sub_sampling_h) {
+        a->vi.sub_sampling_h != f->vi.sub_sampling_h || a->vi.bits_per_sample != f->vi.bits_per_sample ||
+        a->vi.sample_type != f->vi.sample_type) {
         set_error("%s: device clip does not match the format the filter was created for", name);
         return false;
     }
@@ -369,14 +370,25 @@ static int bilateral_upload(const vszip_filter* cf, int dev_index) {
         f->gr_dev.resize(num_devices(), std::vector<float*>(3, nullptr));
         f->gs_dev.resize(num_devices(), std::vector<float*>(3, nullptr));
     }
+    bool uploaded = false;
     for (int i = 0; i < f->vi.num_planes; ++i) {
         if (!f->process[i] || f->gr_dev[dev_index][i]) continue;
         const size_t gsb = f->gs_host[i].size() * sizeof(float), grb = f->gr_host[i].size() * sizeof(float);
-        VSZ_CUDA(cudaMalloc((void**)&f->gs_dev[dev_index][i], gsb));
-        VSZ_CUDA(cudaMalloc((void**)&f->gr_dev[dev_index][i], grb));
-        VSZ_CUDA(cudaMemcpy(f->gs_dev[dev_index][i], f->gs_host[i].data(), gsb, cudaMemcpyHostToDevice));
-        VSZ_CUDA(cudaMemcpy(f->gr_dev[dev_index][i], f->gr_host[i].data(), grb, cudaMemcpyHostToDevice));
+        float *gs = nullptr, *gr = nullptr;
+        // the pointers are published only after the copies have landed: the kernels run on non-blocking streams, which
+        // are not ordered after a pageable cudaMemcpy on the default stream by themselves
+        if (cudaMalloc((void**)&gs, gsb) != cudaSuccess || cudaMalloc((void**)&gr, grb) != cudaSuccess ||
+            cudaMemcpy(gs, f->gs_host[i].data(), gsb, cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMemcpy(gr, f->gr_host[i].data(), grb, cudaMemcpyHostToDevice) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) {
+            set_error("Bilateral: uploading the weight tables failed (%s)", cudaGetErrorString(cudaGetLastError()));
+            cudaFree(gs); cudaFree(gr);
+            return -1;
+        }
+        f->gs_dev[dev_index][i] = gs;
+        f->gr_dev[dev_index][i] = gr;
+        uploaded = true;
     }
+    (void)uploaded;
     return 0;
 }
 
@@ -554,6 +566,7 @@ int vszip_planeminmax_device(const vszip_filter* f, const vszip_dev_clip* a, con
     if (!f || f->kind != F_PLANEMINMAX) { set_error("PlaneMinMax: bad filter handle"); return -1; }
     if (f->has_ref != (b != nullptr)) { set_error("PlaneMinMax: clipb presence does not match the filter instance"); return -1; }
     if (!same_clip_shape(a, f, name) || (b && !same_clip_shape(b, f, name)) || !range_ok(a, first, count, name) || (b && !range_ok(b, first, count, name))) return -1;
+    if (b && b->device_index != a->device_index) { set_error("%s: clips live on different devices", name); return -1; }
     DeviceCtx* d = device_ctx(a->device_index);
     if (!d) { set_error("PlaneMinMax: library not initialised"); return -1; }
     VSZ_CUDA(cudaSetDevice(d->ordinal));
@@ -561,9 +574,10 @@ int vszip_planeminmax_device(const vszip_filter* f, const vszip_dev_clip* a, con
     const int np = processed_planes(f);
     if (count == 0 || np == 0) return 0;
     const size_t fs = a->layout.frame_stride;
-    char* scratch = nullptr;
+    AsyncScratch scratch_mem;
     const size_t sb = stats_scratch_bytes(count, np), rb = sizeof(StatsRaw) * (size_t)count * np;
-    VSZ_CUDA(cudaMallocAsync((void**)&scratch, sb + rb, st));
+    VSZ_CUDA(scratch_mem.alloc(sb + rb, st));
+    char* scratch = scratch_mem.p;
     StatsRaw* raw_dev = (StatsRaw*)(scratch + sb);
     int rc = run_planeminmax(f->layout, f->process, a->base + (size_t)first * fs, fs, b ? b->base + (size_t)first * fs : nullptr, fs, count,
                              f->no_thr, f->minthr, f->maxthr, f->hist_size, scratch, raw_dev, st);
@@ -573,7 +587,6 @@ int vszip_planeminmax_device(const vszip_filter* f, const vszip_dev_clip* a, con
         VSZ_CUDA(cudaStreamSynchronize(st));
         for (int i = 0; i < count; ++i) minmax_finalize(f, raw.data() + (size_t)i * np, out + i);
     }
-    VSZ_CUDA(cudaFreeAsync(scratch, st));
     return rc;
 }
 
@@ -617,10 +630,18 @@ static int average_upload(const vszip_filter* cf, int dev_index, const int32_t**
     if (f->exclude_i_dev.size() < (size_t)num_devices()) { f->exclude_i_dev.resize(num_devices(), nullptr); f->exclude_f_dev.resize(num_devices(), nullptr); }
     if (!f->exclude_i_dev[dev_index]) {
         const size_t n = f->exclude_i.size();
-        VSZ_CUDA(cudaMalloc((void**)&f->exclude_i_dev[dev_index], n * sizeof(int32_t)));
-        VSZ_CUDA(cudaMalloc((void**)&f->exclude_f_dev[dev_index], n * sizeof(float)));
-        VSZ_CUDA(cudaMemcpy(f->exclude_i_dev[dev_index], f->exclude_i.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice));
-        VSZ_CUDA(cudaMemcpy(f->exclude_f_dev[dev_index], f->exclude_f.data(), n * sizeof(float), cudaMemcpyHostToDevice));
+        int32_t* di = nullptr;
+        float* df = nullptr;
+        // published only once the copies have landed (the reductions run on non-blocking streams)
+        if (cudaMalloc((void**)&di, n * sizeof(int32_t)) != cudaSuccess || cudaMalloc((void**)&df, n * sizeof(float)) != cudaSuccess ||
+            cudaMemcpy(di, f->exclude_i.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMemcpy(df, f->exclude_f.data(), n * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) {
+            set_error("PlaneAverage: uploading the exclude list failed (%s)", cudaGetErrorString(cudaGetLastError()));
+            cudaFree(di); cudaFree(df);
+            return -1;
+        }
+        f->exclude_i_dev[dev_index] = di;
+        f->exclude_f_dev[dev_index] = df;
     }
     *xi = f->exclude_i_dev[dev_index]; *xf = f->exclude_f_dev[dev_index];
     return 0;
@@ -679,6 +700,7 @@ int vszip_planeaverage_device(const vszip_filter* f, const vszip_dev_clip* a, co
     if (!f || f->kind != F_PLANEAVERAGE) { set_error("PlaneAverage: bad filter handle"); return -1; }
     if (f->has_ref != (b != nullptr)) { set_error("PlaneAverage: clipb presence does not match the filter instance"); return -1; }
     if (!same_clip_shape(a, f, name) || (b && !same_clip_shape(b, f, name)) || !range_ok(a, first, count, name) || (b && !range_ok(b, first, count, name))) return -1;
+    if (b && b->device_index != a->device_index) { set_error("%s: clips live on different devices", name); return -1; }
     DeviceCtx* d = device_ctx(a->device_index);
     if (!d) { set_error("PlaneAverage: library not initialised"); return -1; }
     VSZ_CUDA(cudaSetDevice(d->ordinal));
@@ -686,9 +708,10 @@ int vszip_planeaverage_device(const vszip_filter* f, const vszip_dev_clip* a, co
     const int np = processed_planes(f);
     if (count == 0 || np == 0) return 0;
     const size_t fs = a->layout.frame_stride;
-    char* scratch = nullptr;
+    AsyncScratch scratch_mem;
     const size_t sb = stats_scratch_bytes(count, np), rb = sizeof(StatsRaw) * (size_t)count * np;
-    VSZ_CUDA(cudaMallocAsync((void**)&scratch, sb + rb, st));
+    VSZ_CUDA(scratch_mem.alloc(sb + rb, st));
+    char* scratch = scratch_mem.p;
     StatsRaw* raw_dev = (StatsRaw*)(scratch + sb);
     const int32_t* xi; const float* xf;
     if (average_upload(f, a->device_index, &xi, &xf)) return -1;
@@ -700,7 +723,6 @@ int vszip_planeaverage_device(const vszip_filter* f, const vszip_dev_clip* a, co
         VSZ_CUDA(cudaStreamSynchronize(st));
         for (int i = 0; i < count; ++i) average_finalize(f, raw.data() + (size_t)i * np, out + i);
     }
-    VSZ_CUDA(cudaFreeAsync(scratch, st));
     return rc;
 }
 
@@ -724,8 +746,9 @@ int vszip_planestats_device(const vszip_filter* fm, const vszip_filter* fa, cons
     const size_t sbm = stats_scratch_bytes(count, std::max(npm, 1)), sba = stats_scratch_bytes(count, std::max(npa, 1));
     const size_t rbm = sizeof(StatsRaw) * (size_t)count * npm, rba = sizeof(StatsRaw) * (size_t)count * npa;
     const size_t rbm_al = (rbm + 255) & ~(size_t)255;
-    char* scratch = nullptr;
-    VSZ_CUDA(cudaMallocAsync((void**)&scratch, sbm + sba + rbm_al + rba + 256, st));
+    AsyncScratch scratch_mem;
+    VSZ_CUDA(scratch_mem.alloc(sbm + sba + rbm_al + rba + 256, st));
+    char* scratch = scratch_mem.p;
     StatsRaw* raw_m = (StatsRaw*)(scratch + sbm + sba);
     StatsRaw* raw_a = (StatsRaw*)(scratch + sbm + sba + rbm_al);
     int rc = 1;
@@ -751,7 +774,6 @@ int vszip_planestats_device(const vszip_filter* fm, const vszip_filter* fa, cons
             if (avg_out) average_finalize(fa, ha.data() + (size_t)i * npa, avg_out + i);
         }
     }
-    VSZ_CUDA(cudaFreeAsync(scratch, st));
     return rc;
 }
 
@@ -1070,7 +1092,6 @@ int vszip_chain_get_frame(const vszip_chain* c, int32_t n, const vszip_frame* sr
     if (stage_in(s, 0, l, src, all)) return -1;  // later filters may read planes that earlier ones do not process
     const int dev_index = device_index_of(d);
     int cur = 0, pixel_seen = 0, stats_seen = 0;
-    char* stats_scratch = nullptr;
     for (size_t i = 0; i < c->fl.size(); ++i) {
         const vszip_filter* f = c->fl[i];
         if (f->kind == F_BOXBLUR || f->kind == F_BILATERAL || f->kind == F_LIMITER || f->kind == F_LIMITFILTER || f->kind == F_ADAPTIVEBINARIZE) {
@@ -1103,7 +1124,9 @@ int vszip_chain_get_frame(const vszip_chain* c, int32_t n, const vszip_frame* sr
             const int np = processed_planes(f);
             if (np == 0) { ++stats_seen; continue; }
             const size_t sb = stats_scratch_bytes(1, np);
-            VSZ_CUDA(cudaMallocAsync((void**)&stats_scratch, sb, s->stream));
+            AsyncScratch stats_mem;
+            VSZ_CUDA(stats_mem.alloc(sb, s->stream));
+            char* stats_scratch = stats_mem.p;
             StatsRaw* raw_dev = (StatsRaw*)s->dev_small + (size_t)stats_seen * 3;
             int rc;
             if (f->kind == F_PLANEMINMAX) {
@@ -1117,7 +1140,6 @@ int vszip_chain_get_frame(const vszip_chain* c, int32_t n, const vszip_frame* sr
             }
             if (rc) return rc;
             VSZ_CUDA(cudaMemcpyAsync((StatsRaw*)s->pin_small + (size_t)stats_seen * 3, raw_dev, sizeof(StatsRaw) * np, cudaMemcpyDeviceToHost, s->stream));
-            VSZ_CUDA(cudaFreeAsync(stats_scratch, s->stream));
             ++stats_seen;
         }
     }

@@ -331,8 +331,9 @@ template <typename T>
 static int launch_pbfic_t(PbficJob j, int count, const std::vector<float>& pk, cudaStream_t st) {
     const size_t per_frame = 4 * j.img_fs * sizeof(float);
     const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)count, ((size_t)1 << 30) / per_frame));
-    float* scratch = nullptr;
-    VSZ_CUDA(cudaMallocAsync((void**)&scratch, per_frame * (size_t)chunk, st));
+    AsyncScratch scratch_mem;
+    VSZ_CUDA(scratch_mem.alloc(per_frame * (size_t)chunk, st));
+    float* scratch = reinterpret_cast<float*>(scratch_mem.p);
     const size_t img_all = j.img_fs * (size_t)chunk;
     const char* src0 = j.src; const char* ref0 = j.ref; char* dst0 = j.dst;
     for (int f0 = 0; f0 < count; f0 += chunk) {
@@ -351,7 +352,6 @@ static int launch_pbfic_t(PbficJob j, int count, const std::vector<float>& pk, c
         }
     }
     VSZ_CUDA(cudaGetLastError());
-    VSZ_CUDA(cudaFreeAsync(scratch, st));
     return 0;
 }
 

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <string>
 
 #include "common.h"
@@ -116,12 +117,86 @@ static void copy_rows(char* dst, ptrdiff_t dpitch, const char* src, ptrdiff_t sp
     for (int y = 0; y < rows; ++y) memcpy(dst + dpitch * y, src + spitch * y, row_bytes);
 }
 
-// true when `p` is page-locked host memory the DMA engines can reach directly (cudaHostAlloc /
-// cudaHostRegister, e.g. a frame buffer the application pinned): the staging memcpy is skipped then.
-static bool is_pinned_host(const void* p) {
+// --------------------------------------------------------------------------- host buffers: pinned or not
+// VapourSynth hands getFrame pageable plane buffers that come out of the core's frame pool, i.e. the same addresses keep
+// coming back (src/helper.zig:510-531 only sees pointers + strides).  A pageable buffer costs a staging memcpy into the slot's
+// pinned buffer in each direction; a page-locked one is DMA'd in place.  So the runtime keeps a cache keyed by buffer address:
+//   * a buffer seen for the second time is page-locked with cudaHostRegister (portable, so every GPU can reach it) and from
+//     then on treated like application-pinned memory;
+//   * buffers the application pinned itself (cudaHostAlloc / cudaHostRegister) are recognised once and remembered;
+//   * the total registered size is capped (VSZIP_HOST_REGISTER_MB, default 4096; 0 switches registration off) - beyond the
+//     cap new buffers simply keep using the staging path; nothing is ever evicted behind the application's back.
+// Invalidation rule: before memory that was passed to a get_frame call is freed or unmapped, call
+// vszip_cuda_host_forget(ptr) (or with NULL for everything, e.g. from the filter's free callback / at core teardown).  A stale
+// entry cannot produce wrong pixels - the driver falls back to a staged copy for memory it does not know - but a
+// registered range must be unregistered before its pages go back to the OS.
+namespace {
+struct HostRange {
+    uintptr_t end = 0;
+    bool ours = false;  // registered by this library (must be unregistered by it)
+    int seen = 0;       // sightings while still pageable
+};
+std::mutex g_host_mu;
+std::map<uintptr_t, HostRange> g_host;  // key = first byte of the plane buffer as passed in
+size_t g_host_registered = 0;
+
+size_t host_register_cap() {
+    static const size_t cap = [] {
+        const char* e = getenv("VSZIP_HOST_REGISTER_MB");
+        return (size_t)(e ? strtoull(e, nullptr, 10) : 4096ull) << 20;
+    }();
+    return cap;
+}
+
+bool driver_says_pinned(const void* p) {
     cudaPointerAttributes a;
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
     return a.type == cudaMemoryTypeHost;
+}
+}  // namespace
+
+// true when the plane buffer [p, p + bytes) can be reached by the DMA engines directly; may page-lock it (see above)
+static bool host_plane_pinned(const void* p, size_t bytes) {
+    const uintptr_t a = (uintptr_t)p;
+    std::lock_guard<std::mutex> lk(g_host_mu);
+    auto it = g_host.find(a);
+    if (it != g_host.end() && it->second.seen < 0) return it->second.end >= a + bytes;  // known pinned (seen = -1)
+    if (it == g_host.end()) {
+        HostRange r;
+        if (driver_says_pinned(p)) { r.end = a + bytes; r.seen = -1; g_host[a] = r; return true; }
+        r.seen = 1;
+        if (g_host.size() < 65536) g_host[a] = r;  // bounded bookkeeping
+        return false;
+    }
+    HostRange& r = it->second;
+    if (r.seen == 0) return false;  // registration failed before: stay on the staging path
+    ++r.seen;
+    const size_t cap = host_register_cap();
+    const uintptr_t lo = a & ~(uintptr_t)4095, hi = (a + bytes + 4095) & ~(uintptr_t)4095;
+    if (cap == 0 || g_host_registered + (hi - lo) > cap) return false;
+    const cudaError_t e = cudaHostRegister((void*)lo, hi - lo, cudaHostRegisterPortable);
+    if (e == cudaSuccess) {
+        r.end = a + bytes; r.ours = true; r.seen = -1;
+        g_host_registered += hi - lo;
+        return true;
+    }
+    cudaGetLastError();
+    // part of the range is page-locked already (planes of one frame carved out of a single registered buffer): fine if the
+    // driver now knows both ends, else give up on this buffer
+    if (e == cudaErrorHostMemoryAlreadyRegistered && driver_says_pinned(p) && driver_says_pinned((const char*)p + bytes - 1)) {
+        r.end = a + bytes; r.seen = -1;
+        return true;
+    }
+    r.seen = 0;
+    return false;
+}
+
+static size_t plane_span_bytes(const FrameLayout& l, int p, ptrdiff_t stride) {
+    return (size_t)(stride < 0 ? -stride : stride) * (size_t)(l.pl[p].h - 1) + (size_t)l.pl[p].w * l.bps;
+}
+static bool is_pinned_host(const FrameLayout& l, int p, const vszip_frame* host) {
+    if (host->stride[p] <= 0) return false;
+    return host_plane_pinned(host->data[p], plane_span_bytes(l, p, host->stride[p]));
 }
 
 // Pinned planes go by DMA straight from/to the application's memory.  Fewer, larger copies keep the copy engines
@@ -154,7 +229,7 @@ static int pinned_copy(Slot* s, int dev_buf, const FrameLayout& l, const vszip_f
 
 int stage_in(Slot* s, int which, const FrameLayout& l, const vszip_frame* host, const bool mask[3]) {
     bool pinned[3] = {false, false, false};
-    for (int p = 0; p < l.nplanes; ++p) pinned[p] = mask[p] && is_pinned_host(host->data[p]);
+    for (int p = 0; p < l.nplanes; ++p) pinned[p] = mask[p] && is_pinned_host(l, p, host);
     for (int p = 0; p < l.nplanes;) {
         if (!mask[p]) { ++p; continue; }
         const PlaneGeom& g = l.pl[p];
@@ -177,7 +252,7 @@ int stage_in(Slot* s, int which, const FrameLayout& l, const vszip_frame* host, 
 // pinned buffer (stage_out_finish then copies it out after the stream has been synchronised).
 int stage_out_begin(Slot* s, const FrameLayout& l, vszip_frame* host, const bool mask[3], bool direct[3]) {
     bool pinned[3] = {false, false, false};
-    for (int p = 0; p < l.nplanes; ++p) { pinned[p] = mask[p] && is_pinned_host(host->data[p]); direct[p] = pinned[p]; }
+    for (int p = 0; p < l.nplanes; ++p) { pinned[p] = mask[p] && is_pinned_host(l, p, host); direct[p] = pinned[p]; }
     for (int p = 0; p < l.nplanes;) {
         if (!mask[p]) { ++p; continue; }
         const PlaneGeom& g = l.pl[p];
@@ -292,6 +367,7 @@ int vszip_cuda_init(const int32_t* device_ids, int32_t n) {
 }
 
 void vszip_cuda_shutdown(void) {
+    vszip_cuda_host_forget(nullptr);
     std::lock_guard<std::mutex> lk(g_init_mu);
     for (DeviceCtx* d : g_devs) {
         cudaSetDevice(d->ordinal);
@@ -307,6 +383,31 @@ void vszip_cuda_shutdown(void) {
         delete d;
     }
     g_devs.clear();
+}
+
+void vszip_cuda_host_forget(const void* ptr) {
+    std::lock_guard<std::mutex> lk(g_host_mu);
+    auto drop = [](std::map<uintptr_t, HostRange>::iterator it) {
+        if (it->second.ours) {
+            const uintptr_t lo = it->first & ~(uintptr_t)4095, hi = (it->second.end + 4095) & ~(uintptr_t)4095;
+            if (cudaHostUnregister((void*)lo) != cudaSuccess) cudaGetLastError();
+            g_host_registered -= std::min(g_host_registered, (size_t)(hi - lo));
+        }
+    };
+    if (!ptr) {
+        for (auto it = g_host.begin(); it != g_host.end(); ++it) drop(it);
+        g_host.clear();
+        return;
+    }
+    auto it = g_host.find((uintptr_t)ptr);
+    if (it == g_host.end()) return;
+    drop(it);
+    g_host.erase(it);
+}
+
+size_t vszip_cuda_host_registered_bytes(void) {
+    std::lock_guard<std::mutex> lk(g_host_mu);
+    return g_host_registered;
 }
 
 int vszip_cuda_stream_sync(int32_t device, void* stream) {
