@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define VSZIP_CUDA_ABI_VERSION 4  /* 2: + vszip_chain_*, vszip_limiter_*; 3: + vszip_limitfilter_*, vszip_adaptivebinarize_*, vszip_planestats_device; 4: + vszip_cuda_host_forget, vszip_cuda_host_registered_bytes */
+#define VSZIP_CUDA_ABI_VERSION 4  /* 2: + vszip_chain_*, vszip_limiter_*; 3: + vszip_limitfilter_*, vszip_adaptivebinarize_*, vszip_planestats_device; 4: + vszip_cuda_host_forget, vszip_cuda_host_registered_bytes, vszip_cuda_host_register_limit */
 
 /* VapourSynth4.h values (VSColorFamily / VSSampleType) so the Zig glue can pass vi.format as is. */
 enum { VSZIP_CF_GRAY = 1, VSZIP_CF_RGB = 2, VSZIP_CF_YUV = 3 };
@@ -73,6 +73,9 @@ uint64_t vszip_cuda_kernel_launches(void);
  * callbacks do the latter once the last instance is gone).  vszip_cuda_shutdown() forgets everything. */
 void vszip_cuda_host_forget(const void* ptr);
 size_t vszip_cuda_host_registered_bytes(void);
+/* Sets the cap on page-locked application memory in bytes (0 = never register; buffers registered so far stay registered until
+ * they are forgotten) and returns the previous cap. */
+size_t vszip_cuda_host_register_limit(size_t bytes);
 
 /* ------------------------------------------------------------------ BoxBlur
  * replaces boxBlurCreate / BoxBlurCT.getFrame / BoxBlurRT.getFrame (src/vapoursynth/boxblur.zig:27-212)

@@ -62,3 +62,14 @@ def test_kernels_are_sm100a_only():
     out = subprocess.run(["/usr/local/cuda/bin/cuobjdump", "-lelf", str(vz.LIB_PATH)], capture_output=True, text=True).stdout
     archs = set(re.findall(r"sm_\d+a?", out))
     assert archs == {"sm_100a"}, archs
+
+
+def test_integration_source_list_matches_the_makefile():
+    """INTEGRATION.md's build.zig fragment must name every .cu the Makefile links, or the maintainer's build would not link."""
+    import re
+    mk = (ROOT / "Makefile").read_text()
+    srcs = re.search(r"^SRCS := (.*)$", mk, re.M).group(1).split()
+    doc = (ROOT / "INTEGRATION.md").read_text()
+    block = re.search(r"const cuda_srcs = \[_\]\[\]const u8\{(.*?)\};", doc, re.S).group(1)
+    assert sorted(re.findall(r'"(\w+)"', block)) == sorted(s[:-3] for s in srcs)
+    assert sorted(p.name for p in (ROOT / "vapoursynth_zip_b200" / "csrc").glob("*.cu")) == sorted(srcs)

@@ -127,3 +127,10 @@ def test_diamond_needs_the_chain_source():
     out2 = n2.get_frame(0)
     assert getattr(n2, "_chain", None) is None
     assert_same_planes(out2.planes, oa.limitfilter(oa.boxblur(a, hradius=2, vradius=2), a, b, dark_thr=8)["planes"], "ref clip")
+
+
+def test_fused_chain_props_follow_the_first_clip():
+    """AdaptiveBinarize allocates dst from `clip`, so stats props computed on the clip2 branch must not leak into the result,
+    fused or not (src/vapoursynth/adaptive_binarize.zig:28-60)."""
+    f = _chain_case("GRAY8", 200, 120, lambda c: c.vszip.AdaptiveBinarize(c.vszip.BoxBlur(hradius=3, vradius=3).vszip.PlaneMinMax(minthr=0.1), c=1))
+    assert "psmMin" not in f.props and f.props["_ColorRange"] == 0

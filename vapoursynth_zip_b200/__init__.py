@@ -104,6 +104,7 @@ ABI = {
     "vszip_cuda_stream_sync": (C.c_int, [C.c_int32, _P]),
     "vszip_cuda_host_forget": (None, [_P]),
     "vszip_cuda_host_registered_bytes": (C.c_size_t, []),
+    "vszip_cuda_host_register_limit": (C.c_size_t, [C.c_size_t]),
     "vszip_boxblur_create": (_P, [C.POINTER(_VideoInfo), C.POINTER(_BoxBlurArgs)]),
     "vszip_boxblur_get_frame": (C.c_int, [_P, C.c_int32, C.POINTER(_Frame), C.POINTER(_Frame)]),
     "vszip_boxblur_device": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, _P]),
@@ -621,6 +622,7 @@ def _multi_node(first: VideoNode, others, flt: _Filter, call, set_props=None, th
     node._chain_info = ("pixel", through, None, None) if through is not None else None
     node._needs_source = needs_source
     node._set_props = set_props
+    node._props_from_source = needs_source is not None and first is needs_source   # dst = first.newVideoFrame(): props of `first` only
     return node
 
 
@@ -697,13 +699,14 @@ def _fused_get(chain_and_source, n: int) -> "VideoFrame":
         outs.append(o)
     _check(load_library().vszip_chain_get_frame(chain.handle, n, C.byref(s), C.byref(d), ptrs))
     props = dict(src.props)
-    for nd, o in zip(chain.nodes, outs):
+    for nd, o in zip(chain.nodes, outs):        # evaluation order, exactly what the unfused nodes would do to the props
         if o is not None:
             to_props, drop_keys = nd._chain_info[3]
             for k in drop_keys:
                 props.pop(k, None)
             props.update(to_props(o))
-    for nd in chain.nodes:
+        if getattr(nd, "_props_from_source", False):
+            props = dict(src.props)             # e.g. AdaptiveBinarize(src, src.BoxBlur().PlaneMinMax()): clip2's props are not inherited
         props.update(getattr(nd, "_set_props", None) or {})
     return VideoFrame(source.format, source.width, source.height, out_planes, props)
 

@@ -3,6 +3,7 @@
 #include <cuda_fp16.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -140,11 +141,15 @@ std::mutex g_host_mu;
 std::map<uintptr_t, HostRange> g_host;  // key = first byte of the plane buffer as passed in
 size_t g_host_registered = 0;
 
+std::atomic<size_t> g_host_cap{SIZE_MAX};  // SIZE_MAX = not set yet: take VSZIP_HOST_REGISTER_MB (default 4096)
+
 size_t host_register_cap() {
-    static const size_t cap = [] {
+    size_t cap = g_host_cap.load(std::memory_order_relaxed);
+    if (cap == SIZE_MAX) {
         const char* e = getenv("VSZIP_HOST_REGISTER_MB");
-        return (size_t)(e ? strtoull(e, nullptr, 10) : 4096ull) << 20;
-    }();
+        cap = (size_t)(e ? strtoull(e, nullptr, 10) : 4096ull) << 20;
+        g_host_cap.store(cap, std::memory_order_relaxed);
+    }
     return cap;
 }
 
@@ -403,6 +408,12 @@ void vszip_cuda_host_forget(const void* ptr) {
     if (it == g_host.end()) return;
     drop(it);
     g_host.erase(it);
+}
+
+size_t vszip_cuda_host_register_limit(size_t bytes) {
+    const size_t before = host_register_cap();
+    g_host_cap.store(bytes == SIZE_MAX ? SIZE_MAX - 1 : bytes, std::memory_order_relaxed);
+    return before;
 }
 
 size_t vszip_cuda_host_registered_bytes(void) {
