@@ -66,11 +66,13 @@ int vszip_cuda_abi_version(void);
 uint64_t vszip_cuda_kernel_launches(void);
 
 /* Host frame buffers.  getFrame hands over pageable planes owned by the VapourSynth core (getReadPtr / getWritePtr,
- * src/helper.zig:510-531), and the core recycles those buffers, so the library page-locks (cudaHostRegister) a plane buffer
- * the second time it sees its address and DMAs it in place from then on (cap: VSZIP_HOST_REGISTER_MB, default 4096, 0 = never).
- * Rule for the caller: before memory that was passed to a *_get_frame call is freed or unmapped, call
- * vszip_cuda_host_forget(ptr) with the plane pointer that was passed, or with NULL to drop every entry (the filters' free
- * callbacks do the latter once the last instance is gone).  vszip_cuda_shutdown() forgets everything. */
+ * src/helper.zig:510-531).  Planes that lie entirely inside memory the application page-locked are DMA'd in place; everything
+ * else goes through the slots' pinned staging buffers.  Opt-in (vszip_cuda_host_register_limit(bytes > 0) or
+ * VSZIP_HOST_REGISTER_MB): the library page-locks (cudaHostRegister) a pageable plane buffer the second time it sees its
+ * address and DMAs it in place from then on.  Rule for the caller when this is switched on: before memory that was passed to a
+ * *_get_frame call is freed or unmapped, call vszip_cuda_host_forget(ptr) with the plane pointer that was passed, or with NULL
+ * to drop every entry - a registration left behind on an address range that is later mapped again makes the GPU copy from/to
+ * the old pages.  vszip_cuda_shutdown() forgets everything. */
 void vszip_cuda_host_forget(const void* ptr);
 size_t vszip_cuda_host_registered_bytes(void);
 /* Sets the cap on page-locked application memory in bytes (0 = never register; buffers registered so far stay registered until

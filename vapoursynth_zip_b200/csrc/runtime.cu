@@ -121,42 +121,67 @@ static void copy_rows(char* dst, ptrdiff_t dpitch, const char* src, ptrdiff_t sp
 // --------------------------------------------------------------------------- host buffers: pinned or not
 // VapourSynth hands getFrame pageable plane buffers that come out of the core's frame pool, i.e. the same addresses keep
 // coming back (src/helper.zig:510-531 only sees pointers + strides).  A pageable buffer costs a staging memcpy into the slot's
-// pinned buffer in each direction; a page-locked one is DMA'd in place.  So the runtime keeps a cache keyed by buffer address:
-//   * a buffer seen for the second time is page-locked with cudaHostRegister (portable, so every GPU can reach it) and from
-//     then on treated like application-pinned memory;
-//   * buffers the application pinned itself (cudaHostAlloc / cudaHostRegister) are recognised once and remembered;
-//   * the total registered size is capped (VSZIP_HOST_REGISTER_MB, default 4096; 0 switches registration off) - beyond the
-//     cap new buffers simply keep using the staging path; nothing is ever evicted behind the application's back.
-// Invalidation rule: before memory that was passed to a get_frame call is freed or unmapped, call
-// vszip_cuda_host_forget(ptr) (or with NULL for everything, e.g. from the filter's free callback / at core teardown).  A stale
-// entry cannot produce wrong pixels - the driver falls back to a staged copy for memory it does not know - but a
-// registered range must be unregistered before its pages go back to the OS.
+// pinned buffer in each direction; a page-locked one is DMA'd in place.  The runtime keeps a cache keyed by buffer address:
+//   * buffers the application pinned itself (cudaHostAlloc / cudaHostRegister) are recognised - the WHOLE plane must lie inside
+//     one registration (CU_POINTER_ATTRIBUTE_RANGE_*), a plane that merely starts in pinned memory is staged - and remembered;
+//   * opt-in (vszip_cuda_host_register_limit / VSZIP_HOST_REGISTER_MB > 0): a pageable buffer seen for the second time is
+//     page-locked with cudaHostRegister (portable, so every GPU can reach it) and from then on treated like application-pinned
+//     memory.  Only a registration of exactly the buffer's own pages counts: a buffer that shares a page with a neighbour that is
+//     already registered (small heap allocations) stays on the staging path.  Nothing is evicted behind the application's back.
+// Why opt-in: a registration describes physical pages.  If the owner frees a registered buffer without telling us (munmap) and the
+// address range is mapped again later, the driver still DMAs to/from the OLD pages - silently wrong pixels.  VapourSynth's frame
+// pool gives a filter no hook for "this buffer is going back to the OS", so registering the core's buffers is only safe when the
+// host application guarantees the rule below: before memory that was passed to a get_frame call is freed or
+// unmapped, call vszip_cuda_host_forget(ptr) (or with NULL for everything).
 namespace {
 struct HostRange {
     uintptr_t end = 0;
     bool ours = false;  // registered by this library (must be unregistered by it)
-    int seen = 0;       // sightings while still pageable
+    int seen = 0;       // sightings while still pageable; -1 = known pinned; 0 = never try again
 };
 std::mutex g_host_mu;
 std::map<uintptr_t, HostRange> g_host;  // key = first byte of the plane buffer as passed in
 size_t g_host_registered = 0;
 
-std::atomic<size_t> g_host_cap{SIZE_MAX};  // SIZE_MAX = not set yet: take VSZIP_HOST_REGISTER_MB (default 4096)
+std::atomic<size_t> g_host_cap{SIZE_MAX};  // SIZE_MAX = not set yet: take VSZIP_HOST_REGISTER_MB (default 0 = off)
 
 size_t host_register_cap() {
     size_t cap = g_host_cap.load(std::memory_order_relaxed);
     if (cap == SIZE_MAX) {
         const char* e = getenv("VSZIP_HOST_REGISTER_MB");
-        cap = (size_t)(e ? strtoull(e, nullptr, 10) : 4096ull) << 20;
+        cap = (size_t)(e ? strtoull(e, nullptr, 10) : 0ull) << 20;
         g_host_cap.store(cap, std::memory_order_relaxed);
     }
     return cap;
 }
 
-bool driver_says_pinned(const void* p) {
+// cuPointerGetAttribute through the runtime's driver entry point lookup (libcuda is not linked)
+using PointerAttrFn = int (*)(void*, int, unsigned long long);
+PointerAttrFn pointer_attr_fn() {
+    static const PointerAttrFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuPointerGetAttribute", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            p = nullptr;
+        }
+        return reinterpret_cast<PointerAttrFn>(p);
+    }();
+    return fn;
+}
+
+// true when [p, p + bytes) lies inside ONE page-locked host allocation / registration known to the driver
+bool whole_range_pinned(const void* p, size_t bytes) {
     cudaPointerAttributes a;
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
-    return a.type == cudaMemoryTypeHost;
+    if (a.type != cudaMemoryTypeHost) return false;
+    const PointerAttrFn attr = pointer_attr_fn();
+    if (!attr) return false;
+    unsigned long long start = 0;
+    size_t size = 0;
+    // CU_POINTER_ATTRIBUTE_RANGE_START_ADDR = 11, CU_POINTER_ATTRIBUTE_RANGE_SIZE = 12 (cuda.h)
+    if (attr(&start, 11, (unsigned long long)(uintptr_t)p) != 0 || attr(&size, 12, (unsigned long long)(uintptr_t)p) != 0) return false;
+    return (uintptr_t)start <= (uintptr_t)p && (uintptr_t)p + bytes <= (uintptr_t)start + size;
 }
 }  // namespace
 
@@ -166,17 +191,17 @@ static bool host_plane_pinned(const void* p, size_t bytes) {
     std::lock_guard<std::mutex> lk(g_host_mu);
     auto it = g_host.find(a);
     if (it != g_host.end() && it->second.seen < 0) return it->second.end >= a + bytes;  // known pinned (seen = -1)
+    const size_t cap = host_register_cap();
     if (it == g_host.end()) {
         HostRange r;
-        if (driver_says_pinned(p)) { r.end = a + bytes; r.seen = -1; g_host[a] = r; return true; }
-        r.seen = 1;
-        if (g_host.size() < 65536) g_host[a] = r;  // bounded bookkeeping
-        return false;
+        const bool pinned = whole_range_pinned(p, bytes);
+        if (pinned) { r.end = a + bytes; r.seen = -1; } else r.seen = 1;
+        if (g_host.size() < 65536) g_host[a] = r;  // bounded bookkeeping; a remembered "pageable" also saves the driver query next time
+        return pinned;
     }
     HostRange& r = it->second;
     if (r.seen == 0) return false;  // registration failed before: stay on the staging path
     ++r.seen;
-    const size_t cap = host_register_cap();
     const uintptr_t lo = a & ~(uintptr_t)4095, hi = (a + bytes + 4095) & ~(uintptr_t)4095;
     if (cap == 0 || g_host_registered + (hi - lo) > cap) return false;
     const cudaError_t e = cudaHostRegister((void*)lo, hi - lo, cudaHostRegisterPortable);
@@ -186,12 +211,9 @@ static bool host_plane_pinned(const void* p, size_t bytes) {
         return true;
     }
     cudaGetLastError();
-    // part of the range is page-locked already (planes of one frame carved out of a single registered buffer): fine if the
-    // driver now knows both ends, else give up on this buffer
-    if (e == cudaErrorHostMemoryAlreadyRegistered && driver_says_pinned(p) && driver_says_pinned((const char*)p + bytes - 1)) {
-        r.end = a + bytes; r.seen = -1;
-        return true;
-    }
+    // e.g. cudaErrorHostMemoryAlreadyRegistered: the buffer shares a page with a registered neighbour, or the application pinned
+    // a larger buffer in the meantime - the latter is fine if the driver now covers the whole plane with one range
+    if (whole_range_pinned(p, bytes)) { r.end = a + bytes; r.seen = -1; return true; }
     r.seen = 0;
     return false;
 }
