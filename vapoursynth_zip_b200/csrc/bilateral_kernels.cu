@@ -271,7 +271,7 @@ int bilateral_weights_exact(int lut_len) { return weight_mode_for(lut_len) != W_
 template <typename T, bool JOINT, int WM, int SAMPLES, int STEP>
 static int launch_one(const BatchJob& j, const BilateralParams& prm, int nf, size_t smem, cudaStream_t st) {
     auto kern = bilateral_kernel<T, JOINT, WM, SAMPLES, STEP>;
-    VSZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VSZ_CUDA(allow_max_dynamic_smem(kern));
     kern<<<dim3(j.ctas_per_frame, nf), dim3(TW, TH), smem, st>>>(j, prm);
     count_launch();
     return 0;

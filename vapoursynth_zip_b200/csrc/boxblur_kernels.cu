@@ -981,7 +981,7 @@ static int launch_v(const FrameLayout& l, const bool mask[3], const char* src, s
     const size_t smem = ((size_t)ap.ring * P * NT * W + VStage<NT, W>::WORDS) * 4;
     if (smem > (size_t)kMaxSmem) { set_error("BoxBlur: vradius %d with %d fused passes exceeds the shared-memory delay ring", r, P); return -2; }
     auto kern = blur_v_kernel<T, P, MODE, NT, W>;
-    VSZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VSZ_CUDA(allow_max_dynamic_smem(kern));
     BatchJob job = make_batch(l, mask, src, src_fs, nullptr, 0, dst, dst_fs,
                               [](int w, int) { return ((w + NL * W - 1) / (NL * W) + NT - 1) / NT; });
     if (job.ctas_per_frame == 0) return 0;
@@ -1007,7 +1007,7 @@ static int launch_h(const FrameLayout& l, const bool mask[3], const char* src, s
     const size_t smem = ((size_t)ap.ring * P * NT_H + TL::IN_WORDS + TL::OUT_WORDS) * 4;
     if (smem > (size_t)kMaxSmem) { set_error("BoxBlur: hradius %d with %d fused passes exceeds the shared-memory delay ring", r, P); return -2; }
     auto kern = blur_h_kernel<T, P, NT_H>;
-    VSZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VSZ_CUDA(allow_max_dynamic_smem(kern));
     BatchJob job = make_batch(l, mask, src, src_fs, nullptr, 0, dst, dst_fs,
                               [](int, int h) { return (h + NT_H * NL - 1) / (NT_H * NL); });
     if (job.ctas_per_frame == 0) return 0;
@@ -1162,8 +1162,8 @@ static int run_ct_float(const FrameLayout& l, const bool mask[3], const char* sr
     }
     const size_t smem_v = (size_t)(CTF_TL + 2 * r) * CTF_PITCH * sizeof(float);
     const size_t smem_h = smem_v;  // the H pass stores its outputs straight from registers
-    VSZ_CUDA(cudaFuncSetAttribute(ctf_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v));
-    VSZ_CUDA(cudaFuncSetAttribute(ctf_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h));
+    VSZ_CUDA(allow_max_dynamic_smem(ctf_kernel<T, false>));
+    VSZ_CUDA(allow_max_dynamic_smem(ctf_kernel<T, true>));
     for (int f0 = 0; f0 < count; f0 += 65535) {
         const int nf = std::min(65535, count - f0);
         BatchJob a = jv, b = jh;

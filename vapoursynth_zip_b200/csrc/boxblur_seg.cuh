@@ -202,7 +202,7 @@ int rowbuf_bytes(int samples, int G) {
 
 template <class K>
 int launch_frames(K kern, SegJob job, int count, int threads, size_t smem, cudaStream_t st) {
-    VSZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VSZ_CUDA(allow_max_dynamic_smem(kern));
     for (int f0 = 0; f0 < count; f0 += 65535) {
         const int nf = std::min(65535, count - f0);
         SegJob j = job;

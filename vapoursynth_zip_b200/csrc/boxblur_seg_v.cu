@@ -249,7 +249,7 @@ int launch_vseg_tile(SegJob job, int count, cudaStream_t st) {
     const size_t smem = ((size_t)S * LVT * 32 + (size_t)2 * S * 2 * R * 32 + 128) * 4;
     if (smem > (size_t)kMaxSmem) return 1;
     auto kern = vseg_tile_kernel<R>;
-    VSZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VSZ_CUDA(allow_max_dynamic_smem(kern));
     int dev = 0, sms = 148, per_sm = 1;
     VSZ_CUDA(cudaGetDevice(&dev));
     VSZ_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

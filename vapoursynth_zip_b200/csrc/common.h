@@ -29,6 +29,16 @@ inline void count_launch(int n = 1) { g_launches.fetch_add((uint64_t)n, std::mem
         }                                                                                           \
     } while (0)
 
+// Opt-in to more than 48 KB of dynamic shared memory.  The attribute belongs to the function (per device), not to a launch:
+// getFrame is re-entrant, so two host threads launching the same kernel with different sizes would race if each set its own size
+// (thread A's small value lands between thread B's set and B's launch -> "invalid argument").  Every launch therefore sets the same
+// constant, the architectural maximum; occupancy is decided by the size passed to the launch itself.
+constexpr int kMaxDynamicSmem = 227 * 1024;
+template <class K>
+inline cudaError_t allow_max_dynamic_smem(K kern) {
+    return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynamicSmem);
+}
+
 // Stream-ordered scratch that is returned to the pool on every exit path (the error macros return early).
 struct AsyncScratch {
     char* p = nullptr;
