@@ -33,10 +33,14 @@ inline void count_launch(int n = 1) { g_launches.fetch_add((uint64_t)n, std::mem
 // getFrame is re-entrant, so two host threads launching the same kernel with different sizes would race if each set its own size
 // (thread A's small value lands between thread B's set and B's launch -> "invalid argument").  Every launch therefore sets the same
 // constant, the architectural maximum; occupancy is decided by the size passed to the launch itself.
-constexpr int kMaxDynamicSmem = 227 * 1024;
+// (227 KB per CTA minus the kernel's static __shared__ variables, looked up once per kernel.)
+constexpr int kMaxSmemPerCta = 227 * 1024;
+int max_dynamic_smem_of(const void* kern);  // runtime.cu
 template <class K>
 inline cudaError_t allow_max_dynamic_smem(K kern) {
-    return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynamicSmem);
+    const int lim = max_dynamic_smem_of(reinterpret_cast<const void*>(kern));
+    if (lim < 0) return cudaErrorInvalidDeviceFunction;
+    return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
 }
 
 // Stream-ordered scratch that is returned to the pool on every exit path (the error macros return early).

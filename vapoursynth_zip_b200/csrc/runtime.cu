@@ -118,6 +118,20 @@ static void copy_rows(char* dst, ptrdiff_t dpitch, const char* src, ptrdiff_t sp
     for (int y = 0; y < rows; ++y) memcpy(dst + dpitch * y, src + spitch * y, row_bytes);
 }
 
+// largest dynamic shared memory size a kernel may ask for (see allow_max_dynamic_smem in common.h)
+int max_dynamic_smem_of(const void* kern) {
+    static std::mutex mu;
+    static std::map<const void*, int> known;
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = known.find(kern);
+    if (it != known.end()) return it->second;
+    cudaFuncAttributes a;
+    if (cudaFuncGetAttributes(&a, kern) != cudaSuccess) { cudaGetLastError(); return -1; }
+    const int lim = kMaxSmemPerCta - (int)a.sharedSizeBytes;
+    known[kern] = lim;
+    return lim;
+}
+
 // --------------------------------------------------------------------------- host buffers: pinned or not
 // VapourSynth hands getFrame pageable plane buffers that come out of the core's frame pool, i.e. the same addresses keep
 // coming back (src/helper.zig:510-531 only sees pointers + strides).  A pageable buffer costs a staging memcpy into the slot's
