@@ -5,7 +5,7 @@ NVFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -fmad=false -Xcompiler -fPIC,-Wall,-
 SRC_DIR := vapoursynth_zip_b200/csrc
 OBJ_DIR := build/obj
 LIB := vapoursynth_zip_b200/lib/libvszip_cuda.so
-SRCS := runtime.cu filters.cu boxblur_kernels.cu boxblur_seg_h.cu boxblur_seg_v.cu boxblur_seg_ct.cu bilateral_kernels.cu pbfic_kernels.cu planestats_kernels.cu pointwise_kernels.cu
+SRCS := runtime.cu filters.cu boxblur_kernels.cu boxblur_seg_h.cu boxblur_seg_v.cu boxblur_seg_ct.cu boxblur_ctf.cu bilateral_kernels.cu pbfic_kernels.cu planestats_kernels.cu pointwise_kernels.cu
 OBJS := $(SRCS:%.cu=$(OBJ_DIR)/%.o)
 HDRS := include/vszip_cuda.h $(SRC_DIR)/common.h $(SRC_DIR)/filter.h $(SRC_DIR)/boxblur_seg_core.h $(SRC_DIR)/boxblur_seg.cuh
 

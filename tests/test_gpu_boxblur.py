@@ -162,3 +162,39 @@ def test_device_batch_matches_get_frame():
     # noise frames differ from each other and use the full range
     a, b = src.download(0)[0], src.download(1)[0]
     assert (a != b).mean() > 0.99 and a.max() > 60000 and a.min() < 5000
+
+
+# --------------------------------------------------------------------------- comptime float path: streaming-accumulator kernels (boxblur_ctf.cu)
+@pytest.mark.parametrize("fmt", ["GRAYS", "GRAYH"])
+@pytest.mark.parametrize("r", list(range(1, 23)))
+def test_comptime_float_every_radius(fmt, r):
+    """Every comptime radius, f32 and f16, on an odd-sized plane (ragged tiles, a partial row block, an odd f16 column pair)
+    and on the smallest plane the streaming kernels take (2r+1 x 2r+1); bit-exact incl. the mirrored edge windows."""
+    for (w, h) in ((331, 203), (2 * r + 1, 2 * r + 1), (2 * r + 2, 2 * r + 5), (2 * r, 2 * r + 1), (5, 3)):
+        clip = noise_clip(fmt, w, h, seed=100 + r)
+        assert_same_planes(run(clip, hradius=r, vradius=r)["planes"], oa.boxblur(clip, hradius=r, vradius=r)["planes"], f"{fmt} r={r} {w}x{h}")
+
+
+@pytest.mark.parametrize(("fmt", "w", "h", "r"), [("GRAYS", 3840, 2160, 13), ("GRAYH", 1920, 1080, 22), ("YUV444PS", 1283, 2047, 5), ("GRAYS", 4099, 517, 1)])
+def test_comptime_float_long_lines_are_cut_into_pieces(fmt, w, h, r):
+    """Single-frame calls on big planes cut every line into several pieces (each with its own warm-up): piece boundaries,
+    the last ragged piece and the signed zeros / denormals of real data must not show."""
+    clip = noise_clip(fmt, w, h, seed=31)
+    p0 = clip["planes"][0]
+    p0[::7, ::5] = 0                       # exact zeros and negative zeros: 0 + (-0) = +0 must be reproduced tap for tap
+    p0[3::11, 1::9] = -0.0
+    p0[5::13, 2::17] = np.finfo(p0.dtype).tiny / 4   # denormals
+    assert_same_planes(run(clip, hradius=r, vradius=r)["planes"], oa.boxblur(clip, hradius=r, vradius=r)["planes"], f"{fmt} {w}x{h} r={r}")
+
+
+def test_comptime_float_batch_matches_single_frames():
+    """Batched launches choose a different cut of the lines than single-frame calls: same bits either way."""
+    fmt, w, h, n = "YUV444PS", 640, 360, 40
+    src, dst = vz.DeviceClip(fmt, w, h, n), vz.DeviceClip(fmt, w, h, n)
+    src.fill_noise(seed=9)
+    vz.BoxBlurFilter(src.info(), hradius=13, vradius=13).run_device(src, dst)
+    vz.core.sync()
+    for i in (0, 17, 39):
+        planes = src.download(i)
+        want = oa.boxblur({"format": fmt, "planes": planes}, hradius=13, vradius=13)["planes"]
+        assert_same_planes(dst.download(i), want, f"frame {i}")

@@ -1212,6 +1212,10 @@ static int run_boxblur_t(const FrameLayout& l, const bool mask[3], const char* s
     if constexpr (Px<T>::flt) {
         AsyncScratch tmp;
         VSZ_CUDA(tmp.alloc(l.frame_stride * (size_t)count, st));
+        if (use_seg_kernels()) {  // streaming accumulators (boxblur_ctf.cu); planes smaller than the window keep the tiled kernel
+            const int rc = run_ctf_stream(l, mask, src, sfs, tmp.p, l.frame_stride, dst, dfs, count, hr, st);
+            if (rc <= 0) return rc;
+        }
         return run_ct_float<T>(l, mask, src, sfs, tmp.p, l.frame_stride, dst, dfs, count, hr, st);
     } else {
         // comptime integer path: exact R101q column sums + rounded mean, then the SYM H pass

@@ -75,6 +75,10 @@ int run_seg_v_u16(const FrameLayout& l, const bool mask[3], const char* src, siz
 int run_seg_ct_u16(const FrameLayout& l, const bool mask[3], const char* src, size_t src_fs, char* dst, size_t dst_fs, int count, int r,
                    cudaStream_t st);
 
+// boxblur_ctf.cu: comptime float path (f16/f32), streaming accumulators; tmp = scratch clip with the layout's frame stride
+int run_ctf_stream(const FrameLayout& l, const bool mask[3], const char* src, size_t src_fs, char* tmp, size_t tmp_fs, char* dst, size_t dst_fs,
+                   int count, int r, cudaStream_t st);
+
 // bilateral_kernels.cu
 struct BilateralLaunch {
     const float* gs[3];
