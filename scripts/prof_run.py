@@ -12,6 +12,8 @@ reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 vz.core.init([0])
 if what in ("minmax", "average", "planestats"):
     fmt, w, h = "GRAY16", 3840, 2160
+elif what in ("boxblur_ctf", "bilateral_f32"):
+    fmt, w, h = "YUV444PS", 3840, 2160
 else:
     fmt, w, h = "YUV420P16", 1920, 1080
 src = vz.DeviceClip(fmt, w, h, frames)
@@ -28,6 +30,12 @@ elif what == "boxblur_v1":
     run = lambda: f.run_device(src, dst)
 elif what == "boxblur_ct":
     f = vz.BoxBlurFilter(src.info(), hradius=13, hpasses=1, vradius=13, vpasses=1)
+    run = lambda: f.run_device(src, dst)
+elif what == "boxblur_ctf":   # config 5a: comptime float path
+    f = vz.BoxBlurFilter(src.info(), hradius=13, hpasses=1, vradius=13, vpasses=1)
+    run = lambda: f.run_device(src, dst)
+elif what == "bilateral_f32":  # config 5b
+    f = vz.BilateralFilter(src.info(), sigmaS=2, sigmaR=2)
     run = lambda: f.run_device(src, dst)
 elif what == "bilateral":
     f = vz.BilateralFilter(src.info(), sigmaS=2, sigmaR=2)

@@ -169,8 +169,8 @@ def test_device_batch_matches_get_frame():
 @pytest.mark.parametrize("r", list(range(1, 23)))
 def test_comptime_float_every_radius(fmt, r):
     """Every comptime radius, f32 and f16, on an odd-sized plane (ragged tiles, a partial row block, an odd f16 column pair)
-    and on the smallest plane the streaming kernels take (2r+1 x 2r+1); bit-exact incl. the mirrored edge windows."""
-    for (w, h) in ((331, 203), (2 * r + 1, 2 * r + 1), (2 * r + 2, 2 * r + 5), (2 * r, 2 * r + 1), (5, 3)):
+    and on the smallest planes the filter accepts (2r+1 samples per line: interior of one sample); bit-exact incl. the mirrored edge windows."""
+    for (w, h) in ((331, 203), (2 * r + 1, 2 * r + 1), (2 * r + 2, 2 * r + 5), (2 * r + 1, 150), (140, 2 * r + 1)):
         clip = noise_clip(fmt, w, h, seed=100 + r)
         assert_same_planes(run(clip, hradius=r, vradius=r)["planes"], oa.boxblur(clip, hradius=r, vradius=r)["planes"], f"{fmt} r={r} {w}x{h}")
 

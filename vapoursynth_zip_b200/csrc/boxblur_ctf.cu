@@ -16,9 +16,9 @@
 //   ctf_v_kernel  columns: thread = column (f16: two columns), rows arrive by coalesced loads that are issued one whole block
 //                 of 2r+1 rows ahead into the registers the consumed samples leave behind.
 //   ctf_h_kernel  rows: thread = row; a CTA owns 128 rows and streams along them in tiles of 2r+1 columns that the TMA engine
-//                 (cp.async.bulk.tensor, mbarrier completion, 3 stages) drops into shared memory with a row pitch that makes the
-//                 per-row 16-byte reads conflict-free; results go back through a shared-memory tile so that the global stores
-//                 are issued a row at a time by whole warps.
+//                 (cp.async.bulk.tensor, mbarrier completion, double buffered) drops into shared memory with a row pitch that makes the
+//                 per-row 16-byte reads conflict-free; results collect in a per-row shared-memory ring that a fifth warp
+//                 drains to global memory in whole aligned 128-byte lines underneath the arithmetic.
 //   The first / last r outputs of a line (mirrored windows) are computed from 2r samples held in registers with compile-time
 //   tap indices.  Long lines are cut into segments (each pays 2r warm-up samples) so that single-frame calls fill the GPU too.
 //
@@ -185,21 +185,22 @@ __global__ void __launch_bounds__(kThreads) ctf_v_kernel(const CtfJob job) {
     for (int s = 0; s < K; ++s)
 #pragma unroll
         for (int c = 0; c < NC; ++c) acc[s][c] = 0.f;
-    // step t (row ts+t) uses slot t mod K as its fresh slot; the window that started at step t-2r (slot (t+1) mod K) is complete
+    // step t (row ts+t) uses slot t mod K as its fresh slot; the window that started at step t-2r (slot (t+1) mod K) is complete.
+    // Whole blocks only: the steps past the piece's end run on rows clamped to the plane and store nothing (every load is
+    // unconditional and lands in the register its consumer reads a block later - a predicated load would go through a
+    // temporary that the next step has to wait for).
+    const int last = h - 1;
     for (int base = 0; base < n; base += K) {
-        auto step = [&](auto uc) {
+        static_for<0, K>([&](auto uc) {
             constexpr int U = decltype(uc)::value;
             const int t = base + U;
-            if (t < n) {
-                const Pack v = cv[U];
-                if (t + K < n) cv[U] = ld(ts + t + K);
-                float p[NC];
-                mul(v, p);
-                push<K, NC, U>(acc, p);
-                if (t >= 2 * R) st(ts + t - R, acc[(U + 1) % K]);
-            }
-        };
-        static_for<0, K>(step);
+            const Pack v = cv[U];
+            cv[U] = ld(min(ts + t + K, last));
+            float p[NC];
+            mul(v, p);
+            push<K, NC, U>(acc, p);
+            if (t >= 2 * R && t < n) st(ts + t - R, acc[(U + 1) % K]);
+        });
     }
 
     if (sg == pj.segs - 1) {  // rows h-r..h-1 from rows h-2r..h-1
@@ -238,19 +239,61 @@ __device__ __forceinline__ void tma_load_3d(void* sdst, const CUtensorMap* map, 
                  : "memory");
 }
 
-// Tile geometry: a tile row holds TW samples (a whole number of 16-byte vectors, an ODD number of them so that the 8 threads of
-// a quarter-warp, one row each, cover all 32 banks with their 16-byte accesses) of which the first 2r+1 are consumed.
+// Tile geometry.  The TMA engine wants the first byte of a box row 16-byte aligned, i.e. the box's x coordinate a multiple of VEC
+// samples, while block i of a line starts at sample a_i = xs + r + i*(2r+1) (odd step): the box starts at a_i rounded down and the
+// thread skips PH = a_i mod VEC samples (a switch over VEC compile-time variants of "copy the tile's registers").  A tile row holds NV
+// 16-byte vectors - enough for the worst phase, and an ODD number so that the 8 threads of a quarter-warp, one row each, cover
+// all 32 banks with their 16-byte accesses.
+#ifndef VSZ_CTF_STAGES
+#define VSZ_CTF_STAGES 3
+#endif
 template <typename T, int R> struct HTile {
     static constexpr int K = 2 * R + 1;
     static constexpr int VEC = 16 / (int)sizeof(T);
-    static constexpr int NV0 = (K + VEC - 1) / VEC;
-    static constexpr int NV = NV0 | 1;          // vectors per tile row (odd)
-    static constexpr int TW = NV * VEC;          // samples per tile row
+    static constexpr int MB = K >= 32 ? 1 : 32 / K;               // blocks of 2r+1 steps per tile (small radii: fewer, larger tiles)
+    static constexpr int TS = MB * K;                            // samples a tile advances along the row
+    static constexpr int NVR = (TS + VEC - 1 + VEC - 1) / VEC;  // vectors a thread reads: covers PH + TS samples for every PH < VEC
+    static constexpr int NV = NVR | 1;
+    static constexpr int TW = NV * VEC;                          // samples per input tile row (TMA box width)
     static constexpr int ROW_BYTES = NV * 16;
-    static constexpr int STAGES = 3;
+    // results: a ring of RCH aligned 128-byte chunks per row (+ one vector of padding: odd pitch again); the store warp writes a
+    // chunk to global memory once all of it has been produced, so global stores are whole aligned 128-byte lines
+    static constexpr int CH = 128 / (int)sizeof(T);              // samples per chunk
+    static constexpr int RCH = (2 * TS + CH - 1 + CH - 1) / CH;  // chunks: two tiles may be in flight behind an incomplete chunk
+    static constexpr int RV = RCH * 8;                           // ring vectors per row
+    static constexpr int OROW_BYTES = (RV + 1) * 16;
+    static constexpr int STAGES = VSZ_CTF_STAGES;
     static constexpr int TILE_BYTES = kThreads * ROW_BYTES;
-    static constexpr int SMEM = (STAGES + 2) * TILE_BYTES;
+    static constexpr int RING_BYTES = kThreads * OROW_BYTES;
+    static constexpr int SMEM = STAGES * TILE_BYTES + RING_BYTES;
 };
+
+// xv[u] = e[PH + u], PH known at compile time
+template <int K, int PH, int N>
+__device__ __forceinline__ void take_from(const float (&e)[N], float (&xv)[K]) {
+#pragma unroll
+    for (int u = 0; u < K; ++u) xv[u] = e[PH + u];
+}
+template <int K, int VEC, int N>
+__device__ __forceinline__ void take_phase(const float (&e)[N], float (&xv)[K], int ph) {
+    static_assert(VEC == 4 || VEC == 8, "16-byte vectors of f32 or f16");
+    switch (ph) {
+        case 0: take_from<K, 0>(e, xv); break;
+        case 1: take_from<K, 1>(e, xv); break;
+        case 2: take_from<K, 2>(e, xv); break;
+        case 3: take_from<K, 3>(e, xv); break;
+        default:
+            if constexpr (VEC == 8) {
+                switch (ph) {
+                    case 4: take_from<K, 4>(e, xv); break;
+                    case 5: take_from<K, 5>(e, xv); break;
+                    case 6: take_from<K, 6>(e, xv); break;
+                    default: take_from<K, 7>(e, xv); break;
+                }
+            }
+            break;
+    }
+}
 
 template <typename T> __device__ __forceinline__ void vec_to_floats(const uint4& q, float* f);
 template <> __device__ __forceinline__ void vec_to_floats<float>(const uint4& q, float* f) {
@@ -284,29 +327,71 @@ template <typename T> __device__ __forceinline__ T cvt1(float v);
 template <> __device__ __forceinline__ float cvt1<float>(float v) { return v; }
 template <> __device__ __forceinline__ __half cvt1<__half>(float v) { return __float2half_rn(v); }
 
+// Appends the TS results of a tile to the row's ring.  The first of them sits PH samples into a 16-byte vector; the PH samples
+// before it are the tail of the previous tile, kept in `carry`, so only whole vectors are written.  hv = ring index of that vector.
+template <typename T, int TS, int VEC, int RV, int PH>
+__device__ __forceinline__ void ring_put_case(const float (&xv)[TS], float (&carry)[VEC - 1], uint4* rowring, int hv) {
+    constexpr int NVP = (PH + TS + VEC - 1) / VEC, NPH = (PH + TS) % VEC;
+    float o[NVP * VEC];
+#pragma unroll
+    for (int j = 0; j < NVP * VEC; ++j) o[j] = j < PH ? carry[j < VEC - 1 ? j : 0] : (j - PH < TS ? xv[j - PH < TS ? j - PH : 0] : 0.f);
+#pragma unroll
+    for (int v = 0; v < NVP; ++v) {
+        int idx = hv + v;
+        if (idx >= RV) idx -= RV;
+        rowring[idx] = floats_to_vec<T>(o + v * VEC);
+    }
+#pragma unroll
+    for (int j = 0; j < NPH; ++j) carry[j] = xv[TS - NPH + j];
+}
+template <typename T, int TS, int VEC, int RV>
+__device__ __forceinline__ void ring_put(const float (&xv)[TS], float (&carry)[VEC - 1], uint4* rowring, int hv, int ph) {
+    switch (ph) {
+        case 0: ring_put_case<T, TS, VEC, RV, 0>(xv, carry, rowring, hv); break;
+        case 1: ring_put_case<T, TS, VEC, RV, 1>(xv, carry, rowring, hv); break;
+        case 2: ring_put_case<T, TS, VEC, RV, 2>(xv, carry, rowring, hv); break;
+        case 3: ring_put_case<T, TS, VEC, RV, 3>(xv, carry, rowring, hv); break;
+        default:
+            if constexpr (VEC == 8) {
+                switch (ph) {
+                    case 4: ring_put_case<T, TS, VEC, RV, 4>(xv, carry, rowring, hv); break;
+                    case 5: ring_put_case<T, TS, VEC, RV, 5>(xv, carry, rowring, hv); break;
+                    case 6: ring_put_case<T, TS, VEC, RV, 6>(xv, carry, rowring, hv); break;
+                    default: ring_put_case<T, TS, VEC, RV, 7>(xv, carry, rowring, hv); break;
+                }
+            }
+            break;
+    }
+}
+
+// named barriers (bar 0 is __syncthreads): the 128 row threads among themselves, and the two output tiles' full / empty hand-over
+// between the row threads and the store warp
+constexpr int kStoreThreads = 32, kHThreads = kThreads + kStoreThreads;
+enum { BAR_ROWS = 1, BAR_FULL = 2, BAR_EMPTY = 4 };
+__device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+// Warps 0-3: one row per thread (the arithmetic); their results go into a per-row ring in shared memory.  Warp 4 writes the
+// ring to global memory in whole aligned 128-byte lines (16 bytes per lane, 4 rows per store instruction) while the row threads
+// are busy with the next tile.  Measured on 4K YUV444PS, r = 13: with every tile's 27 results per row stored as they came
+// (108 bytes at a 4-byte alignment) the stores alone took 27 of the kernel's 58 us per frame.
 template <typename T, int R>
-__global__ void __launch_bounds__(kThreads) ctf_h_kernel(const CtfJob job, const __grid_constant__ CtfMaps maps) {
+__global__ void __launch_bounds__(kHThreads) ctf_h_kernel(const CtfJob job, const __grid_constant__ CtfMaps maps) {
     using G = HTile<T, R>;
-    constexpr int K = G::K, VEC = G::VEC;
+    constexpr int K = G::K, VEC = G::VEC, TS = G::TS;
     extern __shared__ __align__(128) unsigned char ctf_smem[];
     __shared__ uint64_t full[G::STAGES];
     int local;
     const CtfPlane& pj = ctf_plane(job, blockIdx.y, local);
     const int plane = (int)(&pj - job.pl);
     const int rb = local % pj.cross_blocks, sg = local / pj.cross_blocks;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int row0 = rb * kThreads, row = row0 + tid;
-    const bool live = row < pj.h;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int row0 = rb * kThreads;
     const int w = pj.w, f = blockIdx.x;
-    const float div = job.div;
-    const T* srow = reinterpret_cast<const T*>(job.src + (size_t)f * job.src_fs + pj.src_off + (size_t)min(row, pj.h - 1) * pj.src_pitch);
-    T* drow = reinterpret_cast<T*>(job.dst + (size_t)f * job.dst_fs + pj.dst_off + (size_t)min(row, pj.h - 1) * pj.dst_pitch);
-    char* dplane = job.dst + (size_t)f * job.dst_fs + pj.dst_off;
-
     const int xs = R + sg * pj.seg_len, xe = min(xs + pj.seg_len, w - R);  // interior outputs of this piece
-    const int ntiles = (xe - xs + K - 1) / K;                              // tile i: inputs xs+r+iK.., outputs xs+iK..
+    const int ntiles = (xe - xs + TS - 1) / TS;                            // tile i: inputs xs+r+i*TS.., outputs xs+i*TS..
     unsigned char* in_tiles = ctf_smem;
-    unsigned char* out_tiles = ctf_smem + G::STAGES * G::TILE_BYTES;
+    unsigned char* ring = ctf_smem + G::STAGES * G::TILE_BYTES;
 
     if (tid == 0) {
 #pragma unroll
@@ -314,10 +399,59 @@ __global__ void __launch_bounds__(kThreads) ctf_h_kernel(const CtfJob job, const
         fence_mbar_init();
     }
     __syncthreads();
+
+    // the ring's sample 0 is plane sample xbase: the 128-byte line that holds the piece's first output
+    const int xbase = xs & ~(G::CH - 1);
+    if (tid >= kThreads) {  // ---- store warp
+        char* dplane = job.dst + (size_t)f * job.dst_fs + pj.dst_off + (size_t)row0 * pj.dst_pitch;
+        const int rows = min(kThreads, pj.h - row0);
+        const uint32_t dp = (uint32_t)pj.dst_pitch;
+        const int sub = lane >> 3, vq = lane & 7;
+        int chunk = 0;  // next chunk to store
+        for (int i = 0; i < ntiles; ++i) {
+            const int b = i & 1;
+            bar_sync(BAR_FULL + b, kHThreads);
+            const int done = min(xs + (i + 1) * TS, xe) - xbase;  // results [xs - xbase, done) are in the ring
+            while ((chunk + 1) * G::CH <= done || (i == ntiles - 1 && chunk * G::CH < done)) {
+                const int x0 = xbase + chunk * G::CH;              // first plane sample of the chunk
+                const unsigned char* rc = ring + (chunk % G::RCH) * 128;
+                if (x0 >= xs && x0 + G::CH <= xe) {  // whole lines: 8 lanes x 16 bytes per row, 4 rows per instruction
+                    char* g = dplane + (size_t)x0 * sizeof(T) + vq * 16;
+                    int rr = sub;
+                    for (; rr + 12 < rows; rr += 16) {
+                        uint4 v[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) v[q] = *reinterpret_cast<const uint4*>(rc + (rr + 4 * q) * G::OROW_BYTES + vq * 16);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(g + (size_t)((uint32_t)(rr + 4 * q) * dp)) = v[q];
+                    }
+                    for (; rr < rows; rr += 4)
+                        *reinterpret_cast<uint4*>(g + (size_t)((uint32_t)rr * dp)) = *reinterpret_cast<const uint4*>(rc + rr * G::OROW_BYTES + vq * 16);
+                } else {  // the piece's first / last line: sample by sample, inside [xs, xe) only
+                    for (int c = lane; c < G::CH; c += 32) {
+                        const int x = x0 + c;
+                        if (x < xs || x >= xe) continue;
+                        for (int rr = 0; rr < rows; ++rr)
+                            reinterpret_cast<T*>(dplane + (size_t)((uint32_t)rr * dp))[x] = reinterpret_cast<const T*>(rc + rr * G::OROW_BYTES)[c];
+                    }
+                }
+                ++chunk;
+            }
+            bar_arrive(BAR_EMPTY + b, kHThreads);
+        }
+        return;
+    }
+
+    // ---- row threads
+    const int row = row0 + tid;
+    const bool live = row < pj.h;
+    const float div = job.div;
+    const T* srow = reinterpret_cast<const T*>(job.src + (size_t)f * job.src_fs + pj.src_off + (size_t)min(row, pj.h - 1) * pj.src_pitch);
+    T* drow = reinterpret_cast<T*>(job.dst + (size_t)f * job.dst_fs + pj.dst_off + (size_t)min(row, pj.h - 1) * pj.dst_pitch);
     auto issue = [&](int i) {  // thread 0
         const int s = i % G::STAGES;
         mbar_expect_tx(&full[s], (uint32_t)G::TILE_BYTES);
-        tma_load_3d(in_tiles + s * G::TILE_BYTES, &maps.in[plane], xs + R + i * K, row0, f, &full[s]);
+        tma_load_3d(in_tiles + s * G::TILE_BYTES, &maps.in[plane], (xs + R + i * TS) & ~(VEC - 1), row0, f, &full[s]);
     };
     if (tid == 0)
         for (int i = 0; i < min(G::STAGES, ntiles); ++i) issue(i);
@@ -334,36 +468,35 @@ __global__ void __launch_bounds__(kThreads) ctf_h_kernel(const CtfJob job, const
         static_for<0, 2 * R>([&](auto uc) { constexpr int U = decltype(uc)::value; push<K, 1, U>(acc, pe[U]); });
     }
 
+    float carry[VEC - 1];
+#pragma unroll
+    for (int j = 0; j < VEC - 1; ++j) carry[j] = 0.f;
     for (int i = 0; i < ntiles; ++i) {
-        const int s = i % G::STAGES;
+        const int s = i % G::STAGES, b = i & 1;
         mbar_wait(&full[s], (uint32_t)(i / G::STAGES) & 1u);
-        float xv[G::NV0 * VEC];
+        float xv[TS];
         {
+            float e[G::NVR * VEC];
             const uint4* q = reinterpret_cast<const uint4*>(in_tiles + s * G::TILE_BYTES + tid * G::ROW_BYTES);
 #pragma unroll
-            for (int v = 0; v < G::NV0; ++v) vec_to_floats<T>(q[v], xv + v * VEC);
+            for (int v = 0; v < G::NVR; ++v) vec_to_floats<T>(q[v], e + v * VEC);
+            take_phase<TS, VEC>(e, xv, (xs + R + i * TS) & (VEC - 1));
         }
-        // tile step u is global step 2r + iK + u: fresh slot (u - 1) mod K, complete slot u
-        static_for<0, K>([&](auto uc) {
-            constexpr int U = decltype(uc)::value;
-            const float p[1] = {__fmul_rn(div, xv[U])};
+        // tile step j = b*K + u is global step 2r + i*TS + j: fresh slot (u - 1) mod K, complete slot u
+        static_for<0, TS>([&](auto jc) {
+            constexpr int J = decltype(jc)::value, U = J % K;
+            const float p[1] = {__fmul_rn(div, xv[J])};
             push<K, 1, (U + K - 1) % K>(acc, p);
-            xv[U] = acc[U][0];
+            xv[J] = acc[U][0];
         });
+        if (i >= 2) bar_sync(BAR_EMPTY + b, kHThreads);  // the store warp has dealt with tile i-2: the ring has room for this one
         {
-            uint4* q = reinterpret_cast<uint4*>(out_tiles + (i & 1) * G::TILE_BYTES + tid * G::ROW_BYTES);
-#pragma unroll
-            for (int v = 0; v < G::NV0; ++v) q[v] = floats_to_vec<T>(xv + v * VEC);
+            const int rel = xs + i * TS - xbase;
+            ring_put<T, TS, VEC, G::RV>(xv, carry, reinterpret_cast<uint4*>(ring + tid * G::OROW_BYTES), (rel / VEC) % G::RV, rel & (VEC - 1));
         }
-        __syncthreads();  // stage s is consumed and the output tile is complete
+        bar_arrive(BAR_FULL + b, kHThreads);             // hand the tile to the store warp
+        bar_sync(BAR_ROWS, kThreads);                    // every row thread has consumed stage s
         if (tid == 0 && i + G::STAGES < ntiles) issue(i + G::STAGES);
-        // a warp stores whole rows: lane = output within the tile
-        const int xo = xs + i * K;
-        const T* ot = reinterpret_cast<const T*>(out_tiles + (i & 1) * G::TILE_BYTES);
-        const int rows = min(kThreads, pj.h - row0);
-        for (int c = lane; c < K && xo + c < xe; c += 32)
-            for (int rr = warp; rr < rows; rr += kThreads / 32)
-                reinterpret_cast<T*>(dplane + (size_t)(row0 + rr) * pj.dst_pitch)[xo + c] = ot[rr * G::TW + c];
     }
 
     if (sg == pj.segs - 1 && live) {  // outputs w-r..w-1 from samples w-2r..w-1
@@ -434,7 +567,7 @@ int launch_ctf(const FrameLayout& l, const bool mask[3], const char* src, size_t
     int cv = 0, ch = 0;
     for (int q = 0; q < k; ++q) {
         cut_line(jv.pl[q].h - 2 * R, K, base_v * count, sms, jv.pl[q].segs, jv.pl[q].seg_len);
-        cut_line(jh.pl[q].w - 2 * R, K, base_h * count, sms, jh.pl[q].segs, jh.pl[q].seg_len);
+        cut_line(jh.pl[q].w - 2 * R, G::TS, base_h * count, sms, jh.pl[q].segs, jh.pl[q].seg_len);
         jv.pl[q].cta_begin = cv; cv += jv.pl[q].cross_blocks * jv.pl[q].segs;
         jh.pl[q].cta_begin = ch; ch += jh.pl[q].cross_blocks * jh.pl[q].segs;
     }
@@ -457,7 +590,7 @@ int launch_ctf(const FrameLayout& l, const bool mask[3], const char* src, size_t
             if (rc != CUDA_SUCCESS) { set_error("BoxBlur: cuTensorMapEncodeTiled failed (%d)", (int)rc); return -1; }
         }
         ctf_v_kernel<T, R><<<dim3(nf, a.ctas_per_frame), kThreads, 0, st>>>(a);
-        ctf_h_kernel<T, R><<<dim3(nf, b.ctas_per_frame), kThreads, G::SMEM, st>>>(b, maps);
+        ctf_h_kernel<T, R><<<dim3(nf, b.ctas_per_frame), kHThreads, G::SMEM, st>>>(b, maps);
         count_launch(2);
     }
     VSZ_CUDA(cudaGetLastError());
@@ -469,7 +602,11 @@ int dispatch_ctf(const FrameLayout& l, const bool mask[3], const char* src, size
                  int r, cudaStream_t st) {
     switch (r) {
 #define X(R) case R: return launch_ctf<T, R>(l, mask, src, sfs, tmp, tfs, dst, dfs, count, st);
+#ifdef VSZ_SEG_DEV13  // A/B builds (scripts/build_variant.sh): a few radii, seconds to compile
+        X(4) X(13) X(22)
+#else
         X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16) X(17) X(18) X(19) X(20) X(21) X(22)
+#endif
 #undef X
     }
     return 1;
