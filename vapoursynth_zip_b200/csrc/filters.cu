@@ -752,9 +752,9 @@ int vszip_planestats_device(const vszip_filter* fm, const vszip_filter* fa, cons
     StatsRaw* raw_m = (StatsRaw*)(scratch + sbm + sba);
     StatsRaw* raw_a = (StatsRaw*)(scratch + sbm + sba + rbm_al);
     int rc = 1;
-    if (same_planes && npm > 0 && !fm->no_thr && fa->exclude_i.size() <= 16)
-        rc = run_planestats_fused(fm->layout, fm->process, base, fs, count, fm->minthr, fm->maxthr, fm->hist_size, fa->exclude_i.data(),
-                                  (int)fa->exclude_i.size(), scratch, raw_m, raw_a, st);
+    if (same_planes && npm > 0 && fa->exclude_i.size() <= 16)
+        rc = run_planestats_fused(fm->layout, fm->process, base, fs, count, fm->no_thr, fm->minthr, fm->maxthr, fm->hist_size,
+                                  fa->exclude_i.data(), fa->exclude_f.data(), (int)fa->exclude_i.size(), scratch, raw_m, raw_a, st);
     if (rc == 0 && fused_out) *fused_out = 1;
     if (rc == 1) {  // not eligible: the two reductions one after the other (two reads)
         rc = 0;

@@ -219,7 +219,9 @@ __device__ bool block_finish(const StatsJob& j, int frame, int k, int local, int
 // --------------------------------------------------------------------------- PlaneAverage / no-threshold PlaneMinMax
 // LONGEX: the exclude list has more than 4 entries (entries 4..15 in the job, the rest in device memory); the usual
 // short lists compile to four register compares per sample and nothing else.
-template <typename T, bool HAS_B, bool AVERAGE, bool LONGEX = false>
+// BOTH (with AVERAGE): the no-threshold PlaneMinMax of the same samples comes out of the same read; the sum is
+// accumulated exactly as without it, so the average is bit-identical to the separate call.
+template <typename T, bool HAS_B, bool AVERAGE, bool LONGEX = false, bool BOTH = false>
 __global__ void __launch_bounds__(NT) stats_kernel(const StatsJob j) {
     int k, local;
     const StatsPlane& p = find_plane(j, blockIdx.x, k, local);
@@ -258,7 +260,8 @@ __global__ void __launch_bounds__(NT) stats_kernel(const StatsJob j) {
                 }
                 if (found) acc.excluded += 1; else isum32 += (unsigned)av;
             }
-        } else {
+        }
+        if constexpr (!AVERAGE || BOTH) {
             if constexpr (El<T>::flt) {
                 const float f = as_float<T>(av);
                 acc.fmin = fminf(acc.fmin, f); acc.fmax = fmaxf(acc.fmax, f);
@@ -310,6 +313,10 @@ __global__ void __launch_bounds__(NT) stats_kernel(const StatsJob j) {
         r.isum = total.isum; r.idiff = total.idiff; r.fsum = total.fsum; r.fdiff = total.fdiff;
         r.excluded = total.excluded; r.bin_min = total.imin; r.bin_max = total.imax;
         r.fmin = total.fmin; r.fmax = total.fmax;
+        if constexpr (BOTH) {
+            j.out_avg[(size_t)frame * j.nplanes + k] = r;      // PlaneAverage reads isum / fsum / excluded
+            r.isum = 0ull; r.fsum = 0.0; r.excluded = 0u;      // PlaneMinMax (no threshold) reads the raw minima / maxima
+        }
         j.out[(size_t)frame * j.nplanes + k] = r;
     }
 }
@@ -750,7 +757,8 @@ __device__ __forceinline__ PackedThr packed_thr(unsigned int t) {
 // differ from it (the arithmetic of average_u16_kernel); sum and excluded count travel in the Partial's idiff / excluded fields.
 template <typename T, bool HAS_B, bool TRACK, int AVG = -1>
 __global__ void __launch_bounds__(NT) minmax_bracket_kernel(const StatsJob j) {
-    static_assert(AVG < 0 || (!El<T>::flt && !HAS_B), "the fused average is for integer clips without clipb");
+    static_assert(AVG < 0 || !HAS_B, "the fused average is for clips without clipb");
+    constexpr bool FAVG = AVG >= 0 && El<T>::flt;  // float clips: per sample AVG compares against the exclude values and one f64 add
     constexpr int V = El<T>::PER16, NW = V / 2, G = HAS_B ? 2 : 4;
     constexpr int NEX = AVG > 0 ? AVG : 1;
     unsigned int ee[NEX], pk_ne[NEX], differing[NEX];
@@ -758,6 +766,17 @@ __global__ void __launch_bounds__(NT) minmax_bracket_kernel(const StatsJob j) {
     for (int e = 0; e < NEX; ++e) { ee[e] = AVG > 0 ? (unsigned)j.excl_i[e] * 0x10001u : 0u; pk_ne[e] = 0u; differing[e] = 0u; }
     unsigned int s32 = 0u, seen = 0u;
     unsigned long long sum64 = 0ull;
+    float xf[NEX];
+#pragma unroll
+    for (int e = 0; e < NEX; ++e) xf[e] = AVG > 0 ? j.excl_f[e] : 0.f;
+    double fsum = 0.0;
+    unsigned int fexcluded = 0u;
+    auto favg = [&](float f) {
+        bool found = false;
+#pragma unroll
+        for (int e = 0; e < AVG; ++e) found |= (f == xf[e]);
+        if (found) fexcluded += 1u; else fsum += (double)f;
+    };
     __shared__ unsigned int s_fine[2][FINE_W];
     __shared__ uint4 s_q[NT / 32][G * 32];  // per warp: the vectors of one step that hold a sample inside a bracket
     // own plane map: in large batches this kernel uses fewer, longer-running CTAs than the other reductions
@@ -803,13 +822,18 @@ __global__ void __launch_bounds__(NT) minmax_bracket_kernel(const StatsJob j) {
             pk_ge_umax += m3 - t3.C;
             any |= (m0 - m1 + k01) | (m2 - m3 + k23);  // per half: 1 if inside the min / max bracket
             if constexpr (TRACK) { pk_min = __vminu2(pk_min, w[q]); pk_max = __vmaxu2(pk_max, w[q]); }
-            if constexpr (AVG >= 0) {
+            if constexpr (AVG >= 0 && !FAVG) {
                 s32 = __dp2a_lo(w[q], 0x0101u, s32);
 #pragma unroll
                 for (int e = 0; e < AVG; ++e) pk_ne[e] += __vminu2(w[q] ^ ee[e], 0x10001u);
             }
         }
-        if constexpr (AVG >= 0) seen += (unsigned)V;
+        if constexpr (AVG >= 0 && !FAVG) seen += (unsigned)V;
+        if constexpr (FAVG) {
+            const T* ae = reinterpret_cast<const T*>(&av);
+#pragma unroll
+            for (int i = 0; i < V; ++i) favg(as_float<T>(ae[i]));
+        }
         if constexpr (HAS_B) {
             const T* ae = reinterpret_cast<const T*>(&av);
             const T* be = reinterpret_cast<const T*>(&bv);
@@ -825,12 +849,13 @@ __global__ void __launch_bounds__(NT) minmax_bracket_kernel(const StatsJob j) {
         fine_add(bin, 1u);
         if constexpr (TRACK) { pk_min = __vminu2(pk_min, bin * 0x10001u); pk_max = __vmaxu2(pk_max, bin * 0x10001u); }
         if constexpr (HAS_B) acc.fdiff += abs_diff<T>(at, bt, idiff32);
-        if constexpr (AVG >= 0) {
+        if constexpr (AVG >= 0 && !FAVG) {
             s32 += bin;
 #pragma unroll
             for (int e = 0; e < AVG; ++e) differing[e] += (bin != (unsigned)j.excl_i[e]) ? 1u : 0u;
             seen += 1u;
         }
+        if constexpr (FAVG) favg(as_float<T>(at));
     };
 
     const int nvec = p.w / V;
@@ -898,13 +923,16 @@ __global__ void __launch_bounds__(NT) minmax_bracket_kernel(const StatsJob j) {
         ge_umax += (pk_ge_umax & 0xffffu) + (pk_ge_umax >> 16);
         pk_ge_lmin = pk_ge_umax = 0u;
         acc.idiff += idiff32; idiff32 = 0;
-        if constexpr (AVG >= 0) {  // same bounds: <= 4 * 32 * 4 per packed half, <= 4 * 32 * 8 * 65535 in s32 per group of rows
+        if constexpr (AVG >= 0 && !FAVG) {  // same bounds: <= 4 * 32 * 4 per packed half, <= 4 * 32 * 8 * 65535 in s32 per group of rows
             sum64 += s32; s32 = 0u;
 #pragma unroll
             for (int e = 0; e < AVG; ++e) { differing[e] += (pk_ne[e] & 0xffffu) + (pk_ne[e] >> 16); pk_ne[e] = 0u; }
         }
     }
-    if constexpr (AVG >= 0) {
+    if constexpr (FAVG) {
+        acc.fsum = fsum;
+        acc.excluded = fexcluded;
+    } else if constexpr (AVG >= 0) {
         unsigned long long removed = 0ull;
         unsigned int excluded = 0u;
 #pragma unroll
@@ -934,7 +962,7 @@ __global__ void __launch_bounds__(NT) minmax_bracket_kernel(const StatsJob j) {
         StatsRaw& r = j.out[fp];
         if constexpr (AVG >= 0) {
             StatsRaw ra{};
-            ra.isum = total.idiff; ra.excluded = total.excluded;
+            ra.isum = total.idiff; ra.fsum = total.fsum; ra.excluded = total.excluded;
             j.out_avg[fp] = ra;
         } else {
             r.idiff = total.idiff; r.fdiff = total.fdiff;
@@ -1132,9 +1160,8 @@ int run_planeminmax(const FrameLayout& l, const bool mask[3], const char* a, siz
     return -1;
 }
 
-// PlaneMinMax (threshold path) + PlaneAverage of the same planes from ONE read.  Returns 1 when the
+// PlaneMinMax + PlaneAverage of the same planes from ONE read.  run_planestats_fused returns 1 when the
 // combination is not eligible (the caller then runs the two reductions separately), 0 on success, < 0 on error.
-// Eligible: 8..16-bit integer clips, no clipb, thresholds set, sampled fast path enabled, at most 4 distinct in-range exclude values.
 template <typename T>
 static int launch_fused_t(const StatsJob& j, int count, int m, cudaStream_t st) {
     bool lean = (j.hist_size == 65536u) || (sizeof(T) == 1 && j.hist_size == 256u);
@@ -1160,22 +1187,55 @@ static int launch_fused_t(const StatsJob& j, int count, int m, cudaStream_t st) 
     return 0;
 }
 
-int run_planestats_fused(const FrameLayout& l, const bool mask[3], const char* a, size_t a_fs, int count, float minthr, float maxthr,
-                         uint32_t hist_size, const int32_t* excl, int nex, void* scratch, StatsRaw* out_mm, StatsRaw* out_avg, cudaStream_t st) {
-    if ((l.kind != K_U16 && l.kind != K_U8) || count <= 0 || count > 32768) return 1;
+template <typename T>
+static int launch_both_nothr_t(const StatsJob& j, int count, cudaStream_t st) {
+    const dim3 grid(j.ctas_per_frame, count);
+    if (j.nex > 4) stats_kernel<T, false, true, true, true><<<grid, NT, 0, st>>>(j);
+    else stats_kernel<T, false, true, false, true><<<grid, NT, 0, st>>>(j);
+    count_launch();
+    VSZ_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// Eligible: no clipb, at most 32768 frames; without thresholds any sample type and up to 16 exclude values; with thresholds
+// (sampled fast path enabled) at most 4 distinct exclude values that can match a sample.
+int run_planestats_fused(const FrameLayout& l, const bool mask[3], const char* a, size_t a_fs, int count, bool no_thr, float minthr,
+                         float maxthr, uint32_t hist_size, const int32_t* excl, const float* excl_f, int nex, void* scratch, StatsRaw* out_mm,
+                         StatsRaw* out_avg, cudaStream_t st) {
+    if (count <= 0 || count > 32768) return 1;
+    if (no_thr) {
+        if (nex > 16) return 1;
+        size_t zero = 0;
+        StatsJob j = make_job(l, mask, a, a_fs, nullptr, 0, count, scratch, out_mm, &zero);
+        if (j.ctas_per_frame == 0) return 1;
+        VSZ_CUDA(cudaMemsetAsync(scratch, 0, zero, st));
+        j.out_avg = out_avg;
+        j.nex = nex;
+        for (int i = 0; i < nex; ++i) { j.excl_i[i] = excl[i]; j.excl_f[i] = excl_f[i]; }
+        switch (l.kind) {
+            case K_U8: return launch_both_nothr_t<uint8_t>(j, count, st);
+            case K_U16: return launch_both_nothr_t<uint16_t>(j, count, st);
+            case K_F16: return launch_both_nothr_t<__half>(j, count, st);
+            case K_F32: return launch_both_nothr_t<float>(j, count, st);
+        }
+        return -1;
+    }
     const char* ev = getenv("VSZIP_MINMAX_EXACT");
     if (ev && ev[0] == '1') return 1;
+    const bool flt = l.kind == K_F16 || l.kind == K_F32;
     const int32_t top = l.kind == K_U8 ? 255 : 65535;
     int32_t ex[4];
+    float exf[4];
     int m = 0;
     for (int i = 0; i < nex; ++i) {
         const int32_t v = excl[i];
-        if (v < 0 || v > top) continue;  // can never match a sample
+        if (!flt && (v < 0 || v > top)) continue;  // can never match a sample
         bool dup = false;
-        for (int t = 0; t < m; ++t) dup = dup || ex[t] == v;
+        for (int t = 0; t < m; ++t) dup = dup || (flt ? exf[t] == excl_f[i] : ex[t] == v);
         if (dup) continue;
         if (m == 4) return 1;
-        ex[m++] = v;
+        ex[m] = v; exf[m] = excl_f[i];
+        ++m;
     }
     size_t zero = 0;
     StatsJob j = make_job(l, mask, a, a_fs, nullptr, 0, count, scratch, out_mm, &zero);
@@ -1196,8 +1256,14 @@ int run_planestats_fused(const FrameLayout& l, const bool mask[3], const char* a
         j.pl[k].tmax = (unsigned int)(total * (double)maxthr);
     }
     j.nex = m;
-    for (int i = 0; i < m; ++i) j.excl_i[i] = ex[i];
-    return l.kind == K_U8 ? launch_fused_t<uint8_t>(j, count, m, st) : launch_fused_t<uint16_t>(j, count, m, st);
+    for (int i = 0; i < m; ++i) { j.excl_i[i] = ex[i]; j.excl_f[i] = exf[i]; }
+    switch (l.kind) {
+        case K_U8: return launch_fused_t<uint8_t>(j, count, m, st);
+        case K_U16: return launch_fused_t<uint16_t>(j, count, m, st);
+        case K_F16: return launch_fused_t<__half>(j, count, m, st);
+        case K_F32: return launch_fused_t<float>(j, count, m, st);
+    }
+    return -1;
 }
 
 template <typename T>
