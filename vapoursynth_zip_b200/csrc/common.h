@@ -90,6 +90,7 @@ struct Slot {  // one in-flight getFrame request
     size_t cap[4] = {0, 0, 0, 0};
     void* pin_small = nullptr;  // 4 KB pinned scratch for tiny results
     void* dev_small = nullptr;  // 64 KB device scratch for reductions
+    bool streaming_copies = false;  // set at acquire(): the host is crowded, staging copies bypass the cache
 };
 
 struct DeviceCtx {

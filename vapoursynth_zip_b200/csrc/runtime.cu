@@ -71,12 +71,17 @@ size_t layout_algorithmic_bytes(const FrameLayout& l) {
 static std::mutex g_init_mu;
 static std::vector<DeviceCtx*> g_devs;
 static constexpr int kSlotsPerDevice = 16;
+// host_copy.cpp: row copies between application memory and the pinned staging buffers (streaming stores when many requests are in flight)
+void copy_rows(char* dst, ptrdiff_t dpitch, const char* src, ptrdiff_t spitch, size_t row_bytes, int rows, bool streaming);
+static constexpr int kStreamingBusySlots = 10;
 
 Slot* DeviceCtx::acquire() {
     std::unique_lock<std::mutex> lk(mu);
     cv.wait(lk, [&] { return !idle.empty(); });
     Slot* s = idle.back();
     idle.pop_back();
+    // how crowded the host side is right now decides how this request copies its planes (see host_copy.cpp)
+    s->streaming_copies = (int)(all.size() - idle.size()) >= kStreamingBusySlots;
     return s;
 }
 
@@ -108,14 +113,6 @@ int slot_reserve(DeviceCtx* d, Slot* s, int which, size_t bytes) {
     VSZ_CUDA(cudaMalloc((void**)&s->dev[which], bytes));
     s->cap[which] = bytes;
     return 0;
-}
-
-static void copy_rows(char* dst, ptrdiff_t dpitch, const char* src, ptrdiff_t spitch, size_t row_bytes, int rows) {
-    if (dpitch == spitch && (size_t)spitch == row_bytes) {
-        memcpy(dst, src, row_bytes * (size_t)rows);
-        return;
-    }
-    for (int y = 0; y < rows; ++y) memcpy(dst + dpitch * y, src + spitch * y, row_bytes);
 }
 
 // largest dynamic shared memory size a kernel may ask for (see allow_max_dynamic_smem in common.h)
@@ -281,7 +278,7 @@ int stage_in(Slot* s, int which, const FrameLayout& l, const vszip_frame* host, 
             continue;
         }
         // pageable VapourSynth memory -> pinned staging (same layout as the device frame)
-        copy_rows(s->pin[which] + g.offset, g.pitch, (const char*)host->data[p], host->stride[p], (size_t)g.w * l.bps, g.h);
+        copy_rows(s->pin[which] + g.offset, g.pitch, (const char*)host->data[p], host->stride[p], (size_t)g.w * l.bps, g.h, s->streaming_copies);
         VSZ_CUDA(cudaMemcpyAsync(s->dev[which] + g.offset, s->pin[which] + g.offset, (size_t)g.pitch * g.h,
                                  cudaMemcpyHostToDevice, s->stream));
         ++p;
@@ -314,7 +311,7 @@ void stage_out_finish(Slot* s, const FrameLayout& l, vszip_frame* host, const bo
     for (int p = 0; p < l.nplanes; ++p) {
         if (!mask[p] || direct[p]) continue;
         const PlaneGeom& g = l.pl[p];
-        copy_rows((char*)host->data[p], host->stride[p], s->pin[2] + g.offset, g.pitch, (size_t)g.w * l.bps, g.h);
+        copy_rows((char*)host->data[p], host->stride[p], s->pin[2] + g.offset, g.pitch, (size_t)g.w * l.bps, g.h, s->streaming_copies);
     }
 }
 
