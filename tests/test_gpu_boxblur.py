@@ -198,3 +198,12 @@ def test_comptime_float_batch_matches_single_frames():
         planes = src.download(i)
         want = oa.boxblur({"format": fmt, "planes": planes}, hradius=13, vradius=13)["planes"]
         assert_same_planes(dst.download(i), want, f"frame {i}")
+
+
+@pytest.mark.parametrize("fmt", ["GRAYS", "GRAYH"])
+def test_comptime_float_small_case_for_the_sanitizer(fmt):
+    """Two radii on a small plane: the case scripts/sanitize.sh runs under memcheck / racecheck / synccheck (TMA boxes past the
+    plane's right and bottom edge, the store warp's partial first and last lines, several pieces per line)."""
+    for r in (3, 13):
+        clip = noise_clip(fmt, 403, 231, seed=r)
+        assert_same_planes(run(clip, hradius=r, vradius=r)["planes"], oa.boxblur(clip, hradius=r, vradius=r)["planes"], f"{fmt} r={r}")

@@ -780,6 +780,13 @@ class _Core:
         self._ready = True
         return n
 
+    def shutdown(self):
+        """vszip_cuda_shutdown: frees the per-GPU slots, streams and the host pin cache (filters and clips must be gone)."""
+        import gc
+        gc.collect()
+        load_library().vszip_cuda_shutdown()
+        self._ready = False
+
     def _ensure_init(self):
         if not self._ready:
             self.init()

@@ -975,7 +975,9 @@ __global__ void __launch_bounds__(NT) minmax_bracket_kernel(const StatsJob j) {
     }
     for (int i = threadIdx.x; i < 2 * FINE_W; i += NT) (&s_fine[0][0])[i] = __ldcg(gf + i);
     __syncthreads();
-    if (TRACK && s_ans[1] >= hist_size) return;  // samples above the peak: exact path
+    const bool above_peak = TRACK && s_ans[1] >= hist_size;
+    __syncthreads();  // every thread has read s_ans before warps 0/1 overwrite it below (racecheck)
+    if (above_peak) return;  // samples above the peak: exact path
     const unsigned long long npx = (unsigned long long)p.w * p.h;
     const int side = threadIdx.x >> 5;
     if (side < 2) {
