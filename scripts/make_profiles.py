@@ -45,4 +45,21 @@ for rep in sorted(G.glob(f"ncu_*_{R}.ncu-rep")):
         continue
     out = subprocess.run([sys.executable, str(ROOT / "scripts" / "ncu_summary.py"), str(rep)], capture_output=True, text=True).stdout
     (P / (rep.stem + ".md")).write_text(f"# {rep.name} (ncu --set full --clock-control none)\n\n" + out)
+# ---- DRAM bytes per frame of the headline kernels (bench.py reads this for roofline.traffic): from the boxblur capture, 128 frames per launch
+md = P / f"ncu_boxblur_{R}.md"
+if md.exists():
+    import re
+    frames, per, kern = 128, {}, None
+    for line in md.read_text().splitlines():
+        m = re.match(r"### void .*?(\w+_kernel)<", line)
+        if m:
+            kern = m.group(1); per.setdefault(kern, 0.0); continue
+        m = re.match(r"- dram__bytes_(read|write)\.sum: ([0-9.]+) (\w+)", line)
+        if m and kern:
+            per[kern] += float(m.group(2)) * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[m.group(3)]
+    (P / f"traffic_{R}.json").write_text(json.dumps({"source": f"profiles/ncu_boxblur_{R}.md ({frames} frames per launch)",
+                                                     "dram_bytes_per_frame": {k: v / frames for k, v in per.items()}}, indent=1) + "\n")
+for name in (f"sanitizer_memcheck_{R}.log", f"sanitizer_racecheck_{R}.log", f"sanitizer_synccheck_{R}.log"):
+    if (G / name).exists():
+        shutil.copy(G / name, P / name)
 print("profiles updated:", sorted(p.name for p in P.iterdir()))

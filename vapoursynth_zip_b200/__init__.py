@@ -11,6 +11,7 @@ there is no CPU fallback and a missing library or GPU raises `Error`.
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 import os
 from dataclasses import dataclass
 from pathlib import Path
@@ -292,6 +293,9 @@ def _as_list(v):
     return list(v) if isinstance(v, (list, tuple, np.ndarray)) else [v]
 
 
+_live_filters = weakref.WeakSet()
+
+
 class _Filter:
     """Owns one vszip_filter handle."""
 
@@ -302,14 +306,19 @@ class _Filter:
         mask = (C.c_int32 * 3)()
         load_library().vszip_filter_planes(handle, C.byref(mask))
         self.process = [bool(m) for m in mask]
+        _live_filters.add(self)
+
+    def close(self):
+        """vszip_filter_free (xxxFree in the reference's glue); also called by core.shutdown() for every instance still alive."""
+        h, self.handle = getattr(self, "handle", None), None
+        if h and _lib is not None:
+            _lib.vszip_filter_free(h)
 
     def __del__(self):
         try:
-            if self.handle and _lib is not None:
-                _lib.vszip_filter_free(self.handle)
+            self.close()
         except Exception:
             pass
-        self.handle = None
 
 
 def _check(rc):
@@ -784,6 +793,8 @@ class _Core:
         """vszip_cuda_shutdown: frees the per-GPU slots, streams and the host pin cache (filters and clips must be gone)."""
         import gc
         gc.collect()
+        for f in list(_live_filters):     # instances the interpreter has not finalised yet: their device tables go first
+            f.close()
         load_library().vszip_cuda_shutdown()
         self._ready = False
 

@@ -161,8 +161,8 @@ void vszip_filter_free(vszip_filter* f) {
     for (size_t d = 0; d < f->gr_dev.size(); ++d) {
         DeviceCtx* ctx = device_ctx((int)d);
         if (ctx) cudaSetDevice(ctx->ordinal);
-        for (float* p : f->gr_dev[d]) if (p) cudaFree(p);
-        for (float* p : f->gs_dev[d]) if (p) cudaFree(p);
+        for (float* p : f->gr_dev[d]) if (p && cudaFree(p) != cudaSuccess) set_error("vszip_filter_free: cudaFree failed (%s)", cudaGetErrorString(cudaGetLastError()));
+        for (float* p : f->gs_dev[d]) if (p && cudaFree(p) != cudaSuccess) set_error("vszip_filter_free: cudaFree failed (%s)", cudaGetErrorString(cudaGetLastError()));
     }
     for (size_t d = 0; d < f->exclude_i_dev.size(); ++d) {
         DeviceCtx* ctx = device_ctx((int)d);

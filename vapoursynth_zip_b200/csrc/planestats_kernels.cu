@@ -801,7 +801,10 @@ __global__ void __launch_bounds__(NT) minmax_bracket_kernel(const StatsJob j) {
 
     Partial acc = empty_partial();
     unsigned int ge_lmin = 0, ge_umax = 0, idiff32 = 0;    // exact counts of samples with bin >= l_min / >= u_max
-    unsigned int pk_ge_lmin = 0, pk_ge_umax = 0;           // packed 2 x 16-bit partial counts
+    // Sums of the clamp results over both halves of every visited word (IDP.2A): a word adds 2*C + (samples >= t), so the count
+    // is the sum minus 2*C per word; nwords counts the words of the current group of rows.
+    unsigned int sum_m0 = 0, sum_m3 = 0, nwords = 0;
+    const unsigned int c0h = t0.C & 0xffffu, c3h = t3.C & 0xffffu;
     unsigned int pk_min = 0xffffffffu, pk_max = 0u;
 
     auto fine_add = [&](unsigned int bin, unsigned int n) {
@@ -811,16 +814,20 @@ __global__ void __launch_bounds__(NT) minmax_bracket_kernel(const StatsJob j) {
     auto visit_vec = [&](const uint4& av, const uint4& bv) -> bool {  // true: some sample lies inside a bracket
         unsigned int w[NW];
         pack_bins<T>(av, w);
-        unsigned int any = 0u;
+        // inside-a-bracket test for the whole vector: per word (m0 - m1 + k01) + (m2 - m3 + k23) is 1 per half inside the min / max
+        // bracket (as one 32-bit number: i_lo + 65536 * i_hi, no matter how the halves of the partial sums carry), so the vector
+        // holds such a sample iff sum(m0 + m2) + NW * (k01 + k23) != sum(m1 + m3)   (mod 2^32; the true difference is < 2^19)
+        unsigned int in_a = (unsigned)NW * (k01 + k23), in_b = 0u;
 #pragma unroll
         for (int q = 0; q < NW; ++q) {
             const unsigned int m0 = __vminu2(__vmaxu2(w[q], t0.A), t0.B);
             const unsigned int m1 = __vminu2(__vmaxu2(w[q], t1.A), t1.B);
             const unsigned int m2 = __vminu2(__vmaxu2(w[q], t2.A), t2.B);
             const unsigned int m3 = __vminu2(__vmaxu2(w[q], t3.A), t3.B);
-            pk_ge_lmin += m0 - t0.C;
-            pk_ge_umax += m3 - t3.C;
-            any |= (m0 - m1 + k01) | (m2 - m3 + k23);  // per half: 1 if inside the min / max bracket
+            sum_m0 = __dp2a_lo(m0, 0x0101u, sum_m0);
+            sum_m3 = __dp2a_lo(m3, 0x0101u, sum_m3);
+            in_a += m0 + m2;
+            in_b += m1 + m3;
             if constexpr (TRACK) { pk_min = __vminu2(pk_min, w[q]); pk_max = __vmaxu2(pk_max, w[q]); }
             if constexpr (AVG >= 0 && !FAVG) {
                 s32 = __dp2a_lo(w[q], 0x0101u, s32);
@@ -828,6 +835,7 @@ __global__ void __launch_bounds__(NT) minmax_bracket_kernel(const StatsJob j) {
                 for (int e = 0; e < AVG; ++e) pk_ne[e] += __vminu2(w[q] ^ ee[e], 0x10001u);
             }
         }
+        nwords += (unsigned)NW;
         if constexpr (AVG >= 0 && !FAVG) seen += (unsigned)V;
         if constexpr (FAVG) {
             const T* ae = reinterpret_cast<const T*>(&av);
@@ -840,7 +848,7 @@ __global__ void __launch_bounds__(NT) minmax_bracket_kernel(const StatsJob j) {
 #pragma unroll
             for (int i = 0; i < V; ++i) acc.fdiff += abs_diff<T>(ae[i], be[i], idiff32);
         }
-        return any != 0u;
+        return in_a != in_b;
     };
     auto visit_one = [&](T at, T bt) {  // scalar row tails
         const unsigned int bin = bin_of<T>(at);
@@ -918,10 +926,10 @@ __global__ void __launch_bounds__(NT) minmax_bracket_kernel(const StatsJob j) {
                 visit_one(at, bt);
             }
         }
-        // a thread adds at most G * iters * NW <= 4 * 32 * 8 to each 16-bit half per group of rows
-        ge_lmin += (pk_ge_lmin & 0xffffu) + (pk_ge_lmin >> 16);
-        ge_umax += (pk_ge_umax & 0xffffu) + (pk_ge_umax >> 16);
-        pk_ge_lmin = pk_ge_umax = 0u;
+        // a thread visits at most G * iters * NW <= 4 * 32 * 8 words per group of rows: the sums stay below 2^28
+        ge_lmin += sum_m0 - 2u * c0h * nwords;
+        ge_umax += sum_m3 - 2u * c3h * nwords;
+        sum_m0 = sum_m3 = nwords = 0u;
         acc.idiff += idiff32; idiff32 = 0;
         if constexpr (AVG >= 0 && !FAVG) {  // same bounds: <= 4 * 32 * 4 per packed half, <= 4 * 32 * 8 * 65535 in s32 per group of rows
             sum64 += s32; s32 = 0u;
