@@ -12,8 +12,8 @@ import numpy as np
 _DIR = Path(__file__).resolve().parent
 _LIB_PATH = _DIR / "libvszip_oracle.so"
 
-U8, U16, F16, F32 = 0, 1, 2, 3
-_NP = {U8: np.uint8, U16: np.uint16, F16: np.float16, F32: np.float32}
+U8, U16, F16, F32, U32 = 0, 1, 2, 3, 4   # U32: Limiter only
+_NP = {U8: np.uint8, U16: np.uint16, F16: np.float16, F32: np.float32, U32: np.uint32}
 
 
 def sample_type_of(arr: np.ndarray) -> int:

@@ -17,7 +17,7 @@ GOLDEN_DIR = Path(__file__).resolve().parents[1] / "tests" / "golden"
 # name -> (family, sample 'i'/'f', bits, ssw, ssh)
 FORMATS = {
     "GRAY8": ("GRAY", "i", 8, 0, 0), "GRAY10": ("GRAY", "i", 10, 0, 0), "GRAY16": ("GRAY", "i", 16, 0, 0),
-    "GRAYH": ("GRAY", "f", 16, 0, 0), "GRAYS": ("GRAY", "f", 32, 0, 0),
+    "GRAYH": ("GRAY", "f", 16, 0, 0), "GRAYS": ("GRAY", "f", 32, 0, 0), "GRAY32": ("GRAY", "i", 32, 0, 0),
     "YUV420P8": ("YUV", "i", 8, 1, 1), "YUV420P10": ("YUV", "i", 10, 1, 1), "YUV420P16": ("YUV", "i", 16, 1, 1),
     "YUV420PS": ("YUV", "f", 32, 1, 1),
     "YUV444P8": ("YUV", "i", 8, 0, 0), "YUV444P16": ("YUV", "i", 16, 0, 0), "YUV444PS": ("YUV", "f", 32, 0, 0),

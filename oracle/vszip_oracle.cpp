@@ -30,7 +30,7 @@ namespace {
 
 typedef _Float16 f16;
 
-enum SampleType { ST_U8 = 0, ST_U16 = 1, ST_F16 = 2, ST_F32 = 3 };
+enum SampleType { ST_U8 = 0, ST_U16 = 1, ST_F16 = 2, ST_F32 = 3, ST_U32 = 4 };  // ST_U32: Limiter only
 
 template <class T> struct is_flt : std::integral_constant<bool, std::is_same<T, f16>::value || std::is_same<T, float>::value> {};
 
@@ -778,6 +778,7 @@ int vso_limiter_plane(int st, const void* src, ptrdiff_t sstride, void* dst, ptr
         case ST_U16: limiter_plane_t<uint16_t>(src, sstride, dst, dstride, w, h, lo, hi); return 0;
         case ST_F16: limiter_plane_t<f16>(src, sstride, dst, dstride, w, h, lo, hi); return 0;
         case ST_F32: limiter_plane_t<float>(src, sstride, dst, dstride, w, h, lo, hi); return 0;
+        case ST_U32: limiter_plane_t<uint32_t>(src, sstride, dst, dstride, w, h, lo, hi); return 0;
     }
     return -1;
 }

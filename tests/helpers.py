@@ -47,8 +47,8 @@ def noise_clip(fmt_name, width, height, seed=0):
     for p in range(nplanes):
         w, h = (width >> ssw, height >> ssh) if p else (width, height)
         if st == "i":
-            dt = np.uint8 if bits <= 8 else np.uint16
-            planes.append(rng.integers(0, 1 << bits, size=(h, w), dtype=np.uint32).astype(dt))
+            dt = np.uint8 if bits <= 8 else (np.uint16 if bits <= 16 else np.uint32)
+            planes.append(rng.integers(0, 1 << bits, size=(h, w), dtype=np.uint64).astype(dt))
         else:
             v = rng.random((h, w), dtype=np.float32)
             if p and fam == "YUV":

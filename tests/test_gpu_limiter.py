@@ -30,7 +30,7 @@ def test_golden_cases(key):
         assert stats[p]["avg"] == pytest.approx(e["avg"], rel=1e-6)  # the reference suite's own tolerance
 
 
-@pytest.mark.parametrize("fmt", ["GRAY8", "GRAY10", "GRAY16", "GRAYH", "GRAYS", "YUV420P8", "YUV420P16", "YUV444PS", "RGB24", "RGBS"])
+@pytest.mark.parametrize("fmt", ["GRAY8", "GRAY10", "GRAY16", "GRAY32", "GRAYH", "GRAYS", "YUV420P8", "YUV420P16", "YUV444PS", "RGB24", "RGBS"])
 def test_noise(fmt):
     base = "GRAY16" if fmt == "GRAY10" else fmt
     clip = noise_clip(base, 517, 243, seed=61)   # odd width: vector body + scalar row tails

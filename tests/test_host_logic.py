@@ -199,6 +199,15 @@ def test_limiter_format_errors_come_last():
     raises("min array must have", lambda: core.BlankClip("GRAY11", 64, 32).vszip.Limiter(min=[1, 2]))
 
 
+def test_limiter_accepts_32_bit_integer_clips():
+    """BPSType.U32 (src/helper.zig:14-56, src/filters/limiter.zig:16,34,52): the Limiter is the one filter of the path that takes
+    32-bit integer clips; its f32 peak is 2^32, so 4294967295 and even 4294967296 pass the peak check, 4294967808 does not."""
+    c = core.BlankClip("GRAY32", 64, 32)
+    for args in (dict(), dict(tv_range=True), dict(min=[7], max=[4294967295]), dict(min=[0], max=[4294967296])):
+        assert c.vszip.Limiter(**args).format.bits_per_sample == 32
+    raises("Limiter: max value must be less than or equal to peak value", lambda: c.vszip.Limiter(min=[0], max=[4294967808]))
+
+
 # --------------------------------------------------------------------------- LimitFilter (src/vapoursynth/limit_filter.zig:93-124)
 @pytest.mark.parametrize(("args", "msg"), [
     (dict(dark_thr=[1, 2, 3, 4]), "dark_thr has too many elements \\(got 4, max 3\\)"),

@@ -58,7 +58,7 @@ struct AsyncScratch {
 // --------------------------------------------------------------------------- formats / layout
 // helper.zig DataType (src/helper.zig:59-97): selected by bytesPerSample, so 9..16-bit integer
 // clips are all u16.
-enum SampleKind { K_U8 = 0, K_U16 = 1, K_F16 = 2, K_F32 = 3 };
+enum SampleKind { K_U8 = 0, K_U16 = 1, K_F16 = 2, K_F32 = 3, K_U32 = 4 };  // K_U32: Limiter only (src/helper.zig:14-56, BPSType.U32)
 
 struct PlaneGeom {
     int w, h;

@@ -785,10 +785,10 @@ static void limiter_table(const vszip_video_info& vi, bool tv_range, bool yuv, d
         for (int p = 0; p < 3; ++p) { lo[p] = (yuv && p > 0) ? -0.5 : 0.0; hi[p] = (yuv && p > 0) ? 0.5 : 1.0; }
         return;
     }
-    const int sh = vi.bits_per_sample - 8;
+    const int sh = vi.bits_per_sample - 8;  // up to 24 (32-bit integer clips: full32 / yuv32 / rgb32 of src/filters/limiter.zig:72-91)
     for (int p = 0; p < 3; ++p) {
-        if (!tv_range) { lo[p] = 0.0; hi[p] = (double)((1u << vi.bits_per_sample) - 1u); }
-        else { lo[p] = (double)(16u << sh); hi[p] = (double)(((yuv && p > 0) ? 240u : 235u) << sh); }
+        if (!tv_range) { lo[p] = 0.0; hi[p] = (double)((1ull << vi.bits_per_sample) - 1ull); }
+        else { lo[p] = (double)(16ull << sh); hi[p] = (double)(((yuv && p > 0) ? 240ull : 235ull) << sh); }
     }
 }
 
@@ -837,14 +837,15 @@ vszip_filter* vszip_limiter_create(const vszip_video_info* vi, const vszip_limit
     // BPSType.select (src/helper.zig:25-56)
     if (is_int) {
         const int b = vi->bits_per_sample;
-        if (b == 32) { set_error("Limiter: 32-bit integer clips are not supported by the CUDA path."); return nullptr; }
-        if (!(b == 8 || b == 9 || b == 10 || b == 12 || b == 14 || b == 16)) { set_error("Limiter: not supported Int format."); return nullptr; }
+        if (!(b == 8 || b == 9 || b == 10 || b == 12 || b == 14 || b == 16 || b == 32)) { set_error("Limiter: not supported Int format."); return nullptr; }
     } else if (!(vi->bits_per_sample == 16 || vi->bits_per_sample == 32)) {
         set_error("Limiter: not supported Float format.");
         return nullptr;
     }
     SampleKind kind;
-    if (!select_kind(*vi, name, false, &kind)) return nullptr;
+    if (!select_kind(*vi, name, true, &kind)) return nullptr;
+    if (kind == K_U32)  // the f32 peak of a 32-bit clip is 2^32: a bound that passed the check above may be one past the largest sample
+        for (int i = 0; i < np; ++i) { lo[i] = std::min(lo[i], 4294967295.0); hi[i] = std::min(hi[i], 4294967295.0); }
     const bool tv_range = a->has_tv_range && a->tv_range != 0, maskf = a->has_mask && a->mask != 0;
     const bool yuv = vi->color_family == VSZIP_CF_YUV && !maskf;
     if (!has_min) limiter_table(*vi, tv_range, yuv, lo, hi);

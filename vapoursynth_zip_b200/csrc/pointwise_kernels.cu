@@ -10,7 +10,7 @@
 namespace vsz {
 
 struct LimiterParams {
-    uint32_t lo_w[3], hi_w[3];  // bounds replicated into a 32-bit word of samples (u8 x4, u16 x2, f16 x2, f32 x1)
+    uint32_t lo_w[3], hi_w[3];  // bounds replicated into a 32-bit word of samples (u8 x4, u16 x2, f16 x2, f32 / u32 x1)
 };
 
 static constexpr int LNT = 256, LROWS = 4, LGROUPS = 4;  // a CTA streams LGROUPS groups of LROWS rows
@@ -18,6 +18,7 @@ static constexpr int LNT = 256, LROWS = 4, LGROUPS = 4;  // a CTA streams LGROUP
 template <typename T> __device__ __forceinline__ uint32_t clamp_word(uint32_t x, uint32_t lo, uint32_t hi);
 template <> __device__ __forceinline__ uint32_t clamp_word<uint8_t>(uint32_t x, uint32_t lo, uint32_t hi) { return __vminu4(__vmaxu4(lo, x), hi); }
 template <> __device__ __forceinline__ uint32_t clamp_word<uint16_t>(uint32_t x, uint32_t lo, uint32_t hi) { return __vminu2(__vmaxu2(lo, x), hi); }
+template <> __device__ __forceinline__ uint32_t clamp_word<uint32_t>(uint32_t x, uint32_t lo, uint32_t hi) { return min(max(lo, x), hi); }
 template <> __device__ __forceinline__ uint32_t clamp_word<__half>(uint32_t x, uint32_t lo, uint32_t hi) {
     // @max / @min return the other operand when one is NaN, like __hmax2 / __hmin2
     const __half2 r = __hmin2(__hmax2(*reinterpret_cast<const __half2*>(&lo), *reinterpret_cast<const __half2*>(&x)), *reinterpret_cast<const __half2*>(&hi));
@@ -109,6 +110,7 @@ int run_limiter(const FrameLayout& l, const bool mask[3], const char* src, size_
                 a = *reinterpret_cast<const uint32_t*>(&fa); b = *reinterpret_cast<const uint32_t*>(&fb);
                 break;
             }
+            case K_U32: a = (uint32_t)lo[p]; b = (uint32_t)hi[p]; break;
         }
         prm.lo_w[p] = a; prm.hi_w[p] = b;
     }
@@ -117,6 +119,7 @@ int run_limiter(const FrameLayout& l, const bool mask[3], const char* src, size_
         case K_U16: return launch_limiter_t<uint16_t>(job, prm, count, st);
         case K_F16: return launch_limiter_t<__half>(job, prm, count, st);
         case K_F32: return launch_limiter_t<float>(job, prm, count, st);
+        case K_U32: return launch_limiter_t<uint32_t>(job, prm, count, st);
     }
     return -1;
 }

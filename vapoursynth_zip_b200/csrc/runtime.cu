@@ -31,7 +31,7 @@ bool select_kind(const vszip_video_info& vi, const char* name, bool enable_u32, 
     if (vi.sample_type == VSZIP_ST_INTEGER) {
         if (vi.bytes_per_sample == 1) { *out = K_U8; return true; }
         if (vi.bytes_per_sample == 2) { *out = K_U16; return true; }
-        (void)enable_u32;  // the only caller passing true (PlaneAverage) rejects U32 right after
+        if (vi.bytes_per_sample == 4 && enable_u32) { *out = K_U32; return true; }  // Limiter; PlaneAverage rejects it right after
         set_error("%s: not supported Int format.", name);
         return false;
     }
