@@ -16,7 +16,7 @@ cap() {  # name, kernel regex, skip, count, prof_run args...
   timeout 600 ncu --set full --clock-control none --import-source on -k "regex:$rx" -s $skip -c $cnt -o $O/ncu_${name}_$R python scripts/prof_run.py "$@" > /dev/null 2>&1
   python scripts/ncu_summary.py $O/ncu_${name}_$R.ncu-rep > $O/ncu_${name}_$R.md 2>/dev/null
 }
-cap boxblur "hseg_kernel|vseg_tile_kernel" 2 2 boxblur 128 2
+cap boxblur "hseg_kernel|vseg_tile_kernel" 3 3 boxblur 128 2   # one whole call: H, V luma, V chroma
 cap boxblur_ct "ctfused_kernel" 2 2 boxblur_ct 128 2
 cap boxblur_ctf "ctf_" 2 2 boxblur_ctf 8 2
 cap bilateral "bilateral" 3 1 bilateral 32 2
