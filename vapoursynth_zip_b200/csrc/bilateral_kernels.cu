@@ -13,6 +13,8 @@
 //             memory: weights within ~2 ulp, integer outputs within 1 LSB;
 //   W_SCALED  W_COMPUTE for integer clips whose LUT is never clamped (sigmaR >= 1/8): the tile is staged already multiplied
 //             by sqrt(-c2), so a tap's weight is 2^(-(a'-b')^2): FSUB, FMUL, MUFU instead of FSUB, FMNMX, FMUL, FMUL, MUFU;
+//             also f32 clips with sigmaR >= ~1.95 (one FMNMX more per tap for the clamp of |a-b| to 1), where skipping the
+//             quantisation of the range index moves the result by < 4e-6 relative;
 //   W_GLOBAL  gathers from the full LUT in HBM/L2: bit-identical, slow (validation / VSZIP_BILATERAL_EXACT=1).
 #include <cuda_fp16.h>
 
@@ -35,7 +37,8 @@ struct BilateralPlaneParams {
     int lut_len;       // entries [0, lut_len) are distinct; larger indices use gr[lut_len-1]
     int smem_lut;      // entries copied to shared memory (W_SMEM)
     float c2, cnorm;   // W_COMPUTE: weight = cnorm * exp2(c2 * idx^2)
-    float scale, inv_scale;  // W_SCALED: sqrt(-c2) and its reciprocal
+    float scale, inv_scale;  // W_SCALED: sqrt(-c2) (x 65535 for f32 clips: the range index is |a-b|*65535 there) and its reciprocal
+    float dmax;              // W_SCALED on f32 clips: the scaled difference of min(1, |a-b|) = 1
 };
 
 struct BilateralParams {
@@ -208,7 +211,10 @@ __global__ void __launch_bounds__(TW * TH) bilateral_kernel(const BatchJob job, 
                 const float v3 = JOINT ? s_src[up - xx] : r3, v4 = JOINT ? s_src[dn - xx] : r4;
                 float g1, g2, g3, g4;
                 if constexpr (WM == W_SCALED) {
-                    const float d1 = __fsub_rn(cref, r1), d2 = __fsub_rn(cref, r2v), d3 = __fsub_rn(cref, r3), d4 = __fsub_rn(cref, r4);
+                    float d1 = __fsub_rn(cref, r1), d2 = __fsub_rn(cref, r2v), d3 = __fsub_rn(cref, r3), d4 = __fsub_rn(cref, r4);
+                    if constexpr (BTr<T>::flt) {  // rangeIndex clamps float differences to 1 (samples outside [0, 1] are legal)
+                        d1 = fminf(fabsf(d1), pp.dmax); d2 = fminf(fabsf(d2), pp.dmax); d3 = fminf(fabsf(d3), pp.dmax); d4 = fminf(fabsf(d4), pp.dmax);
+                    }
                     g1 = ex2_approx(__fmul_rn(-d1, d1)); g2 = ex2_approx(__fmul_rn(-d2, d2));
                     g3 = ex2_approx(__fmul_rn(-d3, d3)); g4 = ex2_approx(__fmul_rn(-d4, d4));
                 } else {
@@ -318,6 +324,17 @@ static int run_bilateral_t(const FrameLayout& l, const bool mask[3], const char*
             wm = W_SCALED;
             pp.scale = std::sqrt(-pp.c2);
             pp.inv_scale = 1.0f / pp.scale;
+        }
+        // f32 clip with a very wide range kernel (BASELINE config 5: sigmaR = 2).  The reference quantises |a-b| to the index
+        // idx = trunc(min(1,|a-b|)*65535 + 0.5); the scaled form uses t = min(1,|a-b|)*65535 itself.  |idx^2 - t^2| <= 65535, so a
+        // weight changes by at most ln2 * |c2| * 65535 relative and the weighted mean by at most twice that: allowed while that
+        // stays below 4e-6 (the bar is 1e-5 relative; the MUFU weights and the reciprocal add ~5e-7).  sigmaR = 2: 3.8e-6.
+        // f16 clips round the difference in f16 first (bilateral.zig:15-22) and keep the computed-index path.
+        if (wm == W_COMPUTE && std::is_same<T, float>::value && pp.lut_len - 1 >= 65535 && 2.0 * 0.6931472 * (double)(-pp.c2) * 65535.0 <= 4e-6) {
+            wm = W_SCALED;
+            pp.scale = std::sqrt(-pp.c2) * 65535.0f;
+            pp.inv_scale = 1.0f / pp.scale;
+            pp.dmax = pp.scale;
         }
         const int r = pp.radius;
         // strip length: whole tile rows when the batch alone fills the GPU, shorter strips for single frames
