@@ -13,10 +13,10 @@ copies inside the timed region (`e2e`).
 The JSON line carries, next to the contract keys:
   configs   one entry per BASELINE.json config (c1..c5): device-resident frames/s, algorithmic GB/s and fraction of the
             measured HBM peak at this N; c5 also end to end through the fused chain frame API
-  e2e       value = frames/s through vszip_boxblur_get_frame on PAGEABLE host planes, the way VapourSynth hands them over
-            (library default: memcpy through the slots' pinned staging buffers); `pageable_registered` = the opt-in host pin
-            cache (buffers that come back are page-locked in place), `pinned` = application-pinned frames,
-            `pcie_ceiling_fps` = copy-only probe (same bytes up and down, no kernels) at the same N
+  e2e       value = frames/s through vszip_boxblur_get_frame on frames in pinned host memory (the bench contract's definition);
+            `pageable` = the same call on PAGEABLE planes, the way VapourSynth hands them over (library default: CPU copies
+            through the slots' pinned staging buffers), `pageable_registered` = the opt-in host pin cache (buffers that come
+            back are page-locked in place), `pcie_ceiling_fps` = copy-only probe (same bytes up and down, no kernels) at the same N
 
 Multi-GPU (torchrun, one rank per GPU): frames are independent, every rank processes its own frames (frame n -> GPU n mod k),
 no collective on the data path; scaling is weak.  Timed regions are bracketed by barrier + synchronize, timed with CUDA events
@@ -366,11 +366,15 @@ def run_ours(args):
             "config": CONFIG,
             "batch": {"frames_per_step_per_gpu": n, "bytes_per_step_per_gpu": 2 * n * FRAME_BYTES, "host_cores_per_rank": len(my_cores) if my_cores else None},
             "clocks": clocks,
-            "e2e": {"value": e2e_staged, "unit": "frames/s", "h2d_bytes_per_step": ne * FRAME_BYTES, "d2h_bytes_per_step": ne * FRAME_BYTES,
-                    "frames_per_step_per_gpu": ne, "in_flight": in_flight_staged, "in_flight_dma_legs": in_flight,
-                    "api": "vszip_boxblur_get_frame on PAGEABLE host planes (library default: memcpy through pinned staging buffers, both directions)",
-                    "pageable_registered": e2e_registered, "registered_bytes": registered, "pinned": e2e_pinned, "pcie_ceiling_fps": ceiling,
-                    "variants": "value = pageable planes, default path; pageable_registered = opt-in host pin cache (vszip_cuda_host_register_limit); pinned = application-pinned frames",
+            "e2e": {"value": e2e_pinned, "unit": "frames/s", "h2d_bytes_per_step": ne * FRAME_BYTES, "d2h_bytes_per_step": ne * FRAME_BYTES,
+                    "frames_per_step_per_gpu": ne, "in_flight": in_flight,
+                    "api": "vszip_boxblur_get_frame; value = frames in pinned host memory (the bench contract's definition of e2e), one DMA per direction",
+                    "pageable": e2e_staged, "pageable_in_flight": in_flight_staged,
+                    "pageable_note": "the same call on PAGEABLE planes that come back step after step, the way VapourSynth's frame pool hands them "
+                                     "over: the library's default path (CPU copies through pinned staging buffers, both directions) - what a .vpy script gets",
+                    "pageable_registered": e2e_registered, "registered_bytes": registered,
+                    "pageable_registered_note": "opt-in host pin cache (vszip_cuda_host_register_limit): buffers that come back are page-locked in place",
+                    "pcie_ceiling_fps": ceiling,
                     "pcie_ceiling_note": "copy-only probe in this run at this N: the same frames up and down on 8 streams per GPU, no kernels"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

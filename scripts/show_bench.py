@@ -3,7 +3,7 @@ import json, sys
 l = json.loads(open(sys.argv[1]).read())
 print(f"value {l['value']:.0f} {l['unit']} ms/step {l['ms_per_step']:.3f} launches {l['gpu_launches']} clocks {l['clocks']}")
 e = l["e2e"]
-print("e2e", {k: (round(v) if isinstance(v, float) else v) for k, v in e.items() if k in ("value", "pageable_registered", "pinned", "pcie_ceiling_fps", "in_flight", "in_flight_dma_legs")})
+print("e2e", {k: (round(v) if isinstance(v, float) else v) for k, v in e.items() if k in ("value", "pageable", "pageable_registered", "pcie_ceiling_fps", "in_flight", "pageable_in_flight")})
 r = l["roofline"]; print("roofline", r["kernel"], f"{r['achieved']:.0f}/{r['peak']:.0f} = {r['frac']:.3f} traffic {r['traffic']}")
 print("path", {k: round(v, 3) for k, v in l["path"].items()})
 print("cpu", l["cpu_baseline"] and (round(l["cpu_baseline"]["value"]), l["cpu_baseline"]["cores"]))
