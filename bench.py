@@ -417,17 +417,16 @@ def other_configs(vz, lib, torch, np, timed, timed_host, stream, world, peak, he
                  "algorithmic_bytes_per_frame": ALGO_BYTES, "GBps_per_gpu": headline_gbs, "frac_of_hbm_peak": headline_gbs / peak}
     out["c3"] = pixel("configs[2]: Bilateral sigmaS=2 sigmaR=2 planes=[0,1,2]", "YUV420P16", 1920, 1080, 128,
                       lambda s: vz.BilateralFilter(s.info(), sigmaS=2, sigmaR=2, planes=[0, 1, 2]))
-    # the kernel is compute-bound, so the HBM fraction says little: the same measurement against the three SM roofs that bind it
-    # (36 taps per pixel = 36 MUFU.EX2 and 36 shared-memory loads; 156 issued warp-instructions per pixel from the ncu capture in
-    # profiles/ncu_bilateral_r01.md; per SM and clock: 32 MUFU lanes, 32 shared-memory words, 4 issue slots)
+    # the kernel is compute-bound, so the HBM fraction says little: the same measurement against the SM roofs that bind it
+    # (sigmaS = 2 -> pattern (2,2): 16 taps per pixel = 16 MUFU.EX2 + 1 MUFU.RCP; 156 issued warp-instructions per pixel from the ncu
+    # capture in profiles/ncu_bilateral_r02.md; per SM and clock: 16 MUFU lanes, 4 issue slots)
     props = torch.cuda.get_device_properties(torch.cuda.current_device())
-    clock_hz = 1e6 * float(props.clock_rate) / 1e3 if getattr(props, "clock_rate", 0) else 1.965e9
+    clock_hz = float(props.clock_rate) * 1e3 if getattr(props, "clock_rate", 0) else 1.965e9
     px_per_s = out["c3"]["fps"] / world * (1920 * 1080 * 1.5)
     sms = props.multi_processor_count
-    out["c3"]["roofs"] = {"mufu_frac": px_per_s * 36 / (sms * 32 * clock_hz), "smem_load_frac": px_per_s * 36 / (sms * 32 * clock_hz),
-                          "issue_frac": px_per_s * 156 / 32 / (sms * 4 * clock_hz), "sm_clock_hz": clock_hz,
-                          "note": "fractions of per-SM peaks at the SM's maximum clock: MUFU 32 lanes/clk, shared memory 32 words/clk, issue 4 warp-instructions/clk"}
-
+    out["c3"]["roofs"] = {"mufu_frac": px_per_s * 17 / (sms * 16 * clock_hz), "issue_frac": px_per_s * 156 / 32 / (sms * 4 * clock_hz),
+                          "sm_clock_hz": clock_hz,
+                          "note": "fractions of per-SM peaks at the SM's maximum clock: MUFU 16 lanes/clk, issue 4 warp-instructions/clk"}
     # configs[3]: PlaneMinMax + PlaneAverage with minthr/maxthr/exclude on 4K GRAYS and GRAY16; both results per frame
     c4 = {}
     for fmt, excl in (("GRAY16", [0, 32768]), ("GRAYS", [0, 1])):
@@ -448,7 +447,7 @@ def other_configs(vz, lib, torch, np, timed, timed_host, stream, world, peak, he
     out["c4"] = {"config": "configs[3]: PlaneMinMax + PlaneAverage with minthr/maxthr/exclude on 3840x2160 GRAYS and GRAY16", **c4}
 
     # configs[4]: BoxBlur -> Bilateral -> PlaneMinMax on 3840x2160 YUV444PS, frame-parallel
-    fmt, w, h, frames = "YUV444PS", 3840, 2160, 8
+    fmt, w, h, frames = "YUV444PS", 3840, 2160, 16
     a, b, c = (vz.DeviceClip(fmt, w, h, frames) for _ in range(3))
     a.fill_noise(1234)
     blur = vz.BoxBlurFilter(a.info(), hradius=13, hpasses=1, vradius=13, vpasses=1)

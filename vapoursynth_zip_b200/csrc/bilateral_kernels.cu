@@ -49,7 +49,13 @@ struct BilateralParams {
     int strip;                   // tiles per CTA
 };
 
-template <typename T> __device__ __forceinline__ float widen(T v) { return (float)v; }
+// Integer samples reach f32 and come back without the conversion unit: I2F / F2I share the quarter-rate XU pipe with MUFU.EX2,
+// which is the pipe that bounds this kernel (ncu: 16 EX2 + 2.5 conversions + 1 RCP per pixel on config 3).  x < 2^23 is the
+// mantissa of the float 2^23 + x: OR in the exponent, subtract the bias (exact); on the way out FADD.RZ(v, 2^23) leaves trunc(v) in
+// the mantissa for 0 <= v < 2^23.
+template <typename T> __device__ __forceinline__ float widen(T v) { return __fsub_rn(__uint_as_float(0x4B000000u | (unsigned int)v), 8388608.0f); }
+template <> __device__ __forceinline__ float widen<float>(float v) { return v; }
+__device__ __forceinline__ unsigned int trunc_to_uint(float v) { return __float_as_uint(__fadd_rz(v, 8388608.0f)) & 0x7fffffu; }
 template <> __device__ __forceinline__ float widen<__half>(__half v) { return __half2float(v); }
 
 template <typename T> struct BTr { static constexpr bool flt = false; };
@@ -258,7 +264,7 @@ __global__ void __launch_bounds__(TW * TH) bilateral_kernel(const BatchJob job, 
             T* out = reinterpret_cast<T*>(dst + (size_t)y * pj.dst_pitch) + x;
             if constexpr (std::is_same<T, float>::value) *out = q;
             else if constexpr (std::is_same<T, __half>::value) *out = __float2half_rn(q);
-            else *out = (T)fminf(fmaxf(__fadd_rn(q, 0.5f), 0.0f), prm.peak);  // trunc(clamp(q + 0.5, 0, peak))
+            else *out = (T)trunc_to_uint(fminf(fmaxf(__fadd_rn(q, 0.5f), 0.0f), prm.peak));  // trunc(clamp(q + 0.5, 0, peak))
         }
     }
 }

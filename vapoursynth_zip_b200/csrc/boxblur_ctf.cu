@@ -220,6 +220,9 @@ __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n"
@@ -364,10 +367,9 @@ __device__ __forceinline__ void ring_put(const float (&xv)[TS], float (&carry)[V
     }
 }
 
-// named barriers (bar 0 is __syncthreads): the 128 row threads among themselves, and the two output tiles' full / empty hand-over
-// between the row threads and the store warp
+// named barriers (bar 0 is __syncthreads): the full / empty hand-over of the output ring between the row threads and the store warp
 constexpr int kStoreThreads = 32, kHThreads = kThreads + kStoreThreads;
-enum { BAR_ROWS = 1, BAR_FULL = 2, BAR_EMPTY = 4 };
+enum { BAR_FULL = 2, BAR_EMPTY = 4 };
 __device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
@@ -380,7 +382,7 @@ __global__ void __launch_bounds__(kHThreads) ctf_h_kernel(const CtfJob job, cons
     using G = HTile<T, R>;
     constexpr int K = G::K, VEC = G::VEC, TS = G::TS;
     extern __shared__ __align__(128) unsigned char ctf_smem[];
-    __shared__ uint64_t full[G::STAGES];
+    __shared__ uint64_t full[G::STAGES], consumed[G::STAGES];  // per input stage: TMA has landed / all 128 row threads have read it
     int local;
     const CtfPlane& pj = ctf_plane(job, blockIdx.y, local);
     const int plane = (int)(&pj - job.pl);
@@ -395,10 +397,16 @@ __global__ void __launch_bounds__(kHThreads) ctf_h_kernel(const CtfJob job, cons
 
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < G::STAGES; ++s) mbar_init(&full[s], 1);
+        for (int s = 0; s < G::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&consumed[s], kThreads); }
         fence_mbar_init();
     }
     __syncthreads();
+    // the store warp is also the TMA producer: the row threads never wait for each other, only for their data
+    auto issue = [&](int i) {  // one thread
+        const int s = i % G::STAGES;
+        mbar_expect_tx(&full[s], (uint32_t)G::TILE_BYTES);
+        tma_load_3d(in_tiles + s * G::TILE_BYTES, &maps.in[plane], (xs + R + i * TS) & ~(VEC - 1), row0, f, &full[s]);
+    };
 
     // the ring's sample 0 is plane sample xbase: the 128-byte line that holds the piece's first output
     const int xbase = xs & ~(G::CH - 1);
@@ -408,8 +416,15 @@ __global__ void __launch_bounds__(kHThreads) ctf_h_kernel(const CtfJob job, cons
         const uint32_t dp = (uint32_t)pj.dst_pitch;
         const int sub = lane >> 3, vq = lane & 7;
         int chunk = 0;  // next chunk to store
+        if (lane == 0)
+            for (int i = 0; i < min(G::STAGES, ntiles); ++i) issue(i);
         for (int i = 0; i < ntiles; ++i) {
             const int b = i & 1;
+            if (lane == 0 && i + G::STAGES < ntiles) {  // tile i has been read into registers by every row thread: refill its stage
+                mbar_wait(&consumed[i % G::STAGES], (uint32_t)(i / G::STAGES) & 1u);
+                issue(i + G::STAGES);
+            }
+            __syncwarp();
             bar_sync(BAR_FULL + b, kHThreads);
             const int done = min(xs + (i + 1) * TS, xe) - xbase;  // results [xs - xbase, done) are in the ring
             while ((chunk + 1) * G::CH <= done || (i == ntiles - 1 && chunk * G::CH < done)) {
@@ -448,14 +463,6 @@ __global__ void __launch_bounds__(kHThreads) ctf_h_kernel(const CtfJob job, cons
     const float div = job.div;
     const T* srow = reinterpret_cast<const T*>(job.src + (size_t)f * job.src_fs + pj.src_off + (size_t)min(row, pj.h - 1) * pj.src_pitch);
     T* drow = reinterpret_cast<T*>(job.dst + (size_t)f * job.dst_fs + pj.dst_off + (size_t)min(row, pj.h - 1) * pj.dst_pitch);
-    auto issue = [&](int i) {  // thread 0
-        const int s = i % G::STAGES;
-        mbar_expect_tx(&full[s], (uint32_t)G::TILE_BYTES);
-        tma_load_3d(in_tiles + s * G::TILE_BYTES, &maps.in[plane], (xs + R + i * TS) & ~(VEC - 1), row0, f, &full[s]);
-    };
-    if (tid == 0)
-        for (int i = 0; i < min(G::STAGES, ntiles); ++i) issue(i);
-
     // warm-up: the 2r samples before the first tile, straight from global memory (also the low edge's samples for piece 0)
     float acc[K][1];
 #pragma unroll
@@ -482,6 +489,7 @@ __global__ void __launch_bounds__(kHThreads) ctf_h_kernel(const CtfJob job, cons
             for (int v = 0; v < G::NVR; ++v) vec_to_floats<T>(q[v], e + v * VEC);
             take_phase<TS, VEC>(e, xv, (xs + R + i * TS) & (VEC - 1));
         }
+        mbar_arrive(&consumed[s]);  // (the values are in registers: shared-memory reads complete before a dependent instruction issues)
         // tile step j = b*K + u is global step 2r + i*TS + j: fresh slot (u - 1) mod K, complete slot u
         static_for<0, TS>([&](auto jc) {
             constexpr int J = decltype(jc)::value, U = J % K;
@@ -494,9 +502,7 @@ __global__ void __launch_bounds__(kHThreads) ctf_h_kernel(const CtfJob job, cons
             const int rel = xs + i * TS - xbase;
             ring_put<T, TS, VEC, G::RV>(xv, carry, reinterpret_cast<uint4*>(ring + tid * G::OROW_BYTES), (rel / VEC) % G::RV, rel & (VEC - 1));
         }
-        bar_arrive(BAR_FULL + b, kHThreads);             // hand the tile to the store warp
-        bar_sync(BAR_ROWS, kThreads);                    // every row thread has consumed stage s
-        if (tid == 0 && i + G::STAGES < ntiles) issue(i + G::STAGES);
+        bar_arrive(BAR_FULL + b, kHThreads);             // hand the tile's results to the store warp
     }
 
     if (sg == pj.segs - 1 && live) {  // outputs w-r..w-1 from samples w-2r..w-1
