@@ -42,7 +42,7 @@ struct BilateralPlaneParams {
 };
 
 struct BilateralParams {
-    BilateralPlaneParams pl[3];  // indexed by PlaneJob::aux (the real plane number)
+    BilateralPlaneParams pl[1];  // the launch's plane
     float peak;
     int tiles_x[3];              // 32x32 tiles per row, indexed like job.pl[]
     int strips_x[3];             // CTAs per tile row
@@ -103,11 +103,12 @@ __device__ __forceinline__ float range_weight(float fi, float top, const Bilater
 template <typename T, bool JOINT, int WM, int SAMPLES, int STEP>
 __global__ void __launch_bounds__(TW * TH) bilateral_kernel(const BatchJob job, const BilateralParams prm) {
     extern __shared__ float smem_f[];
-    int k = job.nplanes - 1;
-    while (k > 0 && (int)blockIdx.x < job.pl[k].cta_begin) --k;
-    const PlaneJob& pj = job.pl[k];
-    const BilateralPlaneParams& pp = prm.pl[pj.aux];
-    const int local = blockIdx.x - pj.cta_begin;
+    // one plane per launch (planes differ in radius, weight source and shared-memory size): its descriptors sit at index 0, so every
+    // parameter is a constant-bank operand at a fixed offset (a run-time plane index cost 6.5 LDC per pixel in the ncu instruction mix)
+    constexpr int k = 0;
+    const PlaneJob& pj = job.pl[0];
+    const BilateralPlaneParams& pp = prm.pl[0];
+    const int local = blockIdx.x;
     const int strips_x = prm.strips_x[k];
     const int sx = local % strips_x, ty0 = local / strips_x;
     const int y0 = ty0 * TILE;
@@ -318,7 +319,7 @@ static int run_bilateral_t(const FrameLayout& l, const bool mask[3], const char*
         one[p] = true;
         BilateralParams prm{};
         prm.peak = bp.peak;
-        BilateralPlaneParams& pp = prm.pl[p];
+        BilateralPlaneParams& pp = prm.pl[0];
         pp.gs = bp.gs[p]; pp.gr = bp.gr[p];
         pp.radius = bp.radius[p]; pp.step = bp.step[p];
         pp.lut_len = bp.lut_len[p];
