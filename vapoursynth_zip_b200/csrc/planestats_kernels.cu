@@ -112,11 +112,16 @@ template <typename T> __device__ __forceinline__ double abs_diff(T a, T b, unsig
 
 // histogram bin of a sample (src/filters/planeminmax.zig:26,33): ints index directly, floats use
 // sat_u16(trunc(f32(v)*65535 + 0.5)) with separate multiply and add.
+// Float bins without the conversion unit and with one clamp instead of two: saturating the SAMPLE to [0, 1] (NaN -> 0) gives the same
+// bin as clamping v*65535 + 0.5 to [0, 65535] - below 0 both truncate to 0, above 1 both give 65535 - and FADD.RZ(f, 2^23) leaves
+// trunc(f) in the low mantissa bits for f in [0.5, 65535.5].  bin_bits returns that float's bit pattern (bin in bits 0..15).
+template <typename T> __device__ __forceinline__ unsigned int bin_bits(T v) {
+    const float f = __fadd_rn(__fmul_rn(__saturatef(as_float<T>(v)), 65535.0f), 0.5f);
+    return __float_as_uint(__fadd_rz(f, 8388608.0f));
+}
 template <typename T> __device__ __forceinline__ unsigned int bin_of(T v) {
     if constexpr (El<T>::flt) {
-        const float f = __fadd_rn(__fmul_rn(as_float<T>(v), 65535.0f), 0.5f);
-        // NaN and <= 0 -> 0 (fmaxf returns the non-NaN operand), >= 65535 -> 65535, else truncation: two FMNMX + F2I
-        return __float2uint_rz(fminf(fmaxf(f, 0.0f), 65535.0f));
+        return bin_bits<T>(v) & 0xffffu;
     } else {
         return (unsigned int)v;
     }
@@ -734,7 +739,7 @@ template <typename T> __device__ __forceinline__ void pack_bins(const uint4& v, 
     } else {
         const T* e = reinterpret_cast<const T*>(&v);
 #pragma unroll
-        for (int q = 0; q < El<T>::PER16 / 2; ++q) w[q] = bin_of<T>(e[2 * q]) | (bin_of<T>(e[2 * q + 1]) << 16);
+        for (int q = 0; q < El<T>::PER16 / 2; ++q) w[q] = __byte_perm(bin_bits<T>(e[2 * q]), bin_bits<T>(e[2 * q + 1]), 0x5410);  // low halves of both
     }
 }
 
