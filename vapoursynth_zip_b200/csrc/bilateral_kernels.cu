@@ -161,10 +161,11 @@ __global__ void __launch_bounds__(TW * TH) bilateral_kernel(const BatchJob job, 
     }
     auto fetch_tile = [&](int tx) {
         const int x0 = tx * TILE;
+        const bool inner = x0 >= r && x0 + TILE + r <= pj.w;  // tile + halo inside the plane's columns: no clamps (most tiles)
 #pragma unroll
         for (int i = 0; i < NPT; ++i) {
-            if (tid + i * (TW * TH) < tsize) {
-                const int gx = min(max(x0 + lxr[i], 0), pj.w - 1);
+            if (i < NPT - 1 || tid + i * (TW * TH) < tsize) {   // only the last round of a tile is partial
+                const int gx = inner ? x0 + lxr[i] : min(max(x0 + lxr[i], 0), pj.w - 1);
                 pre_s[i] = reinterpret_cast<const T*>(src + row_off[i])[gx];
                 if constexpr (JOINT) pre_r[i] = reinterpret_cast<const T*>(ref + ref_off[i])[gx];
             }
@@ -179,7 +180,7 @@ __global__ void __launch_bounds__(TW * TH) bilateral_kernel(const BatchJob job, 
 #pragma unroll
             for (int i = 0; i < NPT; ++i) {
                 const int e = tid + i * (TW * TH);
-                if (e < tsize) {
+                if (i < NPT - 1 || e < tsize) {
                     const float sv = widen<T>(pre_s[i]);
                     s_src[e] = (WM == W_SCALED && !JOINT) ? __fmul_rn(sv, pp.scale) : sv;
                     if constexpr (JOINT) {
@@ -258,13 +259,19 @@ __global__ void __launch_bounds__(TW * TH) bilateral_kernel(const BatchJob job, 
                 // non-joint values were staged scaled, so the scale goes back in here
                 float rw;
                 asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rw) : "f"(wsum));
-                q = __fmul_rn(sum, JOINT ? rw : __fmul_rn(rw, pp.inv_scale));
+                if constexpr (!JOINT && !BTr<T>::flt) q = __fmaf_rn(__fmul_rn(sum, rw), pp.inv_scale, 0.5f);  // + 0.5: see the store below
+                else q = __fmul_rn(sum, JOINT ? rw : __fmul_rn(rw, pp.inv_scale));
             } else {
                 q = __fdiv_rn(sum, wsum);
             }
             T* out = reinterpret_cast<T*>(dst + (size_t)y * pj.dst_pitch) + x;
             if constexpr (std::is_same<T, float>::value) *out = q;
             else if constexpr (std::is_same<T, __half>::value) *out = __float2half_rn(q);
+            else if constexpr (WM == W_SCALED && !JOINT) {
+                // q = (sum * rw) * inv_scale was formed above; the rounding offset rides on the same multiply here instead
+                // (approximate-weights mode): trunc(clamp(sum * rw * inv_scale + 0.5, 0, peak))
+                *out = (T)trunc_to_uint(fminf(fmaxf(q, 0.0f), prm.peak));
+            }
             else *out = (T)trunc_to_uint(fminf(fmaxf(__fadd_rn(q, 0.5f), 0.0f), prm.peak));  // trunc(clamp(q + 0.5, 0, peak))
         }
     }
