@@ -207,3 +207,17 @@ def test_comptime_float_small_case_for_the_sanitizer(fmt):
     for r in (3, 13):
         clip = noise_clip(fmt, 403, 231, seed=r)
         assert_same_planes(run(clip, hradius=r, vradius=r)["planes"], oa.boxblur(clip, hradius=r, vradius=r)["planes"], f"{fmt} r={r}")
+
+
+# --------------------------------------------------------------------------- 8-bit clips on the segment kernels (runtime path)
+@pytest.mark.parametrize(("fmt", "w", "h"), [("GRAY8", 1920, 1080), ("YUV420P8", 1920, 1080), ("GRAY8", 331, 203), ("YUV420P8", 642, 362),
+                                            ("GRAY8", 1280, 720), ("GRAY8", 64, 90), ("GRAY8", 61, 33), ("YUV444P8", 960, 540)])
+def test_runtime_8bit_on_segment_kernels(fmt, w, h):
+    """8-bit clips run the 16-bit segment arithmetic behind a widen/narrow step: whole and ragged rows, heights that are and are
+    not multiples of 90 (TMA tile kernel / plain loads), several radii and pass counts, H-only and V-only."""
+    clip = noise_clip(fmt, w, h, seed=w + h)
+    for args in (dict(hradius=13, hpasses=5, vradius=13, vpasses=5), dict(hradius=3, hpasses=2, vradius=0, vpasses=0),
+                 dict(hradius=0, hpasses=0, vradius=7, vpasses=3), dict(hradius=22, hpasses=1, vradius=1, vpasses=4)):
+        if 2 * max(args["hradius"], 1) >= (w >> (1 if fmt.startswith("YUV420") else 0)) or 2 * max(args["vradius"], 1) >= (h >> (1 if fmt.startswith("YUV420") else 0)):
+            continue
+        assert_same_planes(run(clip, **args)["planes"], oa.boxblur(clip, **args)["planes"], f"{fmt} {w}x{h} {args}")

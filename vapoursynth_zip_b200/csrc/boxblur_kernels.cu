@@ -1187,10 +1187,10 @@ static bool use_seg_kernels() {
 template <typename T, bool H>
 static int run_axis_any(const FrameLayout& l, const bool mask[3], const char* src, size_t sfs, char* dst, size_t dfs, int count, int r,
                         int passes, cudaStream_t st) {
-    if constexpr (std::is_same<T, uint16_t>::value) {
+    if constexpr (std::is_same<T, uint16_t>::value || std::is_same<T, uint8_t>::value) {
         if (use_seg_kernels()) {
-            const int rc = H ? run_seg_h_u16(l, mask, src, sfs, dst, dfs, count, r, passes, st)
-                             : run_seg_v_u16(l, mask, src, sfs, dst, dfs, count, r, passes, st);
+            const int rc = H ? run_seg_h(l, mask, src, sfs, dst, dfs, count, r, passes, st)
+                             : run_seg_v(l, mask, src, sfs, dst, dfs, count, r, passes, st);
             if (rc <= 0) return rc;  // done, or a CUDA error; 1 = not applicable
         }
     }

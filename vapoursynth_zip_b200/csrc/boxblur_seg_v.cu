@@ -14,7 +14,20 @@ template <int LV> struct VSegShape;
 template <> struct VSegShape<90> { static constexpr int MAX_WARPS = 12; };
 template <> struct VSegShape<60> { static constexpr int MAX_WARPS = 18; };
 
-template <int R, int LV>
+// U8 (both V kernels): a lane's pair of columns is two BYTES per row; they are widened into the packed 16-bit word on the way in
+// and narrowed on the way out, the passes in between are the 16-bit kernel.
+__device__ __forceinline__ uint32_t widen2(uint32_t b2) { return __byte_perm(b2, 0u, 0x4140); }    // bytes 0,1 -> halves
+__device__ __forceinline__ uint16_t narrow2(uint32_t w) { return (uint16_t)__byte_perm(w, 0u, 0x4420); }  // low bytes of both halves
+template <bool U8> __device__ __forceinline__ uint32_t ld_pair(const char* p) {
+    if constexpr (U8) return widen2(*reinterpret_cast<const uint16_t*>(p));
+    else return *reinterpret_cast<const uint32_t*>(p);
+}
+template <bool U8> __device__ __forceinline__ void st_pair(char* p, uint32_t w) {
+    if constexpr (U8) *reinterpret_cast<uint16_t*>(p) = narrow2(w);
+    else *reinterpret_cast<uint32_t*>(p) = w;
+}
+
+template <int R, int LV, bool U8>
 __global__ void __launch_bounds__(VSegShape<LV>::MAX_WARPS * 32, 1) vseg_kernel(const SegJob job) {
     using Gm = VGeom<R, LV>;
     extern __shared__ __align__(128) unsigned char seg_smem[];
@@ -29,8 +42,8 @@ __global__ void __launch_bounds__(VSegShape<LV>::MAX_WARPS * 32, 1) vseg_kernel(
     const bool colok = cw * 2 < pj.w;
     const bool segok = s < S;
     const bool exact = (n % LV) == 0;
-    const char* src = job.src + (size_t)blockIdx.x * job.src_fs + pj.src_off + (size_t)cw * 4;
-    char* dst = job.dst + (size_t)blockIdx.x * job.dst_fs + pj.dst_off + (size_t)cw * 4;
+    const char* src = job.src + (size_t)blockIdx.x * job.src_fs + pj.src_off + (size_t)cw * (U8 ? 2 : 4);
+    char* dst = job.dst + (size_t)blockIdx.x * job.dst_fs + pj.dst_off + (size_t)cw * (U8 ? 2 : 4);
 
     uint32_t e[Gm::NW];
 #pragma unroll
@@ -39,10 +52,10 @@ __global__ void __launch_bounds__(VSegShape<LV>::MAX_WARPS * 32, 1) vseg_kernel(
         const int y0 = LV * s;
         if (y0 + LV <= n) {
 #pragma unroll
-            for (int i = 0; i < LV; ++i) e[R + i] = *reinterpret_cast<const uint32_t*>(src + (size_t)(y0 + i) * pj.src_pitch);
+            for (int i = 0; i < LV; ++i) e[R + i] = ld_pair<U8>(src + (size_t)(y0 + i) * pj.src_pitch);
         } else {
 #pragma unroll
-            for (int i = 0; i < LV; ++i) e[R + i] = *reinterpret_cast<const uint32_t*>(src + (size_t)min(y0 + i, n - 1) * pj.src_pitch);
+            for (int i = 0; i < LV; ++i) e[R + i] = ld_pair<U8>(src + (size_t)min(y0 + i, n - 1) * pj.src_pitch);
         }
     }
     for (int p = 0; p < job.passes; ++p) {
@@ -104,11 +117,11 @@ __global__ void __launch_bounds__(VSegShape<LV>::MAX_WARPS * 32, 1) vseg_kernel(
         const int y0 = LV * s;
         if (y0 + LV <= n) {
 #pragma unroll
-            for (int i = 0; i < LV; ++i) *reinterpret_cast<uint32_t*>(dst + (size_t)(y0 + i) * pj.dst_pitch) = e[R + i];
+            for (int i = 0; i < LV; ++i) st_pair<U8>(dst + (size_t)(y0 + i) * pj.dst_pitch, e[R + i]);
         } else {
 #pragma unroll
             for (int i = 0; i < LV; ++i)
-                if (y0 + i < n) *reinterpret_cast<uint32_t*>(dst + (size_t)(y0 + i) * pj.dst_pitch) = e[R + i];
+                if (y0 + i < n) st_pair<U8>(dst + (size_t)(y0 + i) * pj.dst_pitch, e[R + i]);
         }
     }
 }
@@ -128,7 +141,7 @@ __device__ __forceinline__ void tma_load_3d(void* sdst, const CUtensorMap* map, 
                  : "memory");
 }
 
-template <int R>
+template <int R, bool U8>
 __global__ void __launch_bounds__(VSegShape<LVT>::MAX_WARPS * 32, 1)
     vseg_tile_kernel(const SegJob job, const __grid_constant__ VTiles tiles, int strips, int nitems) {
     using Gm = VGeom<R, LVT>;
@@ -136,10 +149,11 @@ __global__ void __launch_bounds__(VSegShape<LVT>::MAX_WARPS * 32, 1)
     __shared__ uint64_t tile_bar;
     const int s = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int S = blockDim.x >> 5;
-    uint32_t* tile = reinterpret_cast<uint32_t*>(seg_smem);         // [S * 90 rows][32 words]
-    uint32_t* halo = tile + (size_t)S * LVT * 32;                    // [2][S][2r][32]: first r and last r rows of every segment
+    constexpr int ROWB = U8 ? 64 : 128;                              // bytes of a tile row: 64 columns
+    unsigned char* tile = seg_smem;                                  // [S * 90 rows][64 columns]
+    uint32_t* halo = reinterpret_cast<uint32_t*>(seg_smem + (size_t)S * LVT * ROWB);  // [2][S][2r][32]: first r and last r rows of every segment
     uint32_t* cbuf = halo + (size_t)2 * S * 2 * R * 32;              // [2][2][32] line constants
-    const uint32_t tile_bytes = (uint32_t)S * LVT * 128;
+    const uint32_t tile_bytes = (uint32_t)S * LVT * ROWB;
 
     if (threadIdx.x == 0) {
         mbar_init(&tile_bar, 1);
@@ -149,7 +163,7 @@ __global__ void __launch_bounds__(VSegShape<LVT>::MAX_WARPS * 32, 1)
     auto issue = [&](int item) {  // thread 0: one box per warp segment
         const int strip = item % strips, k = (item / strips) % job.nplanes, f = item / (strips * job.nplanes);
         mbar_expect_tx(&tile_bar, tile_bytes);
-        for (int q = 0; q < S; ++q) tma_load_3d(tile + (size_t)q * LVT * 32, &tiles.map[k], strip * 64, q * LVT, f, &tile_bar);
+        for (int q = 0; q < S; ++q) tma_load_3d(tile + (size_t)q * LVT * ROWB, &tiles.map[k], strip * 64, q * LVT, f, &tile_bar);
     };
     if (threadIdx.x == 0 && (int)blockIdx.x < nitems) issue(blockIdx.x);
 
@@ -197,9 +211,15 @@ __global__ void __launch_bounds__(VSegShape<LVT>::MAX_WARPS * 32, 1)
         mbar_wait(&tile_bar, phase);
         phase ^= 1u;
         {
-            const uint32_t* t = tile + (size_t)s * LVT * 32 + lane;
+            if constexpr (U8) {
+                const uint16_t* t = reinterpret_cast<const uint16_t*>(tile + (size_t)s * LVT * ROWB) + lane;
 #pragma unroll
-            for (int i = 0; i < LVT; ++i) ea[R + i] = t[i * 32];
+                for (int i = 0; i < LVT; ++i) ea[R + i] = widen2(t[i * 32]);
+            } else {
+                const uint32_t* t = reinterpret_cast<const uint32_t*>(tile + (size_t)s * LVT * ROWB) + lane;
+#pragma unroll
+                for (int i = 0; i < LVT; ++i) ea[R + i] = t[i * 32];
+            }
         }
         __syncthreads();  // the tile is in registers
         if (threadIdx.x == 0 && item + (int)gridDim.x < nitems) {
@@ -208,9 +228,9 @@ __global__ void __launch_bounds__(VSegShape<LVT>::MAX_WARPS * 32, 1)
         }
         // Every call site has fixed roles for the two register arrays, so at most one and a bit of them is live at any time.
         // In the last pass the results leave for global memory as they are produced (idle columns of the last strip write nowhere).
-        char* const q = job.dst + (size_t)f * job.dst_fs + pj.dst_off + (size_t)(s * LVT) * pj.dst_pitch + (size_t)cw * 4;
+        char* const q = job.dst + (size_t)f * job.dst_fs + pj.dst_off + (size_t)(s * LVT) * pj.dst_pitch + (size_t)cw * (U8 ? 2 : 4);
         const uint32_t dp = (uint32_t)pj.dst_pitch;
-        auto store = [&](int i, uint32_t v) { *reinterpret_cast<uint32_t*>(q + (size_t)((uint32_t)i * dp)) = v; };  // strips are whole (w % 64 == 0)
+        auto store = [&](int i, uint32_t v) { st_pair<U8>(q + (size_t)((uint32_t)i * dp), v); };  // strips are whole (w % 64 == 0)
         auto to_a = [&](int i, uint32_t v) { ea[R + i] = v; };
         auto to_b = [&](int i, uint32_t v) { eb[R + i] = v; };
         int left = job.passes;
@@ -241,14 +261,14 @@ TensorMapEncodeFn tensor_map_encoder() {
     return fn;
 }
 
-template <int R>
+template <int R, bool U8>
 int launch_vseg_tile(SegJob job, int count, cudaStream_t st) {
     const TensorMapEncodeFn encode = tensor_map_encoder();
     if (!encode) return 1;  // no tensor-map encoder in this driver: the generic kernel below does the job
     const int S = job.pl[0].h / LVT, strips = ((job.pl[0].w + 1) / 2 + 31) / 32;
-    const size_t smem = ((size_t)S * LVT * 32 + (size_t)2 * S * 2 * R * 32 + 128) * 4;
+    const size_t smem = (size_t)S * LVT * (U8 ? 64 : 128) + ((size_t)2 * S * 2 * R * 32 + 128) * 4;
     if (smem > (size_t)kMaxSmem) return 1;
-    auto kern = vseg_tile_kernel<R>;
+    auto kern = vseg_tile_kernel<R, U8>;
     VSZ_CUDA(allow_max_dynamic_smem(kern));
     int dev = 0, sms = 148, per_sm = 1;
     VSZ_CUDA(cudaGetDevice(&dev));
@@ -265,7 +285,7 @@ int launch_vseg_tile(SegJob job, int count, cudaStream_t st) {
             const cuuint64_t dims[3] = {(cuuint64_t)pl.w, (cuuint64_t)pl.h, (cuuint64_t)nf};
             const cuuint64_t strides[2] = {(cuuint64_t)pl.src_pitch, (cuuint64_t)j.src_fs};
             const cuuint32_t box[3] = {64, (cuuint32_t)LVT, 1}, estr[3] = {1, 1, 1};
-            const CUresult rc = encode(&tiles.map[k], CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, const_cast<char*>(j.src) + pl.src_off, dims, strides, box,
+            const CUresult rc = encode(&tiles.map[k], U8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, const_cast<char*>(j.src) + pl.src_off, dims, strides, box,
                                        estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (rc != CUDA_SUCCESS) { set_error("BoxBlur: cuTensorMapEncodeTiled failed (%d)", (int)rc); return -1; }
@@ -282,7 +302,7 @@ int launch_vseg_tile(SegJob job, int count, cudaStream_t st) {
 template <int LV> bool vseg_fits(int h) { return (h + LV - 1) / LV <= VSegShape<LV>::MAX_WARPS; }
 inline bool vseg_long(int w, int h) { return h % 90 == 0 && vseg_fits<90>(h) && w % 64 == 0; }  // whole strips, whole segments
 
-template <int R, int LV>
+template <int R, int LV, bool U8>
 int launch_vseg_shape(SegJob job, int count, cudaStream_t st) {
     int cta = 0;
     const int S = (job.pl[0].h + LV - 1) / LV;
@@ -294,28 +314,36 @@ int launch_vseg_shape(SegJob job, int count, cudaStream_t st) {
     }
     job.ctas_per_frame = cta;
     const size_t smem = ((size_t)(R + LV * S + R + 1) * 32 + 64) * 4;
-    return launch_frames(vseg_kernel<R, LV>, job, count, S * 32, smem, st);
+    return launch_frames(vseg_kernel<R, LV, U8>, job, count, S * 32, smem, st);
 }
 
-template <int R>
+template <int R, bool U8>
 int launch_vseg(const SegJob& whole, int count, cudaStream_t st) {
     for (int k = 0; k < whole.nplanes; ++k)
         if (!vseg_long(whole.pl[k].w, whole.pl[k].h) && !vseg_fits<60>(whole.pl[k].h)) return 1;
     return for_each_shape(whole, [&](SegJob job) {
-        if (vseg_long(job.pl[0].w, job.pl[0].h)) return launch_vseg_tile<R>(job, count, st);
-        return launch_vseg_shape<R, 60>(job, count, st);
+        if (vseg_long(job.pl[0].w, job.pl[0].h)) return launch_vseg_tile<R, U8>(job, count, st);
+        return launch_vseg_shape<R, 60, U8>(job, count, st);
     });
 }
 
 }  // namespace
 
 // Entry points.  Return 0 = done, 1 = not applicable (the caller falls back to the streaming kernels), < 0 = error.
-int run_seg_v_u16(const FrameLayout& l, const bool mask[3], const char* src, size_t sfs, char* dst, size_t dfs, int count, int r, int passes,
-                  cudaStream_t st) {
-    if (l.kind != K_U16 || passes < 1) return 1;
+int run_seg_v(const FrameLayout& l, const bool mask[3], const char* src, size_t sfs, char* dst, size_t dfs, int count, int r, int passes,
+              cudaStream_t st) {
+    if ((l.kind != K_U16 && l.kind != K_U8) || passes < 1) return 1;
     const SegJob job = base_job(l, mask, src, sfs, dst, dfs, r, passes);
+    if (l.kind == K_U8) {
+        switch (r) {
+#define X(R) case R: return launch_vseg<R, true>(job, count, st);
+            VSZ_SEG_RADII(X)
+#undef X
+        }
+        return 1;
+    }
     switch (r) {
-#define X(R) case R: return launch_vseg<R>(job, count, st);
+#define X(R) case R: return launch_vseg<R, false>(job, count, st);
         VSZ_SEG_RADII(X)
 #undef X
     }
