@@ -1,6 +1,6 @@
 """Secondary measurements: the other BASELINE.json configs, device-resident, CUDA-event timed.
 Not the contract line (bench.py prints that); results go to stdout as JSON and, with --out, to a file.
-usage: python scripts/bench_extras.py [--frames N] [--reps R] [--out profiles/bench_extras_rXX.json]"""
+usage: python scripts/bench_extras.py [--frames N] [--reps R] [--only REGEX] [--out profiles/bench_extras_rXX.json]"""
 import argparse
 import json
 import sys
@@ -15,6 +15,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--frames", type=int, default=128)
 ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--out", default=None)
+ap.add_argument("--only", default=None, help="regex: run only the configurations whose name matches")
 args = ap.parse_args()
 
 vz.core.init([0])
@@ -48,7 +49,14 @@ def record(name, fmt, w, h, frames, algo_bytes_per_frame, ms):
     print(f"{name:58s} {fps:12.0f} fps  {ms * 1e3 / frames:8.2f} us/frame  {gbs:8.1f} GB/s  {100 * gbs / PEAK:5.1f}% of {PEAK:.0f}", file=sys.stderr)
 
 
+def skip(name):
+    import re
+    return args.only is not None and not re.search(args.only, name)
+
+
 def pixel_cfg(name, fmt, w, h, frames, make_filter, noise=True):
+    if skip(name):
+        return
     src, dst = vz.DeviceClip(fmt, w, h, frames), vz.DeviceClip(fmt, w, h, frames)
     if noise:
         src.fill_noise(1234)
@@ -60,6 +68,8 @@ def pixel_cfg(name, fmt, w, h, frames, make_filter, noise=True):
 
 def multi_cfg(name, fmt, w, h, frames, nin, run, prep=None):
     """pointwise filters with several input clips: algorithmic bytes = nin reads + 1 write per sample"""
+    if skip(name):
+        return
     clips = [vz.DeviceClip(fmt, w, h, frames) for _ in range(nin + 1)]
     for i, c in enumerate(clips[:nin]):
         c.fill_noise(1234 + i)
@@ -72,6 +82,8 @@ def multi_cfg(name, fmt, w, h, frames, nin, run, prep=None):
 
 
 def stats_cfg(name, fmt, w, h, frames, make_filter):
+    if skip(name):
+        return
     src = vz.DeviceClip(fmt, w, h, frames)
     src.fill_noise(1234)
     f = make_filter(src)
@@ -122,11 +134,14 @@ multi_cfg("C8 AdaptiveBinarize(clip, clip2, c=3) YUV420P8 (8f rank 3)", "YUV420P
 M = max(8, N // 2)
 stats_cfg("C4 PlaneMinMax(minthr=.1,maxthr=.1) GRAY16 4K", "GRAY16", 3840, 2160, M, lambda s: vz.PlaneMinMaxFilter(s.info(), minthr=0.1, maxthr=0.1))
 stats_cfg("C4 PlaneMinMax(minthr=.1,maxthr=.1) GRAYS 4K", "GRAYS", 3840, 2160, M, lambda s: vz.PlaneMinMaxFilter(s.info(), minthr=0.1, maxthr=0.1))
+stats_cfg("C4 PlaneMinMax(minthr=.1,maxthr=.1) GRAY8 4K", "GRAY8", 3840, 2160, M, lambda s: vz.PlaneMinMaxFilter(s.info(), minthr=0.1, maxthr=0.1))
 stats_cfg("C4 PlaneMinMax no threshold GRAY16 4K", "GRAY16", 3840, 2160, M, lambda s: vz.PlaneMinMaxFilter(s.info()))
 stats_cfg("C4 PlaneAverage(exclude=[0,32768]) GRAY16 4K", "GRAY16", 3840, 2160, M, lambda s: vz.PlaneAverageFilter(s.info(), exclude=[0, 32768]))
 stats_cfg("C4 PlaneAverage(exclude=[0,1]) GRAYS 4K", "GRAYS", 3840, 2160, M, lambda s: vz.PlaneAverageFilter(s.info(), exclude=[0, 1]))
 def both_stats_cfg(fmt, w, h, frames, mm_args, excl):
     """config 4 runs PlaneMinMax and PlaneAverage over the same plane: the two batch calls back to back (two HBM reads)"""
+    if skip(f"C4 both {fmt}"):
+        return
     src = vz.DeviceClip(fmt, w, h, frames)
     src.fill_noise(1234)
     mmf, avf = vz.PlaneMinMaxFilter(src.info(), **mm_args), vz.PlaneAverageFilter(src.info(), exclude=excl)
