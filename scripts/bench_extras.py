@@ -100,6 +100,7 @@ def stats_cfg(name, fmt, w, h, frames, make_filter):
 N = args.frames
 pixel_cfg("C1 BoxBlur(13,1,13,1) comptime path", "YUV420P16", 1920, 1080, N, lambda s: vz.BoxBlurFilter(s.info(), hradius=13, hpasses=1, vradius=13, vpasses=1))
 pixel_cfg("C2 BoxBlur(13,5,13,5) runtime path [headline]", "YUV420P16", 1920, 1080, N, lambda s: vz.BoxBlurFilter(s.info(), hradius=13, hpasses=5, vradius=13, vpasses=5))
+pixel_cfg("C1 on 8-bit frames (YUV420P8): the fused comptime kernel, byte rows widened on the way in", "YUV420P8", 1920, 1080, N, lambda s: vz.BoxBlurFilter(s.info(), hradius=13, hpasses=1, vradius=13, vpasses=1))
 pixel_cfg("C2 on 8-bit frames (YUV420P8): the same segment kernels behind a widen/narrow step", "YUV420P8", 1920, 1080, N, lambda s: vz.BoxBlurFilter(s.info(), hradius=13, hpasses=5, vradius=13, vpasses=5))
 pixel_cfg("C2 on constant frames (README BlankClip)", "YUV420P16", 1920, 1080, N, lambda s: vz.BoxBlurFilter(s.info(), hradius=13, hpasses=5, vradius=13, vpasses=5), noise=False)
 pixel_cfg("C3 Bilateral(sigmaS=2,sigmaR=2) all planes", "YUV420P16", 1920, 1080, N, lambda s: vz.BilateralFilter(s.info(), sigmaS=2, sigmaR=2, planes=[0, 1, 2]))

@@ -221,3 +221,18 @@ def test_runtime_8bit_on_segment_kernels(fmt, w, h):
         if 2 * max(args["hradius"], 1) >= (w >> (1 if fmt.startswith("YUV420") else 0)) or 2 * max(args["vradius"], 1) >= (h >> (1 if fmt.startswith("YUV420") else 0)):
             continue
         assert_same_planes(run(clip, **args)["planes"], oa.boxblur(clip, **args)["planes"], f"{fmt} {w}x{h} {args}")
+
+
+# --------------------------------------------------------------------------- 8-bit clips on the fused comptime kernel
+@pytest.mark.parametrize(("fmt", "w", "h"), [("GRAY8", 1920, 1080), ("YUV420P8", 1920, 1080), ("GRAY8", 331, 203), ("YUV420P8", 642, 362),
+                                            ("GRAY8", 2048, 270), ("GRAY8", 64, 90), ("GRAY8", 61, 33), ("YUV444P8", 960, 540), ("GRAY8", 120, 77)])
+def test_comptime_8bit_on_fused_kernel(fmt, w, h):
+    """hradius == vradius, one pass each (boxblur_comptime.zig) on 8-bit clips: byte rows through the TMA ring, widened on the way
+    into the 16-bit column sums and narrowed on the way out; widths that are not multiples of 8 or 16, both column splits (4 and 8
+    columns per thread), the defaults (radius 1) and the largest comptime radius."""
+    clip = noise_clip(fmt, w, h, seed=3 * w + h)
+    sub = 1 if fmt.startswith("YUV420") else 0
+    for r in (1, 2, 5, 13, 22):
+        if 2 * r >= (w >> sub) or 2 * r >= (h >> sub):
+            continue
+        assert_same_planes(run(clip, hradius=r, vradius=r)["planes"], oa.boxblur(clip, hradius=r, vradius=r)["planes"], f"{fmt} {w}x{h} r={r}")

@@ -1219,9 +1219,9 @@ static int run_boxblur_t(const FrameLayout& l, const bool mask[3], const char* s
         return run_ct_float<T>(l, mask, src, sfs, tmp.p, l.frame_stride, dst, dfs, count, hr, st);
     } else {
         // comptime integer path: exact R101q column sums + rounded mean, then the SYM H pass
-        if constexpr (std::is_same<T, uint16_t>::value) {
+        if constexpr (std::is_same<T, uint16_t>::value || std::is_same<T, uint8_t>::value) {
             if (use_seg_kernels()) {  // one read, one write
-                const int rc = run_seg_ct_u16(l, mask, src, sfs, dst, dfs, count, hr, st);
+                const int rc = run_seg_ct(l, mask, src, sfs, dst, dfs, count, hr, st);
                 if (rc <= 0) return rc;
             }
         }

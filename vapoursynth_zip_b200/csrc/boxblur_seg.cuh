@@ -17,7 +17,8 @@
 //                  horizontal closed form on one (two) of them.
 //
 // The radius is a template parameter (1..22: every comptime radius); other radii, other sample types and planes wider
-// than 1920 / taller than 1080 keep the streaming kernels of boxblur_kernels.cu.
+// than 1920 / taller than 1080 keep the streaming kernels of boxblur_kernels.cu.  8-bit clips run the same kernels: bytes are widened
+// after the TMA load and narrowed before the store (template parameter U8).
 #pragma once
 
 #include <algorithm>

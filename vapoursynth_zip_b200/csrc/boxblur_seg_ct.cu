@@ -1,4 +1,6 @@
 // boxblur_seg_ct.cu — ctfused_kernel: the comptime path in one read and one write (see boxblur_seg.cuh for the design of the segment kernels).
+#include <type_traits>
+
 #include "boxblur_seg.cuh"
 
 namespace vsz {
@@ -8,20 +10,30 @@ namespace {
 // =========================================================================== comptime path, fused
 constexpr int CTF_WARPS = 8;
 
-template <int CPT> struct ColVec;
-template <> struct ColVec<8> { using T = uint4; };
-template <> struct ColVec<4> { using T = uint2; };
-template <int CPT>
-__device__ __forceinline__ void colvec_words(const typename ColVec<CPT>::T& v, uint32_t (&w)[CPT / 2]) {
-    if constexpr (CPT == 8) { w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w; }
-    else { w[0] = v.x; w[1] = v.y; }
+// CPT consecutive samples of a row as CPT / 2 packed 16-bit words; 8-bit rows are widened on the way in
+// (`PRMT`), so that everything after the load is the 16-bit code.
+template <int CPT, bool U8>
+__device__ __forceinline__ void load_cols(const void* p, uint32_t (&w)[CPT / 2]) {
+    if constexpr (!U8) {
+        if constexpr (CPT == 8) { const uint4 v = *reinterpret_cast<const uint4*>(p); w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w; }
+        else { const uint2 v = *reinterpret_cast<const uint2*>(p); w[0] = v.x; w[1] = v.y; }
+    } else {
+        if constexpr (CPT == 8) {
+            const uint2 v = *reinterpret_cast<const uint2*>(p);
+            w[0] = __byte_perm(v.x, 0u, 0x4140); w[1] = __byte_perm(v.x, 0u, 0x4342);
+            w[2] = __byte_perm(v.y, 0u, 0x4140); w[3] = __byte_perm(v.y, 0u, 0x4342);
+        } else {
+            const uint32_t v = *reinterpret_cast<const uint32_t*>(p);
+            w[0] = __byte_perm(v, 0u, 0x4140); w[1] = __byte_perm(v, 0u, 0x4342);
+        }
+    }
 }
 
-template <int R, int CPT>
+template <int R, int CPT, bool U8>
 __global__ void __launch_bounds__(CTF_WARPS * 32, 2) ctfused_kernel(const SegJob job) {
     using Gm = HGeom<R>;
-    using CV = typename ColVec<CPT>::T;
-    constexpr int CW = CPT / 2;
+    using CV = typename std::conditional<CPT == 8, uint4, uint2>::type;  // CPT 16-bit means
+    constexpr int CW = CPT / 2, BPS = U8 ? 1 : 2;
     extern __shared__ __align__(128) unsigned char seg_smem[];
     __shared__ uint64_t ring_bar;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -33,7 +45,7 @@ __global__ void __launch_bounds__(CTF_WARPS * 32, 2) ctfused_kernel(const SegJob
     const int sg = act ? sg0 : 0;
     const int w = pj.w, h = pj.h;
     const int y0 = local * pj.per_cta, y1 = min(y0 + pj.per_cta, h);
-    const uint32_t row_bytes = (uint32_t)((w * 2 + 15) & ~15);
+    const uint32_t row_bytes = (uint32_t)((w * BPS + 15) & ~15);
     unsigned char* ring = seg_smem;                                  // [2*GR][row_bytes]: rows entering (0..GR-1) and leaving (GR..) the window
     unsigned char* tmpb = seg_smem + (size_t)2 * GR * row_bytes;     // [GR][rowbuf]: rounded column means, then the finished rows
     const char* src = job.src + (size_t)blockIdx.x * job.src_fs + pj.src_off;
@@ -67,19 +79,17 @@ __global__ void __launch_bounds__(CTF_WARPS * 32, 2) ctfused_kernel(const SegJob
     if (vact) {
         constexpr int NB = 9;
         for (int k0 = 0; k0 <= 2 * R; k0 += NB) {
-            CV v[NB];
+            uint32_t v[NB][CW];
 #pragma unroll
             for (int u = 0; u < NB; ++u) {
                 const int k = min(k0 + u, 2 * R);
-                v[u] = *reinterpret_cast<const CV*>(src + (size_t)ct_tap_row(y0, k, R, h) * pj.src_pitch + (size_t)c0 * 2);
+                load_cols<CPT, U8>(src + (size_t)ct_tap_row(y0, k, R, h) * pj.src_pitch + (size_t)c0 * BPS, v[u]);
             }
 #pragma unroll
             for (int u = 0; u < NB; ++u) {
                 if (k0 + u <= 2 * R) {
-                    uint32_t ww[CW];
-                    colvec_words<CPT>(v[u], ww);
 #pragma unroll
-                    for (int m = 0; m < CW; ++m) { col[2 * m] = dp2a(ww[m], ADD_LO, col[2 * m]); col[2 * m + 1] += ww[m] >> 16; }
+                    for (int m = 0; m < CW; ++m) { col[2 * m] = dp2a(v[u][m], ADD_LO, col[2 * m]); col[2 * m + 1] += v[u][m] >> 16; }
                 }
             }
         }
@@ -103,8 +113,8 @@ __global__ void __launch_bounds__(CTF_WARPS * 32, 2) ctfused_kernel(const SegJob
                     else t = make_uint2(pack_lo(m[0], m[1]), pack_lo(m[2], m[3]));
                     *reinterpret_cast<CV*>(tmpb + (size_t)j * pj.rowbuf + (size_t)(Gm::PAD + c0) * 2) = t;
                     uint32_t a[CW], b[CW];
-                    colvec_words<CPT>(*reinterpret_cast<const CV*>(ring + (size_t)j * row_bytes + (size_t)c0 * 2), a);
-                    colvec_words<CPT>(*reinterpret_cast<const CV*>(ring + (size_t)(GR + j) * row_bytes + (size_t)c0 * 2), b);
+                    load_cols<CPT, U8>(ring + (size_t)j * row_bytes + (size_t)c0 * BPS, a);
+                    load_cols<CPT, U8>(ring + (size_t)(GR + j) * row_bytes + (size_t)c0 * BPS, b);
 #pragma unroll
                     for (int q = 0; q < CW; ++q) {
                         col[2 * q] = dp2a(b[q], SUB_LO, dp2a(a[q], ADD_LO, col[2 * q]));
@@ -130,7 +140,14 @@ __global__ void __launch_bounds__(CTF_WARPS * 32, 2) ctfused_kernel(const SegJob
                 if (y < y1) {
                     const unsigned char* from = tmpb + (size_t)(warp * RPW + s2) * pj.rowbuf + Gm::PAD * 2;
                     char* to = dst + (size_t)y * pj.dst_pitch;
-                    for (uint32_t off = lane * 16; off < row_bytes; off += 512) st_global_hint(to + off, *reinterpret_cast<const uint4*>(from + off), drop);
+                    if constexpr (!U8) {
+                        for (uint32_t off = lane * 16; off < row_bytes; off += 512) st_global_hint(to + off, *reinterpret_cast<const uint4*>(from + off), drop);
+                    } else {  // 16 bytes of 16-bit results -> 8 bytes of the 8-bit row
+                        for (uint32_t off = lane * 8; off < (uint32_t)((w + 7) & ~7); off += 256) {  // (the same extent of tmpb as the 16-bit copy)
+                            const uint4 t = *reinterpret_cast<const uint4*>(from + 2 * off);
+                            __stcs(reinterpret_cast<uint2*>(to + off), make_uint2(__byte_perm(t.x, t.y, 0x6420), __byte_perm(t.z, t.w, 0x6420)));
+                        }
+                    }
                 }
             }
         }
@@ -138,7 +155,7 @@ __global__ void __launch_bounds__(CTF_WARPS * 32, 2) ctfused_kernel(const SegJob
     }
 }
 
-template <int R>
+template <int R, bool U8>
 int launch_ctfused(const SegJob& whole, int count, cudaStream_t st) {
     using Gm = HGeom<R>;
     for (int k = 0; k < whole.nplanes; ++k)
@@ -148,7 +165,7 @@ int launch_ctfused(const SegJob& whole, int count, cudaStream_t st) {
         const int cpt = (w <= CTF_WARPS * 32 * 4) ? 4 : 8;
         const int S = (w + L - 1) / L, G = lanes_per_row(S), RPW = 32 / G, GR = CTF_WARPS * RPW;
         const int rowbuf = rowbuf_bytes(Gm::row_samples(S), G);
-        const size_t row_bytes = (size_t)((w * 2 + 15) & ~15);
+        const size_t row_bytes = (size_t)((w * (U8 ? 1 : 2) + 15) & ~15);
         const size_t smem = (size_t)2 * GR * row_bytes + (size_t)GR * rowbuf;
         // rows per band: the first 2r rows of a band are read twice, so bands are as tall as the batch allows while the launch
         // still has ~4 waves of CTAs (a whole plane per CTA for big batches, 2 groups per band for a lone frame)
@@ -164,19 +181,20 @@ int launch_ctfused(const SegJob& whole, int count, cudaStream_t st) {
             cta += (h + band - 1) / band;
         }
         job.ctas_per_frame = cta;
-        if (cpt == 4) return launch_frames(ctfused_kernel<R, 4>, job, count, CTF_WARPS * 32, smem, st);
-        return launch_frames(ctfused_kernel<R, 8>, job, count, CTF_WARPS * 32, smem, st);
+        if (cpt == 4) return launch_frames(ctfused_kernel<R, 4, U8>, job, count, CTF_WARPS * 32, smem, st);
+        return launch_frames(ctfused_kernel<R, 8, U8>, job, count, CTF_WARPS * 32, smem, st);
     });
 }
 
 }  // namespace
 
 // Entry points.  Return 0 = done, 1 = not applicable (the caller falls back to the streaming kernels), < 0 = error.
-int run_seg_ct_u16(const FrameLayout& l, const bool mask[3], const char* src, size_t sfs, char* dst, size_t dfs, int count, int r, cudaStream_t st) {
-    if (l.kind != K_U16 || src == dst) return 1;
+int run_seg_ct(const FrameLayout& l, const bool mask[3], const char* src, size_t sfs, char* dst, size_t dfs, int count, int r, cudaStream_t st) {
+    if ((l.kind != K_U16 && l.kind != K_U8) || src == dst) return 1;
     const SegJob job = base_job(l, mask, src, sfs, dst, dfs, r, 1);
+    const bool u8 = l.kind == K_U8;
     switch (r) {
-#define X(R) case R: return launch_ctfused<R>(job, count, st);
+#define X(R) case R: return u8 ? launch_ctfused<R, true>(job, count, st) : launch_ctfused<R, false>(job, count, st);
         VSZ_SEG_RADII(X)
 #undef X
     }

@@ -67,14 +67,14 @@ namespace vsz {
 int run_boxblur(const FrameLayout& l, const bool mask[3], const char* src, size_t src_fs, char* dst, size_t dst_fs, int count,
                 int hr, int hp, int vr, int vp, cudaStream_t st);
 
-// boxblur_seg_{h,v,ct}.cu: integer clips (runtime passes: 8- and 16-bit; comptime path: 16-bit), radius 1..22, planes up to 1920x1080.
+// boxblur_seg_{h,v,ct}.cu: 8- and 16-bit integer clips, radius 1..22, planes up to 1920x1080 (comptime path: up to 2048 wide).
 // 0 = done, 1 = not applicable (use the streaming kernels), < 0 = error
 int run_seg_h(const FrameLayout& l, const bool mask[3], const char* src, size_t src_fs, char* dst, size_t dst_fs, int count, int r,
               int passes, cudaStream_t st);
 int run_seg_v(const FrameLayout& l, const bool mask[3], const char* src, size_t src_fs, char* dst, size_t dst_fs, int count, int r,
               int passes, cudaStream_t st);
-int run_seg_ct_u16(const FrameLayout& l, const bool mask[3], const char* src, size_t src_fs, char* dst, size_t dst_fs, int count, int r,
-                   cudaStream_t st);
+int run_seg_ct(const FrameLayout& l, const bool mask[3], const char* src, size_t src_fs, char* dst, size_t dst_fs, int count, int r,
+               cudaStream_t st);
 
 // boxblur_ctf.cu: comptime float path (f16/f32), streaming accumulators; tmp = scratch clip with the layout's frame stride
 int run_ctf_stream(const FrameLayout& l, const bool mask[3], const char* src, size_t src_fs, char* tmp, size_t tmp_fs, char* dst, size_t dst_fs,
