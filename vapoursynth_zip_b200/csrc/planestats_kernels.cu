@@ -37,9 +37,11 @@ struct Partial {
 };
 
 // Coarse-bin brackets guessed from a row sample (threshold fast path) and the "already resolved" flag.
-struct Bracket { unsigned int l_min, u_min, l_max, u_max; unsigned int done; unsigned int pad[3]; };  // [l, u) in bins
+// Both brackets are 2^kbits - 1 bins wide and start at bin 1 or above (see minmax_bracket_kernel).
+struct Bracket { unsigned int l_min, u_min, l_max, u_max; unsigned int done; unsigned int kbits; unsigned int pad[2]; };  // [l, u) in bins
 static constexpr int SBINS = 4096;   // bins of the sample histogram
-static constexpr int FINE_W = 768;   // widest bracket the single-read kernel can histogram
+static constexpr int FINE_KMAX = 10; // widest bracket the single-read kernel can histogram: 2^10 - 1 bins
+static constexpr int FINE_W = 1 << FINE_KMAX;
 
 struct StatsPlane {
     size_t a_off, b_off;
@@ -709,21 +711,31 @@ __global__ void __launch_bounds__(NT) hist_sample_kernel(const StatsJob j) {
     __syncthreads();
     if (threadIdx.x != 0) return;
     const int nsb = (int)((hist_size + (1u << sshift) - 1u) >> sshift);
-    auto to_bins = [&](int lo_sb, int hi_sb, unsigned int& l, unsigned int& u) {
+    // The full-read kernel wants both brackets 2^k - 1 bins wide with one k, and bin l - 1 >= 0 below each of them:
+    // the sampled ranges are widened to the next such width around their middle (a range wider than 2^FINE_KMAX - 1
+    // keeps its middle; a range that starts at bin 0 loses bin 0 - the exactness check of the full-read kernel
+    // resolves a rank that falls into that single bin, and sends everything else it cannot prove to the exact path).
+    auto sampled = [&](int lo_sb, int hi_sb, unsigned int& l, unsigned int& u) {
         if (lo_sb < 0) lo_sb = 0;
         if (hi_sb < 0) hi_sb = nsb - 1;
         l = (unsigned)lo_sb << sshift;
         u = min((unsigned)(hi_sb + 1) << sshift, hist_size);
-        if (u - l > (unsigned)FINE_W) {  // sparse codes: keep the middle, the exactness check decides
-            const unsigned int mid = l + (u - l) / 2u;
-            l = max(l, mid - FINE_W / 2u);
-            u = l + FINE_W;
-        }
+    };
+    unsigned int l0, u0, l1, u1;
+    sampled(s_res[0], s_res[1], l0, u0);
+    sampled(s_res[2], s_res[3], l1, u1);
+    unsigned int kbits = 1u;
+    while (kbits < (unsigned)FINE_KMAX && (1u << kbits) - 1u < max(u0 - l0, u1 - l1)) ++kbits;
+    const int width = (1 << kbits) - 1;
+    auto place = [&](unsigned int l, unsigned int u, unsigned int& lo, unsigned int& hi) {
+        int start = (int)l - (width - (int)(u - l)) / 2;   // needed range in the middle of the window (negative slack: its middle)
+        start = max(1, min(start, 65536 - width));
+        lo = (unsigned)start; hi = (unsigned)(start + width);
     };
     Bracket br;
-    to_bins(s_res[0], s_res[1], br.l_min, br.u_min);
-    to_bins(s_res[2], s_res[3], br.l_max, br.u_max);
-    br.done = 0u; br.pad[0] = br.pad[1] = br.pad[2] = 0u;
+    place(l0, u0, br.l_min, br.u_min);
+    place(l1, u1, br.l_max, br.u_max);
+    br.done = 0u; br.kbits = kbits; br.pad[0] = br.pad[1] = 0u;
     j.brackets[fp] = br;
 }
 
@@ -743,17 +755,14 @@ template <typename T> __device__ __forceinline__ void pack_bins(const uint4& v, 
     }
 }
 
-// "count samples whose bin is >= t" as packed arithmetic: min(max(x, A), B) - C is 1 in each 16-bit half whose
-// bin is >= t and 0 otherwise (A = t-1, B = t, C = t-1; t = 0 and t = 65536 degenerate to constants).
-struct PackedThr { unsigned int A, B, C; };
-__device__ __forceinline__ PackedThr packed_thr(unsigned int t) {
-    unsigned int a, b, c;
-    if (t == 0u) { a = b = 1u; c = 0u; }
-    else if (t >= 65536u) { a = b = 0u; c = 0u; }
-    else { a = t - 1u; b = t; c = t - 1u; }
-    return PackedThr{a * 0x10001u, b * 0x10001u, c * 0x10001u};
-}
-
+// Per bracket [l, u) with u - l = 2^k - 1 and A = l - 1:  h = min(max(x, A) - A, 2^k)  (VIMNMX.U16x2 + VIADDMNMX.U16x2, two
+// samples per instruction) is 0 below the bracket, 2^k at or above u and x - A in 1 .. 2^k - 1 inside.  So
+//   - a word holds a sample inside a bracket iff the OR of its two h values has one of the low k bits set (one LOP3 with a
+//     predicate result per word), and
+//   - the sum of h over everything a lane has visited (IDP.2A) is 2^k * (samples >= u) + sum(x - A) over its inside samples;
+//     the lane visits those one by one anyway (the fine histograms), subtracts their part and has the exact count.
+// Words with an inside sample go to a LANE-PRIVATE queue in shared memory (a predicated store and a predicated add: no ballot, no
+// prefix, no __syncwarp); when a lane has 16 waiting the warp drains, every lane its own words.
 // TRACK = false: every bin is valid (full-depth integer or float clip) and both ranks are > 0, so the exact
 // min/max tracking drops out of the per-sample work.  With TRACK the packed min/max give the answers for zero
 // ranks and detect samples above the format's peak (such planes are left to the exact two-pass kernels).
@@ -782,8 +791,14 @@ __global__ void __launch_bounds__(NT) minmax_bracket_kernel(const StatsJob j) {
         for (int e = 0; e < AVG; ++e) found |= (f == xf[e]);
         if (found) fexcluded += 1u; else fsum += (double)f;
     };
+    // lane-private queue of QCAP words, looked at after every step of G vectors (after every vector where a step could overflow it:
+    // 8-bit clips) and drained when some lane could not take another such portion
+    constexpr int QCAP = 32;
+    constexpr bool PER_VEC = G * NW > QCAP / 2;
+    constexpr int QDRAIN = QCAP - (PER_VEC ? NW : G * NW) + 1;
+    static_assert(QDRAIN >= 1 && NW <= QCAP, "queue too small");
     __shared__ unsigned int s_fine[2][FINE_W];
-    __shared__ uint4 s_q[NT / 32][G * 32];  // per warp: the vectors of one step that hold a sample inside a bracket
+    __shared__ unsigned int s_q[NT / 32][QCAP][32];  // [warp][entry][lane]: a lane only ever touches bank `lane`
     // own plane map: in large batches this kernel uses fewer, longer-running CTAs than the other reductions
     int k = j.nplanes - 1;
     while (k > 0 && (int)blockIdx.x < j.pl[k].b_cta_begin) --k;
@@ -800,39 +815,37 @@ __global__ void __launch_bounds__(NT) minmax_bracket_kernel(const StatsJob j) {
     __syncthreads();
     const unsigned int hist_size = j.hist_size;
     const unsigned int l_min = br.l_min, u_min = br.u_min, l_max = br.l_max, u_max = br.u_max;  // [l, u) in bins
-    const unsigned int w_min = u_min - l_min, w_max = u_max - l_max;
-    const PackedThr t0 = packed_thr(l_min), t1 = packed_thr(u_min), t2 = packed_thr(l_max), t3 = packed_thr(u_max);
-    const unsigned int k01 = t1.C - t0.C, k23 = t3.C - t2.C;
+    const unsigned int kbits = br.kbits, w_min = u_min - l_min, w_max = u_max - l_max;           // both 2^kbits - 1
+    const unsigned int a_min = l_min - 1u, a_max = l_max - 1u;
+    const unsigned int pkA0 = a_min * 0x10001u, pkN0 = ((65536u - a_min) & 0xffffu) * 0x10001u;
+    const unsigned int pkA1 = a_max * 0x10001u, pkN1 = ((65536u - a_max) & 0xffffu) * 0x10001u;
+    const unsigned int pkW = (1u << kbits) * 0x10001u, pk_low = ((1u << kbits) - 1u) * 0x10001u;
 
     Partial acc = empty_partial();
-    unsigned int ge_lmin = 0, ge_umax = 0, idiff32 = 0;    // exact counts of samples with bin >= l_min / >= u_max
-    // Sums of the clamp results over both halves of every visited word (IDP.2A): a word adds 2*C + (samples >= t), so the count
-    // is the sum minus 2*C per word; nwords counts the words of the current group of rows.
-    unsigned int sum_m0 = 0, sum_m3 = 0, nwords = 0;
-    const unsigned int c0h = t0.C & 0xffffu, c3h = t3.C & 0xffffu;
+    unsigned int ge_lmin = 0, ge_umax = 0, idiff32 = 0;    // scalar row tails: samples with bin >= l_min / >= u_max
+    unsigned int sum_h0 = 0, sum_h1 = 0;                   // sums of h over both halves of the words of one group of rows
+    unsigned long long tot_h0 = 0ull, tot_h1 = 0ull;       // ... of the lane's whole share
+    unsigned long long in_h0 = 0ull, in_h1 = 0ull;         // sum(x - A) over the inside samples this lane drained
+    unsigned int in_n0 = 0u;                               // how many were inside the min bracket
     unsigned int pk_min = 0xffffffffu, pk_max = 0u;
+    const int lane = threadIdx.x & 31;
+    unsigned int* myq = &s_q[threadIdx.x >> 5][0][lane];   // entry e at myq[e * 32]
+    unsigned int qn = 0u;                                   // words waiting in this lane's queue
 
     auto fine_add = [&](unsigned int bin, unsigned int n) {
         if (bin - l_min < w_min) atomicAdd(&s_fine[0][bin - l_min], n);
         if (bin - l_max < w_max) atomicAdd(&s_fine[1][bin - l_max], n);
     };
-    auto visit_vec = [&](const uint4& av, const uint4& bv) -> bool {  // true: some sample lies inside a bracket
+    auto visit_vec = [&](const uint4& av, const uint4& bv) {
         unsigned int w[NW];
         pack_bins<T>(av, w);
-        // inside-a-bracket test for the whole vector: per word (m0 - m1 + k01) + (m2 - m3 + k23) is 1 per half inside the min / max
-        // bracket (as one 32-bit number: i_lo + 65536 * i_hi, no matter how the halves of the partial sums carry), so the vector
-        // holds such a sample iff sum(m0 + m2) + NW * (k01 + k23) != sum(m1 + m3)   (mod 2^32; the true difference is < 2^19)
-        unsigned int in_a = (unsigned)NW * (k01 + k23), in_b = 0u;
 #pragma unroll
         for (int q = 0; q < NW; ++q) {
-            const unsigned int m0 = __vminu2(__vmaxu2(w[q], t0.A), t0.B);
-            const unsigned int m1 = __vminu2(__vmaxu2(w[q], t1.A), t1.B);
-            const unsigned int m2 = __vminu2(__vmaxu2(w[q], t2.A), t2.B);
-            const unsigned int m3 = __vminu2(__vmaxu2(w[q], t3.A), t3.B);
-            sum_m0 = __dp2a_lo(m0, 0x0101u, sum_m0);
-            sum_m3 = __dp2a_lo(m3, 0x0101u, sum_m3);
-            in_a += m0 + m2;
-            in_b += m1 + m3;
+            const unsigned int h0 = __viaddmin_u16x2(__vmaxu2(w[q], pkA0), pkN0, pkW);
+            const unsigned int h1 = __viaddmin_u16x2(__vmaxu2(w[q], pkA1), pkN1, pkW);
+            sum_h0 = __dp2a_lo(h0, 0x0101u, sum_h0);
+            sum_h1 = __dp2a_lo(h1, 0x0101u, sum_h1);
+            if (((h0 | h1) & pk_low) != 0u) { myq[qn * 32u] = w[q]; qn += 1u; }  // (packed bins: the drain needs no conversion)
             if constexpr (TRACK) { pk_min = __vminu2(pk_min, w[q]); pk_max = __vmaxu2(pk_max, w[q]); }
             if constexpr (AVG >= 0 && !FAVG) {
                 s32 = __dp2a_lo(w[q], 0x0101u, s32);
@@ -840,7 +853,6 @@ __global__ void __launch_bounds__(NT) minmax_bracket_kernel(const StatsJob j) {
                 for (int e = 0; e < AVG; ++e) pk_ne[e] += __vminu2(w[q] ^ ee[e], 0x10001u);
             }
         }
-        nwords += (unsigned)NW;
         if constexpr (AVG >= 0 && !FAVG) seen += (unsigned)V;
         if constexpr (FAVG) {
             const T* ae = reinterpret_cast<const T*>(&av);
@@ -853,7 +865,23 @@ __global__ void __launch_bounds__(NT) minmax_bracket_kernel(const StatsJob j) {
 #pragma unroll
             for (int i = 0; i < V; ++i) acc.fdiff += abs_diff<T>(ae[i], be[i], idiff32);
         }
-        return in_a != in_b;
+    };
+    // every lane walks its own queued words: the fine histogram(s) each half belongs to, and the inside samples' share of the h sums
+    auto drain = [&]() {
+        const unsigned int most = __reduce_max_sync(0xffffffffu, qn);
+        for (unsigned int e = 0; e < most; ++e) {
+            if (e < qn) {
+                const unsigned int w = myq[e * 32u];
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    const unsigned int bin = half ? (w >> 16) : (w & 0xffffu);
+                    const unsigned int d0 = bin - l_min, d1 = bin - l_max;
+                    if (d0 < w_min) { atomicAdd(&s_fine[0][d0], 1u); in_h0 += d0 + 1u; in_n0 += 1u; }
+                    if (d1 < w_max) { atomicAdd(&s_fine[1][d1], 1u); in_h1 += d1 + 1u; }
+                }
+            }
+        }
+        qn = 0u;
     };
     auto visit_one = [&](T at, T bt) {  // scalar row tails
         const unsigned int bin = bin_of<T>(at);
@@ -873,16 +901,10 @@ __global__ void __launch_bounds__(NT) minmax_bracket_kernel(const StatsJob j) {
 
     const int nvec = p.w / V;
     const int iters = (nvec + NT - 1) / NT;
-    const int lane = threadIdx.x & 31;
-    const unsigned int lt_mask = (1u << lane) - 1u;
-    uint4* myq = s_q[threadIdx.x >> 5];
     for (int y = y0; y < y1; y += G) {
         for (int it = 0; it < iters; ++it) {
             const int v = it * NT + (int)threadIdx.x;
             uint4 av[G], bv[G];
-            bool hit[G];
-#pragma unroll
-            for (int g = 0; g < G; ++g) hit[g] = false;
             if (v < nvec) {
 #pragma unroll
                 for (int g = 0; g < G; ++g) {
@@ -891,37 +913,13 @@ __global__ void __launch_bounds__(NT) minmax_bracket_kernel(const StatsJob j) {
                     if constexpr (HAS_B) bv[g] = __ldg(reinterpret_cast<const uint4*>(b + (size_t)yy * p.b_pitch) + v);
                     else bv[g] = av[g];
                 }
-#pragma unroll
-                for (int g = 0; g < G; ++g)
-                    if (y + g < y1) hit[g] = visit_vec(av[g], bv[g]);
             }
-            // queue the vectors with hits (slots from a ballot, no atomics), then the warp drains its own queue one
-            // sample per lane; nothing here needs a CTA barrier
-            unsigned int nq = 0u;
 #pragma unroll
             for (int g = 0; g < G; ++g) {
-                const unsigned int m = __ballot_sync(0xffffffffu, hit[g]);
-                if (hit[g]) myq[nq + __popc(m & lt_mask)] = av[g];
-                nq += __popc(m);
+                if (v < nvec && y + g < y1) visit_vec(av[g], bv[g]);
+                if constexpr (PER_VEC) { if (__any_sync(0xffffffffu, qn >= (unsigned)QDRAIN)) drain(); }
             }
-            __syncwarp();
-            nq *= (unsigned)V;
-            for (unsigned int i0 = 0; i0 < nq; i0 += 32) {
-                const unsigned int i = i0 + lane;
-                const bool ok = i < nq;
-                const unsigned int bin = ok ? bin_of<T>(reinterpret_cast<const T*>(myq)[i]) : 0xffffffffu;
-                const unsigned int d0 = bin - l_min, d1 = bin - l_max;
-                const bool v0 = ok && d0 < w_min, v1 = ok && d1 < w_max;
-                if (!__any_sync(0xffffffffu, v0 || v1)) continue;
-                if (__all_sync(0xffffffffu, bin == __shfl_sync(0xffffffffu, bin, 0))) {
-                    // flat picture area: one atomic instead of 32 serialised on the same address
-                    if (lane == 0) { if (v0) atomicAdd(&s_fine[0][d0], 32u); if (v1) atomicAdd(&s_fine[1][d1], 32u); }
-                } else {
-                    if (v0) atomicAdd(&s_fine[0][d0], 1u);
-                    if (v1) atomicAdd(&s_fine[1][d1], 1u);
-                }
-            }
-            __syncwarp();
+            if constexpr (!PER_VEC) { if (__any_sync(0xffffffffu, qn >= (unsigned)QDRAIN)) drain(); }
         }
         const int x = nvec * V + threadIdx.x;
         if (x < p.w) {
@@ -931,10 +929,9 @@ __global__ void __launch_bounds__(NT) minmax_bracket_kernel(const StatsJob j) {
                 visit_one(at, bt);
             }
         }
-        // a thread visits at most G * iters * NW <= 4 * 32 * 8 words per group of rows: the sums stay below 2^28
-        ge_lmin += sum_m0 - 2u * c0h * nwords;
-        ge_umax += sum_m3 - 2u * c3h * nwords;
-        sum_m0 = sum_m3 = nwords = 0u;
+        // a thread visits at most G * iters * NW <= 4 * 32 * 8 words per group of rows, each adds at most 2 * 2^FINE_KMAX: below 2^22
+        tot_h0 += sum_h0; tot_h1 += sum_h1;
+        sum_h0 = sum_h1 = 0u;
         acc.idiff += idiff32; idiff32 = 0;
         if constexpr (AVG >= 0 && !FAVG) {  // same bounds: <= 4 * 32 * 4 per packed half, <= 4 * 32 * 8 * 65535 in s32 per group of rows
             sum64 += s32; s32 = 0u;
@@ -957,12 +954,17 @@ __global__ void __launch_bounds__(NT) minmax_bracket_kernel(const StatsJob j) {
         acc.idiff = sum64 - removed;  // (no clipb here: the diff field is free)
         acc.excluded = excluded;
     }
+    drain();
+    // exact counts of the lane's vector samples: (sum of h - the inside samples' share) / 2^k are at or above u; those at or above
+    // l_min are the ones at or above u_min plus the inside ones
+    ge_lmin += (unsigned int)((tot_h0 - in_h0) >> kbits) + in_n0;
+    ge_umax += (unsigned int)((tot_h1 - in_h1) >> kbits);
     acc.isum = (unsigned long long)ge_lmin + ((unsigned long long)ge_umax << 32);
     acc.imin = min(pk_min & 0xffffu, pk_min >> 16);
     acc.imax = max(pk_max & 0xffffu, pk_max >> 16);
     __syncthreads();
-    unsigned int* gf = j.bfine + fp * 1536;
-    for (int i = threadIdx.x; i < 1536; i += NT) {
+    unsigned int* gf = j.bfine + fp * (2 * FINE_W);
+    for (int i = threadIdx.x; i < 2 * FINE_W; i += NT) {
         const unsigned int c = (&s_fine[0][0])[i];
         if (c) atomicAdd(&gf[i], c);
     }
@@ -1010,8 +1012,11 @@ __global__ void __launch_bounds__(NT) minmax_bracket_kernel(const StatsJob j) {
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
         const unsigned int before = outside + incl - sum;
+        const unsigned int inside_total = __shfl_sync(0xffffffffu, incl, 31);
         if ((unsigned long long)thr >= npx) { if (lane == 0) { s_okk[side] = 1; s_ans[side] = side == 0 ? hist_size - 1u : 0u; } }  // planeminmax.zig:44-48
         else if (thr == 0u) { if (lane == 0) s_okk[side] = TRACK ? 1 : 0; }  // first / last non-empty bin (already in s_ans)
+        else if (side == 0 && l_min == 1u && outside > thr) { if (lane == 0) { s_okk[0] = 1; s_ans[0] = 0u; } }  // "below the bracket" is bin 0 alone
+        else if (side == 1 && l_max == 1u && outside + inside_total <= thr) { if (lane == 0) { s_okk[1] = 1; s_ans[1] = 0u; } }  // ditto, scanning down
         else if (outside <= thr && before <= thr && before + sum > thr) {
             unsigned int c = before;
 #pragma unroll
@@ -1040,7 +1045,7 @@ __global__ void __launch_bounds__(NT) minmax_bracket_kernel(const StatsJob j) {
 static size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 size_t stats_scratch_bytes(int count, int np) {
     const size_t n = (size_t)count * np;
-    return align256(3 * n * 4) + align256(n * 256 * 4) + align256(n * SBINS * 4) + align256(n * 512 * 4) + align256(n * 1536 * 4) + align256(n * sizeof(Bracket)) +
+    return align256(3 * n * 4) + align256(n * 256 * 4) + align256(n * SBINS * 4) + align256(n * 512 * 4) + align256(n * 2 * FINE_W * 4) + align256(n * sizeof(Bracket)) +
            align256(n * MAX_CTAS_PER_PLANE * sizeof(Partial));
 }
 
@@ -1086,7 +1091,7 @@ static StatsJob make_job(const FrameLayout& l, const bool mask[3], const char* a
     j.coarse = (unsigned int*)sp; sp += align256(n * 256 * 4);
     j.ssample = (unsigned int*)sp; sp += align256(n * SBINS * 4);
     j.fine = (unsigned int*)sp; sp += align256(n * 512 * 4);
-    j.bfine = (unsigned int*)sp; sp += align256(n * 1536 * 4);
+    j.bfine = (unsigned int*)sp; sp += align256(n * 2 * FINE_W * 4);
     j.brackets = (Bracket*)sp; sp += align256(n * sizeof(Bracket));
     *zero_bytes = (size_t)(sp - (char*)scratch);
     j.partials = (Partial*)sp;
@@ -1118,7 +1123,7 @@ static int launch_minmax_t(StatsJob j, int count, bool no_thr, bool has_b, size_
             c.counters += (size_t)f0 * np; c.counters2 += (size_t)f0 * np;
             c.coarse += (size_t)f0 * np * 256; c.fine += (size_t)f0 * np * 512;
             c.out += (size_t)f0 * np;
-            c.counters3 += (size_t)f0 * np; c.ssample += (size_t)f0 * np * SBINS; c.bfine += (size_t)f0 * np * 1536;
+            c.counters3 += (size_t)f0 * np; c.ssample += (size_t)f0 * np * SBINS; c.bfine += (size_t)f0 * np * 2 * FINE_W;
             c.brackets += (size_t)f0 * np;
             const dim3 grid(j.ctas_per_frame, nf);
             // VSZIP_MINMAX_EXACT=1 skips the sampled fast path (used by the tests to exercise the exact kernels)
