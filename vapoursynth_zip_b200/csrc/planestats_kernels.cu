@@ -39,7 +39,12 @@ struct Partial {
 // Coarse-bin brackets guessed from a row sample (threshold fast path) and the "already resolved" flag.
 // Both brackets are 2^kbits - 1 bins wide and start at bin 1 or above (see minmax_bracket_kernel).
 struct Bracket { unsigned int l_min, u_min, l_max, u_max; unsigned int done; unsigned int kbits; unsigned int pad[2]; };  // [l, u) in bins
-static constexpr int SBINS = 4096;   // bins of the sample histogram
+// (2048 bins: the per-CTA flush and the last CTA's scan are a visible part of the sampling pass; 4096 bins cost 4 % of the whole
+// threshold path and bracket no tighter once the bracket is widened to 2^k - 1 bins)
+#ifndef VSZ_SBITS
+#define VSZ_SBITS 11
+#endif
+static constexpr int SBITS = VSZ_SBITS, SBINS = 1 << SBITS;   // bins of the sample histogram
 static constexpr int FINE_KMAX = 10; // widest bracket the single-read kernel can histogram: 2^10 - 1 bins
 static constexpr int FINE_W = 1 << FINE_KMAX;
 
@@ -592,7 +597,7 @@ __global__ void __launch_bounds__(NT) hist_fine_kernel(const StatsJob j, const i
 
 // --------------------------------------------------------------------------- threshold path, sampled fast path
 // The exact two-pass select above costs two full reads and one shared-memory atomic per sample.  The fast path
-// brackets, from a 1/16 sample of the plane's 128-byte lines (4096-bin histogram), the bin range that must hold each
+// brackets, from a 1/16 sample of the plane's 128-byte lines (2048-bin histogram), the bin range that must hold each
 // requested rank and then makes ONE full pass that (a) counts exactly how many samples lie below / above the
 // brackets with packed 16-bit min/max arithmetic (no atomics, content independent) and (b) builds exact histograms
 // of the (few) samples inside the brackets.  If the true rank lies inside its bracket - which the exact counts
@@ -1162,7 +1167,7 @@ int run_planeminmax(const FrameLayout& l, const bool mask[3], const char* a, siz
     int bits = 0;
     while ((1u << bits) < hist_size) ++bits;
     j.shift = bits > 8 ? bits - 8 : 0;
-    j.sshift = bits > 12 ? bits - 12 : 0;
+    j.sshift = bits > SBITS ? bits - SBITS : 0;
     for (int k = 0; k < j.nplanes; ++k) {
         const double total = (double)((uint32_t)j.pl[k].w * (uint32_t)j.pl[k].h);
         j.pl[k].tmin = (unsigned int)(total * (double)minthr);  // trunc (src/filters/planeminmax.zig:40-41)
@@ -1269,7 +1274,7 @@ int run_planestats_fused(const FrameLayout& l, const bool mask[3], const char* a
     int bits = 0;
     while ((1u << bits) < hist_size) ++bits;
     j.shift = bits > 8 ? bits - 8 : 0;
-    j.sshift = bits > 12 ? bits - 12 : 0;
+    j.sshift = bits > SBITS ? bits - SBITS : 0;
     for (int k = 0; k < j.nplanes; ++k) {
         const double total = (double)((uint32_t)j.pl[k].w * (uint32_t)j.pl[k].h);
         j.pl[k].tmin = (unsigned int)(total * (double)minthr);
