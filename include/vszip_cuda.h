@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define VSZIP_CUDA_ABI_VERSION 4  /* 2: + vszip_chain_*, vszip_limiter_*; 3: + vszip_limitfilter_*, vszip_adaptivebinarize_*, vszip_planestats_device; 4: + vszip_cuda_host_forget, vszip_cuda_host_registered_bytes, vszip_cuda_host_register_limit */
+#define VSZIP_CUDA_ABI_VERSION 5  /* 2: + vszip_chain_*, vszip_limiter_*; 3: + vszip_limitfilter_*, vszip_adaptivebinarize_*, vszip_planestats_device; 4: + vszip_cuda_host_forget, vszip_cuda_host_registered_bytes, vszip_cuda_host_register_limit; 5: + vszip_cuda_reserve */
 
 /* VapourSynth4.h values (VSColorFamily / VSSampleType) so the Zig glue can pass vi.format as is. */
 enum { VSZIP_CF_GRAY = 1, VSZIP_CF_RGB = 2, VSZIP_CF_YUV = 3 };
@@ -78,6 +78,13 @@ size_t vszip_cuda_host_registered_bytes(void);
 /* Sets the cap on page-locked application memory in bytes (0 = never register; buffers registered so far stay registered until
  * they are forgotten) and returns the previous cap. */
 size_t vszip_cuda_host_register_limit(size_t bytes);
+
+/* Optional, from a filter's create callback: allocates the pinned + device staging buffers of every request slot on every GPU
+ * for frames of this format (`buffers` of them per slot: 2 for one input clip + the output, 3 with a ref / second clip, 4 for
+ * LimitFilter with ref) so that the first getFrame calls do not pay for cudaHostAlloc / cudaMalloc.  Blocks until no request is
+ * in flight.  0 on success, -1 with vszip_cuda_last_error() otherwise.  Without it the buffers grow on first use (and on the
+ * first larger format), exactly as before. */
+int32_t vszip_cuda_reserve(const vszip_video_info* vi, int32_t buffers);
 
 /* ------------------------------------------------------------------ BoxBlur
  * replaces boxBlurCreate / BoxBlurCT.getFrame / BoxBlurRT.getFrame (src/vapoursynth/boxblur.zig:27-212)

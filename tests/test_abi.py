@@ -24,7 +24,7 @@ def test_header_symbols_are_exported_and_bound():
     for name in decl:
         assert hasattr(lib, name), f"{name} declared in vszip_cuda.h but not exported"
     assert decl == set(vz.ABI), f"python binding and header disagree: {decl ^ set(vz.ABI)}"
-    assert vz.load_library().vszip_cuda_abi_version() == 4
+    assert vz.load_library().vszip_cuda_abi_version() == 5
 
 
 def test_signatures_are_plain_c():

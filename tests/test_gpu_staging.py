@@ -128,3 +128,20 @@ def test_plane_that_only_starts_in_pinned_memory_is_staged():
     finally:
         lib.vszip_cuda_host_forget(None)
         rt.cudaHostUnregister(src.ctypes.data)
+
+
+def test_reserve_sizes_the_slots_up_front():
+    """vszip_cuda_reserve: the staging buffers of every slot exist before the first frame (no allocation on the request path); frames
+    of that format and of a larger one still come out right (the buffers grow as before)."""
+    small = noise_clip("YUV420P16", 320, 180, seed=5)
+    node = to_node(small)
+    vz.core.reserve(node._info(), buffers=3)
+    got = node.vszip.BoxBlur(hradius=3, vradius=3).get_frame(0)
+    assert_same_planes(got.planes, oa.boxblur(small, hradius=3, vradius=3)["planes"])
+    big = noise_clip("YUV444P16", 640, 362, seed=6)
+    got = to_node(big).vszip.BoxBlur(hradius=2, hpasses=2, vradius=2, vpasses=2).get_frame(0)
+    assert_same_planes(got.planes, oa.boxblur(big, hradius=2, hpasses=2, vradius=2, vpasses=2)["planes"])
+    with pytest.raises(vz.Error):
+        bad = node._info()
+        bad.width = 0
+        vz.core.reserve(bad)

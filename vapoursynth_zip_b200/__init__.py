@@ -106,6 +106,7 @@ ABI = {
     "vszip_cuda_host_forget": (None, [_P]),
     "vszip_cuda_host_registered_bytes": (C.c_size_t, []),
     "vszip_cuda_host_register_limit": (C.c_size_t, [C.c_size_t]),
+    "vszip_cuda_reserve": (C.c_int32, [C.POINTER(_VideoInfo), C.c_int32]),
     "vszip_boxblur_create": (_P, [C.POINTER(_VideoInfo), C.POINTER(_BoxBlurArgs)]),
     "vszip_boxblur_get_frame": (C.c_int, [_P, C.c_int32, C.POINTER(_Frame), C.POINTER(_Frame)]),
     "vszip_boxblur_device": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, _P]),
@@ -788,6 +789,11 @@ class _Core:
             raise Error(_last_error())
         self._ready = True
         return n
+
+    def reserve(self, info, buffers=2):
+        """vszip_cuda_reserve: allocate every request slot's staging buffers for frames of this format now (first-call latency)."""
+        self._ensure_init()
+        _check(load_library().vszip_cuda_reserve(C.byref(info), buffers))
 
     def shutdown(self):
         """vszip_cuda_shutdown: frees the per-GPU slots, streams and the host pin cache (filters and clips must be gone)."""

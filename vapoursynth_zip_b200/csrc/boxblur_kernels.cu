@@ -1177,7 +1177,7 @@ static int run_ct_float(const FrameLayout& l, const bool mask[3], const char* sr
     return 0;
 }
 
-// 16-bit integer clips take the segment kernels (boxblur_seg_kernels.cu) where they apply; VSZIP_BOXBLUR_LEGACY=1 keeps
+// 8- and 16-bit integer clips take the segment kernels (boxblur_seg_{h,v,ct}.cu) where they apply; VSZIP_BOXBLUR_LEGACY=1 keeps
 // every clip on the streaming kernels of this file (A/B timing, and the parity tests run both).
 static bool use_seg_kernels() {
     static const bool on = [] { const char* e = getenv("VSZIP_BOXBLUR_LEGACY"); return !(e && e[0] == '1'); }();

@@ -1,4 +1,4 @@
-// boxblur_seg.cuh — shared by boxblur_seg_{h,v,ct}.cu: sm_100a "segment" kernels for vszip.BoxBlur on 16-bit integer clips.
+// boxblur_seg.cuh — shared by boxblur_seg_{h,v,ct}.cu: sm_100a "segment" kernels for vszip.BoxBlur on 8- and 16-bit integer clips.
 //
 // Integer BoxBlur has a closed form per pass (boxblur_seg_core.h; src/filters/boxblur_runtime.zig:10-41), so a line
 // does not have to be walked by one thread.  Here a thread owns a segment of 60 consecutive samples of a line, keeps
@@ -16,7 +16,7 @@
 //                  shared-memory ring; the rounded means of 8 (16) rows go to shared memory and each warp then runs the
 //                  horizontal closed form on one (two) of them.
 //
-// The radius is a template parameter (1..22: every comptime radius); other radii, other sample types and planes wider
+// The radius is a template parameter (1..22: every comptime radius); other radii, float clips and planes wider
 // than 1920 / taller than 1080 keep the streaming kernels of boxblur_kernels.cu.  8-bit clips run the same kernels: bytes are widened
 // after the TMA load and narrowed before the store (template parameter U8).
 #pragma once

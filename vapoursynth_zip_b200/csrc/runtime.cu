@@ -449,6 +449,29 @@ size_t vszip_cuda_host_register_limit(size_t bytes) {
     return before;
 }
 
+// Sizes the staging buffers of every request slot of every GPU for frames of this format now, instead of on the first frames
+// that come through each slot (cudaHostAlloc + cudaMalloc of a frame: a first-call latency spike of milliseconds).
+int32_t vszip_cuda_reserve(const vszip_video_info* vi, int32_t buffers) {
+    if (!vi || vi->width <= 0 || vi->height <= 0 || vi->bytes_per_sample <= 0) { set_error("vszip_cuda_reserve: bad video info"); return -1; }
+    if (num_devices() == 0) { set_error("vszip_cuda_reserve: vszip_cuda_init has not been called"); return -1; }
+    const SampleKind kind = vi->bytes_per_sample == 1 ? K_U8 : (vi->bytes_per_sample == 2 ? K_U16 : K_F32);  // only the sample size matters here
+    const FrameLayout l = make_layout(*vi, kind);
+    const int nb = std::max(1, std::min(buffers, 4));
+    for (int i = 0; i < num_devices(); ++i) {
+        DeviceCtx* d = device_ctx(i);
+        size_t nslots;
+        { std::lock_guard<std::mutex> lk(d->mu); nslots = d->all.size(); }
+        std::vector<Slot*> held;
+        int rc = 0;
+        for (size_t k = 0; k < nslots; ++k) held.push_back(d->acquire());  // every slot once: none is in flight while it grows
+        for (Slot* s : held)
+            for (int which = 0; which < nb && rc == 0; ++which) rc = slot_reserve(d, s, which, l.frame_stride);
+        for (Slot* s : held) d->release(s);
+        if (rc) return -1;
+    }
+    return 0;
+}
+
 size_t vszip_cuda_host_registered_bytes(void) {
     std::lock_guard<std::mutex> lk(g_host_mu);
     return g_host_registered;
