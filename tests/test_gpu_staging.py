@@ -9,7 +9,7 @@ import torch
 
 import oracle_api as oa
 import vapoursynth_zip_b200 as vz
-from helpers import assert_same_planes, noise_clip
+from helpers import assert_same_planes, noise_clip, to_node
 
 pytestmark = pytest.mark.gpu
 
