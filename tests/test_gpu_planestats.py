@@ -200,6 +200,46 @@ def test_structured_planeminmax(kind):
             props_close(mm(clip, **args), oa.planeminmax(clip, **args))
 
 
+def _edge_content(kind, dtype, peak, w, h, rng):
+    """Planes whose requested ranks fall at the ends of the sample range, where the bracket windows of the single-read kernel
+    (2^k - 1 bins, never starting at bin 0) are clamped or lose bin 0."""
+    n = w * h
+    if kind == "mostly_zero":      # min rank in bin 0, max rank just above it
+        img = np.zeros(n, np.float64)
+        idx = rng.choice(n, n // 20, replace=False)
+        img[idx] = rng.integers(1, 6, idx.size)
+    elif kind == "all_zero":
+        img = np.zeros(n, np.float64)
+    elif kind == "mostly_peak":    # max rank in the top bin, min rank a few bins below it
+        img = np.full(n, peak, np.float64)
+        idx = rng.choice(n, n // 20, replace=False)
+        img[idx] = peak - rng.integers(1, 6, idx.size)
+    elif kind == "both_ends":      # a third at 0, a third at the peak, the rest spread out
+        img = rng.integers(0, int(peak) + 1, n).astype(np.float64)
+        img[rng.random(n) < 0.33] = 0
+        img[rng.random(n) < 0.33] = peak
+    elif kind == "low_codes":      # everything inside the first 40 codes: both windows are clamped at bin 1
+        img = rng.integers(0, 40, n).astype(np.float64)
+    else:
+        raise KeyError(kind)
+    img = img.reshape(h, w)
+    if np.issubdtype(dtype, np.floating):
+        return (img / peak).astype(dtype)
+    return img.astype(dtype)
+
+
+@pytest.mark.parametrize("kind", ["mostly_zero", "all_zero", "mostly_peak", "both_ends", "low_codes"])
+@pytest.mark.parametrize("fmt", ["GRAY8", "GRAY10", "GRAY16", "GRAYS"])
+def test_planeminmax_ranks_at_the_ends_of_the_range(fmt, kind):
+    rng = np.random.default_rng(5)
+    dtype, peak = {"GRAY8": (np.uint8, 255), "GRAY10": (np.uint16, 1023), "GRAY16": (np.uint16, 65535), "GRAYS": (np.float32, 65535)}[fmt]
+    for (w, h) in ((333, 207), (1283, 900)):   # sampled completely / by lines
+        clip = {"format": fmt, "planes": [_edge_content(kind, dtype, peak, w, h, rng)]}
+        for thr in ((0.1, 0.1), (0.001, 0.6), (0.7, 0.02), (0.04, 0.04)):
+            args = dict(minthr=thr[0], maxthr=thr[1])
+            props_close(mm(clip, **args), oa.planeminmax(clip, **args))
+
+
 @pytest.mark.parametrize("fmt", ["GRAY16", "GRAYS"])
 def test_full_size_config4(fmt):
     """BASELINE config 4: 3840x2160 GRAY16 / GRAYS, PlaneMinMax(minthr, maxthr) + PlaneAverage(exclude)."""
