@@ -780,9 +780,9 @@ __global__ void __launch_bounds__(NT) minmax_bracket_kernel(const StatsJob j) {
     constexpr bool FAVG = AVG >= 0 && El<T>::flt;  // float clips: per sample AVG compares against the exclude values and one f64 add
     constexpr int V = El<T>::PER16, NW = V / 2, G = HAS_B ? 2 : 4;
     constexpr int NEX = AVG > 0 ? AVG : 1;
-    unsigned int ee[NEX], pk_ne[NEX], differing[NEX];
+    unsigned int ee[NEX], differing[NEX];
 #pragma unroll
-    for (int e = 0; e < NEX; ++e) { ee[e] = AVG > 0 ? (unsigned)j.excl_i[e] * 0x10001u : 0u; pk_ne[e] = 0u; differing[e] = 0u; }
+    for (int e = 0; e < NEX; ++e) { ee[e] = AVG > 0 ? (unsigned)j.excl_i[e] * 0x10001u : 0u; differing[e] = 0u; }
     unsigned int s32 = 0u, seen = 0u;
     unsigned long long sum64 = 0ull;
     float xf[NEX];
@@ -855,7 +855,7 @@ __global__ void __launch_bounds__(NT) minmax_bracket_kernel(const StatsJob j) {
             if constexpr (AVG >= 0 && !FAVG) {
                 s32 = __dp2a_lo(w[q], 0x0101u, s32);
 #pragma unroll
-                for (int e = 0; e < AVG; ++e) pk_ne[e] += __vminu2(w[q] ^ ee[e], 0x10001u);
+                for (int e = 0; e < AVG; ++e) differing[e] = __dp2a_lo(__vminu2(w[q] ^ ee[e], 0x10001u), 0x0101u, differing[e]);  // + 1 per half that differs
             }
         }
         if constexpr (AVG >= 0 && !FAVG) seen += (unsigned)V;
@@ -938,10 +938,8 @@ __global__ void __launch_bounds__(NT) minmax_bracket_kernel(const StatsJob j) {
         tot_h0 += sum_h0; tot_h1 += sum_h1;
         sum_h0 = sum_h1 = 0u;
         acc.idiff += idiff32; idiff32 = 0;
-        if constexpr (AVG >= 0 && !FAVG) {  // same bounds: <= 4 * 32 * 4 per packed half, <= 4 * 32 * 8 * 65535 in s32 per group of rows
+        if constexpr (AVG >= 0 && !FAVG) {  // same bound: <= 4 * 32 * 8 * 65535 in s32 per group of rows
             sum64 += s32; s32 = 0u;
-#pragma unroll
-            for (int e = 0; e < AVG; ++e) { differing[e] += (pk_ne[e] & 0xffffu) + (pk_ne[e] >> 16); pk_ne[e] = 0u; }
         }
     }
     if constexpr (FAVG) {
