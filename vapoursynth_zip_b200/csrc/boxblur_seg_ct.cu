@@ -29,8 +29,8 @@ __device__ __forceinline__ void load_cols(const void* p, uint32_t (&w)[CPT / 2])
     }
 }
 
-template <int R, int CPT, bool U8>
-__global__ void __launch_bounds__(CTF_WARPS * 32, 2) ctfused_kernel(const SegJob job) {
+template <int R, int CPT, bool U8, int NWARPS = CTF_WARPS>
+__global__ void __launch_bounds__(NWARPS * 32, NWARPS == 4 ? 4 : 2) ctfused_kernel(const SegJob job) {
     using Gm = HGeom<R>;
     using CV = typename std::conditional<CPT == 8, uint4, uint2>::type;  // CPT 16-bit means
     constexpr int CW = CPT / 2, BPS = U8 ? 1 : 2;
@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(CTF_WARPS * 32, 2) ctfused_kernel(const SegJob
     int local;
     const SegPlane& pj = seg_plane(job, blockIdx.y, local);
     const int G = pj.G, RPW = 32 / G, sub = lane / G, sg0 = lane % G;
-    const int GR = CTF_WARPS * RPW;  // rows per group
+    const int GR = NWARPS * RPW;  // rows per group
     const bool act = sg0 < pj.S;
     const int sg = act ? sg0 : 0;
     const int w = pj.w, h = pj.h;
@@ -162,8 +162,12 @@ int launch_ctfused(const SegJob& whole, int count, cudaStream_t st) {
         if (whole.pl[k].w > CTF_WARPS * 32 * 8 || (whole.pl[k].w + L - 1) / L > 32) return 1;
     return for_each_shape(whole, [&](SegJob job) {
         const int w = job.pl[0].w, h = job.pl[0].h;
-        const int cpt = (w <= CTF_WARPS * 32 * 4) ? 4 : 8;
-        const int S = (w + L - 1) / L, G = lanes_per_row(S), RPW = 32 / G, GR = CTF_WARPS * RPW;
+        // planes up to 1024 wide (1080p chroma): 4 warps x 8 columns per thread and 4 CTAs per SM instead of 8 warps x 4 columns and 2 -
+        // the two CTA-wide barriers per group of rows cost less across 4 warps, and 4 CTAs interleave their V and H phases
+        // (1080p YUV420P16, r = 13: 2.96 -> 2.74 us per frame)
+        const bool narrow = w <= 4 * 32 * 8;
+        const int nwarps = narrow ? 4 : CTF_WARPS;
+        const int S = (w + L - 1) / L, G = lanes_per_row(S), RPW = 32 / G, GR = nwarps * RPW;
         const int rowbuf = rowbuf_bytes(Gm::row_samples(S), G);
         const size_t row_bytes = (size_t)((w * (U8 ? 1 : 2) + 15) & ~15);
         const size_t smem = (size_t)2 * GR * row_bytes + (size_t)GR * rowbuf;
@@ -181,7 +185,7 @@ int launch_ctfused(const SegJob& whole, int count, cudaStream_t st) {
             cta += (h + band - 1) / band;
         }
         job.ctas_per_frame = cta;
-        if (cpt == 4) return launch_frames(ctfused_kernel<R, 4, U8>, job, count, CTF_WARPS * 32, smem, st);
+        if (narrow) return launch_frames(ctfused_kernel<R, 8, U8, 4>, job, count, 4 * 32, smem, st);
         return launch_frames(ctfused_kernel<R, 8, U8>, job, count, CTF_WARPS * 32, smem, st);
     });
 }
