@@ -236,3 +236,13 @@ def test_comptime_8bit_on_fused_kernel(fmt, w, h):
         if 2 * r >= (w >> sub) or 2 * r >= (h >> sub):
             continue
         assert_same_planes(run(clip, hradius=r, vradius=r)["planes"], oa.boxblur(clip, hradius=r, vradius=r)["planes"], f"{fmt} {w}x{h} r={r}")
+
+
+@pytest.mark.parametrize("w", [959, 960, 961, 1000, 1024, 1025])
+@pytest.mark.parametrize("fmt", ["GRAY16", "GRAY8"])
+def test_comptime_widths_around_the_cta_shape_switch(fmt, w):
+    """The fused comptime kernel runs 4-warp CTAs up to 960 columns and 8-warp CTAs above (both with 8 columns per thread); 961..1024
+    still fits 4 warps' columns but not their rows-per-group rule."""
+    clip = noise_clip(fmt, w, 75, seed=w)
+    for r in (2, 13):
+        assert_same_planes(run(clip, hradius=r, vradius=r)["planes"], oa.boxblur(clip, hradius=r, vradius=r)["planes"], f"{fmt} w={w} r={r}")

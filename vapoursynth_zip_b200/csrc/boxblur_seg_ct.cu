@@ -162,10 +162,10 @@ int launch_ctfused(const SegJob& whole, int count, cudaStream_t st) {
         if (whole.pl[k].w > CTF_WARPS * 32 * 8 || (whole.pl[k].w + L - 1) / L > 32) return 1;
     return for_each_shape(whole, [&](SegJob job) {
         const int w = job.pl[0].w, h = job.pl[0].h;
-        // planes up to 1024 wide (1080p chroma): 4 warps x 8 columns per thread and 4 CTAs per SM instead of 8 warps x 4 columns and 2 -
+        // planes up to 960 wide (1080p chroma): 4 warps x 8 columns per thread and 4 CTAs per SM instead of 8 warps x 4 columns and 2 -
         // the two CTA-wide barriers per group of rows cost less across 4 warps, and 4 CTAs interleave their V and H phases
         // (1080p YUV420P16, r = 13: 2.96 -> 2.74 us per frame)
-        const bool narrow = w <= 4 * 32 * 8;
+        const bool narrow = w <= 16 * L;   // at most 16 lanes per row: 2 or 4 rows per warp, so a group is still a multiple of 8 rows
         const int nwarps = narrow ? 4 : CTF_WARPS;
         const int S = (w + L - 1) / L, G = lanes_per_row(S), RPW = 32 / G, GR = nwarps * RPW;
         const int rowbuf = rowbuf_bytes(Gm::row_samples(S), G);
