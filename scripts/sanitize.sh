@@ -7,7 +7,7 @@ mkdir -p $O
 CS=/usr/local/cuda/bin/compute-sanitizer
 # one representative, small case per kernel family (segment/TMA BoxBlur, ring BoxBlur, comptime float, Bilateral smem/compute/PBFIC,
 # reductions incl. the sampled bracket path, pointwise, fused chain, host pin cache)
-SEL="test_noise_bit_exact or test_small_sigma_r_is_bit_exact_16bit or test_joint_ref or test_pbfic_joint_and_tiny_planes or test_minmax_and_average_from_one_read or test_structured_planeminmax or test_fused_chain_partial_planes or test_fused_chain_adaptive_binarize or test_pageable_buffers or test_comptime_float_small_case_for_the_sanitizer or test_full_size_config1"
+SEL="test_noise_bit_exact or test_small_sigma_r_is_bit_exact_16bit or test_joint_ref or test_pbfic_joint_and_tiny_planes or test_minmax_and_average_from_one_read or test_structured_planeminmax or test_fused_chain_partial_planes or test_fused_chain_adaptive_binarize or test_pageable_buffers or test_comptime_float_small_case_for_the_sanitizer or test_comptime_widths_around_the_cta_shape_switch or test_planeminmax_ranks_at_the_ends_of_the_range or test_full_size_config1"
 for tool in memcheck racecheck synccheck; do
   extra=""
   [ $tool = memcheck ] && extra="--leak-check full"
