@@ -38,6 +38,13 @@ namespace vsz {
 namespace {
 
 constexpr int kThreads = 128;
+#ifndef VSZ_CTF_HROWS
+#define VSZ_CTF_HROWS 64
+#endif
+// rows (= row threads) per CTA of the H kernel.  64 rows and 2 TMA stages need 44 KB of shared memory (f32, r = 13): 5 CTAs of 3 warps per SM
+// instead of 2 CTAs of 5 warps with 128 rows and 3 stages (4K YUV444PS r = 13: 84.3 -> 81.4 us per frame, r = 22: 171 -> 146, 1080p GRAYS 7.4 -> 7.0;
+// 32 rows: 101 us - one store warp per 32 row threads is too many)
+constexpr int kHRows = VSZ_CTF_HROWS;
 
 struct CtfPlane {
     size_t src_off, dst_off;
@@ -248,7 +255,7 @@ __device__ __forceinline__ void tma_load_3d(void* sdst, const CUtensorMap* map, 
 // 16-byte vectors - enough for the worst phase, and an ODD number so that the 8 threads of a quarter-warp, one row each, cover
 // all 32 banks with their 16-byte accesses.
 #ifndef VSZ_CTF_STAGES
-#define VSZ_CTF_STAGES 3
+#define VSZ_CTF_STAGES 2
 #endif
 template <typename T, int R> struct HTile {
     static constexpr int K = 2 * R + 1;
@@ -266,8 +273,8 @@ template <typename T, int R> struct HTile {
     static constexpr int RV = RCH * 8;                           // ring vectors per row
     static constexpr int OROW_BYTES = (RV + 1) * 16;
     static constexpr int STAGES = VSZ_CTF_STAGES;
-    static constexpr int TILE_BYTES = kThreads * ROW_BYTES;
-    static constexpr int RING_BYTES = kThreads * OROW_BYTES;
+    static constexpr int TILE_BYTES = kHRows * ROW_BYTES;
+    static constexpr int RING_BYTES = kHRows * OROW_BYTES;
     static constexpr int SMEM = STAGES * TILE_BYTES + RING_BYTES;
 };
 
@@ -368,7 +375,7 @@ __device__ __forceinline__ void ring_put(const float (&xv)[TS], float (&carry)[V
 }
 
 // named barriers (bar 0 is __syncthreads): the full / empty hand-over of the output ring between the row threads and the store warp
-constexpr int kStoreThreads = 32, kHThreads = kThreads + kStoreThreads;
+constexpr int kStoreThreads = 32, kHThreads = kHRows + kStoreThreads;
 enum { BAR_FULL = 2, BAR_EMPTY = 4 };
 __device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
@@ -388,7 +395,7 @@ __global__ void __launch_bounds__(kHThreads) ctf_h_kernel(const CtfJob job, cons
     const int plane = (int)(&pj - job.pl);
     const int rb = local % pj.cross_blocks, sg = local / pj.cross_blocks;
     const int tid = threadIdx.x, lane = tid & 31;
-    const int row0 = rb * kThreads;
+    const int row0 = rb * kHRows;
     const int w = pj.w, f = blockIdx.x;
     const int xs = R + sg * pj.seg_len, xe = min(xs + pj.seg_len, w - R);  // interior outputs of this piece
     const int ntiles = (xe - xs + TS - 1) / TS;                            // tile i: inputs xs+r+i*TS.., outputs xs+i*TS..
@@ -397,7 +404,7 @@ __global__ void __launch_bounds__(kHThreads) ctf_h_kernel(const CtfJob job, cons
 
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < G::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&consumed[s], kThreads); }
+        for (int s = 0; s < G::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&consumed[s], kHRows); }
         fence_mbar_init();
     }
     __syncthreads();
@@ -410,9 +417,9 @@ __global__ void __launch_bounds__(kHThreads) ctf_h_kernel(const CtfJob job, cons
 
     // the ring's sample 0 is plane sample xbase: the 128-byte line that holds the piece's first output
     const int xbase = xs & ~(G::CH - 1);
-    if (tid >= kThreads) {  // ---- store warp
+    if (tid >= kHRows) {  // ---- store warp
         char* dplane = job.dst + (size_t)f * job.dst_fs + pj.dst_off + (size_t)row0 * pj.dst_pitch;
-        const int rows = min(kThreads, pj.h - row0);
+        const int rows = min(kHRows, pj.h - row0);
         const uint32_t dp = (uint32_t)pj.dst_pitch;
         const int sub = lane >> 3, vq = lane & 7;
         int chunk = 0;  // next chunk to store
@@ -564,7 +571,7 @@ int launch_ctf(const FrameLayout& l, const bool mask[3], const char* src, size_t
         a.src_pitch = a.dst_pitch = b.src_pitch = b.dst_pitch = l.pl[p].pitch;
         a.w = b.w = l.pl[p].w; a.h = b.h = l.pl[p].h;
         a.cross_blocks = (a.w + kThreads * NC - 1) / (kThreads * NC);
-        b.cross_blocks = (b.h + kThreads - 1) / kThreads;
+        b.cross_blocks = (b.h + kHRows - 1) / kHRows;
         base_v += a.cross_blocks; base_h += b.cross_blocks;
         ++k;
     }
@@ -589,7 +596,7 @@ int launch_ctf(const FrameLayout& l, const bool mask[3], const char* src, size_t
             const CtfPlane& pl = b.pl[q];
             const cuuint64_t dims[3] = {(cuuint64_t)pl.w, (cuuint64_t)pl.h, (cuuint64_t)nf};
             const cuuint64_t strides[2] = {(cuuint64_t)pl.src_pitch, (cuuint64_t)b.src_fs};
-            const cuuint32_t box[3] = {(cuuint32_t)G::TW, (cuuint32_t)kThreads, 1}, estr[3] = {1, 1, 1};
+            const cuuint32_t box[3] = {(cuuint32_t)G::TW, (cuuint32_t)kHRows, 1}, estr[3] = {1, 1, 1};
             const CUresult rc = encode(&maps.in[q], sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_UINT32 : CU_TENSOR_MAP_DATA_TYPE_UINT16, 3,
                                        const_cast<char*>(b.src) + pl.src_off, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
