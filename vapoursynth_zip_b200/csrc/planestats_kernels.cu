@@ -906,6 +906,43 @@ __global__ void __launch_bounds__(NT) minmax_bracket_kernel(const StatsJob j) {
 
     const int nvec = p.w / V;
     const int iters = (nvec + NT - 1) / NT;
+    auto flush32 = [&]() {  // the 32-bit running sums go to 64 bit
+        tot_h0 += sum_h0; tot_h1 += sum_h1;
+        sum_h0 = sum_h1 = 0u;
+        acc.idiff += idiff32; idiff32 = 0;
+        if constexpr (AVG >= 0 && !FAVG) { sum64 += s32; s32 = 0u; }
+    };
+    bool contiguous = nvec > 0 && p.a_pitch == nvec * 16;  // rows back to back (the pitch is the row: no tail samples either)
+    if constexpr (HAS_B) contiguous = contiguous && p.b_pitch == p.a_pitch;
+    if (contiguous) {
+        // the CTA's rows as one run of vectors: every thread gets the same share whatever the width (per row, 480 vectors over 256
+        // threads leave an eighth of the lanes idle in every second step)
+        const long long total = (long long)(y1 - y0) * nvec;
+        const uint4* abase = reinterpret_cast<const uint4*>(a + (size_t)y0 * p.a_pitch);
+        const uint4* bbase = HAS_B ? reinterpret_cast<const uint4*>(b + (size_t)y0 * p.b_pitch) : nullptr;
+        int step = 0;
+        for (long long i0 = 0; i0 < total; i0 += (long long)NT * G, ++step) {
+            uint4 av[G], bv[G];
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                const long long idx = i0 + (long long)g * NT + threadIdx.x;
+                if (idx < total) {
+                    av[g] = __ldg(abase + idx);
+                    if constexpr (HAS_B) bv[g] = __ldg(bbase + idx);
+                    else bv[g] = av[g];
+                }
+            }
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                if (i0 + (long long)g * NT + threadIdx.x < total) visit_vec(av[g], bv[g]);
+                if constexpr (PER_VEC) { if (__any_sync(0xffffffffu, qn >= (unsigned)QDRAIN)) drain(); }
+            }
+            if constexpr (!PER_VEC) { if (__any_sync(0xffffffffu, qn >= (unsigned)QDRAIN)) drain(); }
+            // a step adds at most G * NW * 2 * 2^FINE_KMAX to the h sums and G * V * 65535 to s32: far below 2^32 in 32 steps
+            if ((step & 31) == 31) flush32();
+        }
+        flush32();
+    } else
     for (int y = y0; y < y1; y += G) {
         for (int it = 0; it < iters; ++it) {
             const int v = it * NT + (int)threadIdx.x;
